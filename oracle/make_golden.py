@@ -1,0 +1,115 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference, CPU, fp32) on synthetic weights/inputs.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+The reference cannot travel to the GPU box, so the fixtures are committed together with
+this script.  TEST INFRASTRUCTURE ONLY (see oracle/motion_oracle.py header).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/Diffusion_Stage")
+
+from models import GaussianDiffusion, MotionTransformer  # noqa: E402  (the reference)
+from models.gaussian_diffusion import LossType, ModelMeanType, ModelVarType, get_named_beta_schedule  # noqa: E402
+from models.transformer import timestep_embedding  # noqa: E402
+
+from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+TABLE_NAMES = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+               "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+               "posterior_mean_coef1", "posterior_mean_coef2"]
+
+
+def build(num_layers, seed):
+    m = MotionTransformer(26, num_frames=1800, num_layers=num_layers, latent_dim=128, device="cpu",
+                          music_model_path=None)
+    sd = synth_state_dict(seed, num_layers=num_layers)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    m.eval()
+    return m
+
+
+def diffusion(S):
+    return GaussianDiffusion(betas=get_named_beta_schedule("linear", S), model_mean_type=ModelMeanType.START_X,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+
+
+def run_loop(m, d, noise, kw, kind, eta=0.0):
+    x0s, samples = [], []
+    gen = (d.ddim_sample_loop_progressive(m, noise.shape, noise=noise, clip_denoised=False, model_kwargs=kw, eta=eta)
+           if kind == "ddim" else
+           d.p_sample_loop_progressive(m, noise.shape, noise=noise, clip_denoised=False, model_kwargs=kw))
+    for out in gen:
+        x0s.append(out["pred_xstart"].numpy().copy())
+        samples.append(out["sample"].numpy().copy())
+    return np.stack(x0s), np.stack(samples)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+
+    # ---- (1) schedule tables, bit-exact fp64, and the fp32 values the samplers actually use
+    tabs = {}
+    for S in (25, 50, 1000):
+        d = diffusion(S)
+        for n in TABLE_NAMES:
+            tabs[f"S{S}_{n}"] = getattr(d, n)
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), **tabs)
+
+    # ---- (2) timestep embedding + time MLP for a few integer timesteps
+    m2 = build(2, seed=7)
+    t = torch.tensor([0, 1, 7, 24, 49, 500, 999])
+    with torch.no_grad():
+        temb = timestep_embedding(t, 128)
+        te = m2.time_embed(temb)
+    np.savez_compressed(os.path.join(OUT, "time_embed.npz"), t=t.numpy(), sinusoid=temb.numpy(), te=te.numpy())
+
+    # ---- (3) small masked config: 2 layers, B=3, T=40, ragged lengths, arbitrary per-sample t
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    length = [40, 33, 1]
+    tt = torch.tensor([24, 3, 0])
+    with torch.no_grad():
+        y = m2(x, tt, length=length, xf_proj=xf_proj, xf_out=xf_out)
+    d25 = diffusion(25)
+    kw = dict(xf_proj=xf_proj, xf_out=xf_out, length=length)
+    with torch.no_grad():
+        x0s, smp = run_loop(m2, d25, x, kw, "ddim")
+    torch.manual_seed(123)
+    with torch.no_grad():
+        x0s_p, smp_p = run_loop(m2, d25, x, kw, "ddpm")
+    # the DDPM noise stream the reference drew (global CPU generator, one randn_like per step)
+    torch.manual_seed(123)
+    ddpm_noise = np.stack([torch.randn_like(x).numpy() for _ in range(25)])
+    np.savez_compressed(os.path.join(OUT, "small_masked.npz"), length=np.array(length), t=tt.numpy(),
+                        forward=y.numpy(), ddim_x0=x0s, ddim_sample=smp, ddpm_x0=x0s_p, ddpm_sample=smp_p,
+                        ddpm_noise=ddpm_noise)
+
+    # ---- (4) C1: 8 layers, B=1, T=180, S=25, through the music encoder (BASELINE.json configs[0])
+    m8 = build(8, seed=0)
+    mel, noise = synth_inputs(1, 180, seed=0)
+    with torch.no_grad():
+        xp, xo = m8.encode_music(mel, "cpu")
+        kw = dict(xf_proj=xp, xf_out=xo, length=[180])
+        x0s, smp = run_loop(m8, d25, noise, kw, "ddim")
+    np.savez_compressed(os.path.join(OUT, "c1.npz"), xf_proj=xp.numpy(), xf_out=xo.numpy(), ddim_x0=x0s,
+                        final=smp[-1])
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

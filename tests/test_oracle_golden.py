@@ -1,0 +1,86 @@
+"""The oracle restatement must reproduce what the unmodified reference produced
+(fixtures written by oracle/make_golden.py in the build container)."""
+import os
+
+import numpy as np
+import torch
+
+from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict
+from oracle import motion_oracle as O
+
+TABLE_NAMES = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+               "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+               "posterior_mean_coef1", "posterior_mean_coef2"]
+
+
+def test_tables_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tables.npz"))
+    for S in (25, 50, 1000):
+        tb = O.Tables(O.linear_betas(S))
+        for n in TABLE_NAMES:
+            a, b = getattr(tb, n), g[f"S{S}_{n}"]
+            assert a.dtype == np.float64 and np.array_equal(a.view(np.uint64), b.view(np.uint64)), (S, n)
+
+
+def test_time_embedding(golden_dir):
+    g = np.load(os.path.join(golden_dir, "time_embed.npz"))
+    sd = synth_state_dict(7, num_layers=2)
+    t = torch.from_numpy(g["t"])
+    s = O.timestep_embedding(t, 128)
+    assert np.array_equal(s.numpy(), g["sinusoid"])          # bit-exact: same ops, same order
+    te = O._lin(sd, "time_embed.2", torch.nn.functional.silu(O._lin(sd, "time_embed.0", s)))
+    np.testing.assert_allclose(te.numpy(), g["te"], rtol=0, atol=1e-6)
+
+
+def test_small_masked_forward_and_loops(golden_dir):
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    sd = synth_state_dict(7, num_layers=2)
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    length = [int(v) for v in g["length"]]
+    with torch.no_grad():
+        y = O.motion_transformer_forward(sd, x, torch.from_numpy(g["t"]), length, xf_proj, xf_out)
+    np.testing.assert_allclose(y.numpy(), g["forward"], rtol=0, atol=2e-6)
+    tb = O.Tables(O.linear_betas(25))
+    final, x0s, smp = O.sample_loop(sd, tb, x, length, xf_proj, xf_out, kind="ddim")
+    np.testing.assert_allclose(torch.stack(x0s).numpy(), g["ddim_x0"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(torch.stack(smp).numpy(), g["ddim_sample"], rtol=0, atol=2e-5)
+    # last DDIM step: alpha_bar_prev == 1 -> sample == pred_xstart bit for bit
+    assert np.array_equal(smp[-1].numpy(), x0s[-1].numpy())
+    final, x0s, smp = O.sample_loop(sd, tb, x, length, xf_proj, xf_out, kind="ddpm",
+                                    step_noise=torch.from_numpy(g["ddpm_noise"]))
+    np.testing.assert_allclose(torch.stack(smp).numpy(), g["ddpm_sample"], rtol=0, atol=5e-5)
+
+
+def test_update_rules_bit_exact_given_x0(golden_dir):
+    """Index handling and coefficient arithmetic are bit-exact when fed the reference's own x0."""
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    _, x = synth_inputs(3, 40, seed=11)
+    tb = O.Tables(O.linear_betas(25))
+    img = x
+    for n, i in enumerate(range(24, -1, -1)):
+        t = torch.tensor([i] * 3)
+        img = O.ddim_update(tb, img, t, torch.from_numpy(g["ddim_x0"][n]))
+        assert np.array_equal(img.numpy(), g["ddim_sample"][n]), i
+        img = torch.from_numpy(g["ddim_sample"][n])
+    img = x
+    for n, i in enumerate(range(24, -1, -1)):
+        t = torch.tensor([i] * 3)
+        out = O.ddpm_update(tb, img, t, torch.from_numpy(g["ddpm_x0"][n]), torch.from_numpy(g["ddpm_noise"][n]))
+        assert np.array_equal(out.numpy(), g["ddpm_sample"][n]), i
+        img = torch.from_numpy(g["ddpm_sample"][n])
+
+
+def test_c1_music_encoder_and_trajectory(golden_dir):
+    g = np.load(os.path.join(golden_dir, "c1.npz"))
+    sd = synth_state_dict(0, num_layers=8)
+    mel, noise = synth_inputs(1, 180, seed=0)
+    with torch.no_grad():
+        xp, xo = O.encode_music(sd, mel)
+    np.testing.assert_allclose(xo.numpy(), g["xf_out"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(xp.numpy(), g["xf_proj"], rtol=0, atol=2e-5)
+    tb = O.Tables(O.linear_betas(25))
+    final, x0s, _ = O.sample_loop(sd, tb, noise, [180], torch.from_numpy(g["xf_proj"]), torch.from_numpy(g["xf_out"]))
+    np.testing.assert_allclose(torch.stack(x0s).numpy(), g["ddim_x0"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(final.numpy(), g["final"], rtol=0, atol=5e-5)
