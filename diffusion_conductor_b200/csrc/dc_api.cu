@@ -1,0 +1,803 @@
+// Host side of the C ABI declared in include/dc_b200.h: weight ingestion / packing, workspaces,
+// the per-step launch schedule, CUDA-graph capture of the sampling loop.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dc_b200.h"
+#include "tile_kernels.cuh"
+
+using namespace dc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct HostTensor {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+};
+
+// byte offsets of the packed matrices inside one layer's 1 MiB slab (schedule order)
+constexpr uint32_t kOffWeSa = 0;
+constexpr uint32_t kOffWoSa = kOffWeSa + 8 * 32768;
+constexpr uint32_t kOffWeCa = kOffWoSa + 32768;
+constexpr uint32_t kOffWqCa = kOffWeCa + 8 * 32768;
+constexpr uint32_t kOffWoCa = kOffWqCa + 32768;
+constexpr uint32_t kOffWeFf = kOffWoCa + 32768;
+constexpr uint32_t kOffW1 = kOffWeFf + 8 * 32768;
+constexpr uint32_t kOffW2 = kOffW1 + 16384;
+constexpr uint32_t kOffWoFf = kOffW2 + 16384;
+constexpr uint32_t kOffWq = kOffWoFf + 32768;
+constexpr uint32_t kOffWk = kOffWq + 32768;
+constexpr uint32_t kOffWv = kOffWk + 32768;
+constexpr uint32_t kLayerSlab = kOffWv + 32768;
+static_assert(kLayerSlab == 1u << 20, "layer slab is 1 MiB");
+
+struct GraphKey {
+    int sampler = -1;
+    const void* noise = nullptr;
+    const void* tx0 = nullptr;
+    const void* tx = nullptr;
+    int steps = 0;
+    bool operator==(const GraphKey& o) const {
+        return sampler == o.sampler && noise == o.noise && tx0 == o.tx0 && tx == o.tx && steps == o.steps;
+    }
+};
+
+}  // namespace
+
+struct dc_handle {
+    dc_config cfg{};
+    bool bf16 = true;
+    bool finalized = false;
+    std::string err;
+    std::map<std::string, HostTensor> w;
+
+    // packed / derived weights (device, owned)
+    uint8_t* wbuf = nullptr;      // [L][1 MiB]
+    float* prm = nullptr;         // [L][kPrmFloats]
+    uint8_t* wkv = nullptr;       // [L][8][256 x 128 B] folded cross-attention K|V weights
+    float* bkv = nullptr;         // [L][256]
+    float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
+    float *WlinT = nullptr, *blin = nullptr;
+    float *teW0 = nullptr, *teb0 = nullptr, *teW2 = nullptr, *teb2 = nullptr, *freqs = nullptr;
+
+    // schedule
+    int S = 0;
+    float* coef = nullptr;        // [S][8]
+    float* te_table = nullptr;    // [S][512]
+    int* step_ctr = nullptr;
+
+    // workspace for the prepared condition
+    int B = 0, T = 0, M = 0, tiles = 0;
+    size_t cap_tokens = 0;
+    int cap_B = 0;
+    float* xp = nullptr;
+    uint8_t* zimg = nullptr;
+    uint8_t* aemb = nullptr;
+    float* hbuf = nullptr;
+    uint16_t* q = nullptr;
+    float* kv = nullptr;
+    float* A_sa = nullptr;
+    float* A_ca = nullptr;
+    long long* length = nullptr;
+    bool has_length = false;
+    float* te_b = nullptr;        // [B][512]
+    float* xwork = nullptr;       // [M][26]
+    float* x0work = nullptr;      // [M][26]
+    float* in_proj = nullptr;     // staging for dc_generate_host
+    float* in_out = nullptr;
+    bool prepared = false;
+
+    // graphs
+    bool use_graphs = true;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    GraphKey gkey;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(dc_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (h) h->err = buf;
+    return code;
+}
+
+#define DC_CUDA(h, expr)                                                                                          \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) return fail(h, DC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                                   \
+    } while (0)
+
+uint16_t to16(float f, bool bf16) {
+    if (bf16) {
+        __nv_bfloat16 b = __float2bfloat16_rn(f);
+        uint16_t u;
+        memcpy(&u, &b, 2);
+        return u;
+    }
+    __half hh = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &hh, 2);
+    return u;
+}
+
+// fp32 [*, ldw] -> K-major SW128 image at dst (bytes), Kblocks blocks of Nrows x 128 B
+void pack_image(uint8_t* dst, const float* W, int ldw, int Ksrc, const int* rowmap, const float* colscale, int Nrows,
+                int Kblocks, bool bf16) {
+    for (int n = 0; n < Nrows; ++n) {
+        const int src = rowmap ? rowmap[n] : n;
+        for (int k = 0; k < Kblocks * 64; ++k) {
+            float v = 0.f;
+            if (src >= 0 && k < Ksrc) {
+                v = W[(size_t)src * ldw + k];
+                if (colscale) v *= colscale[k];
+            }
+            const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+            const size_t off = (size_t)kb * Nrows * 128 + sw128_offset((uint32_t)n, (uint32_t)c) + e * 2;
+            const uint16_t u = to16(v, bf16);
+            memcpy(dst + off, &u, 2);
+        }
+    }
+}
+
+template <class T>
+int upload(dc_handle* h, T** dptr, const void* src, size_t bytes) {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    DC_CUDA(h, cudaMalloc((void**)dptr, bytes));
+    DC_CUDA(h, cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+const HostTensor* get(dc_handle* h, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = h->w.find(key);
+    if (it == h->w.end()) {
+        fail(h, DC_ERR_INVALID, "missing weight '%s'", key.c_str());
+        return nullptr;
+    }
+    std::vector<int64_t> want(shape);
+    if (it->second.shape != want) {
+        std::string got;
+        for (auto d : it->second.shape) got += std::to_string(d) + ",";
+        fail(h, DC_ERR_INVALID, "weight '%s' has shape [%s] (unexpected)", key.c_str(), got.c_str());
+        return nullptr;
+    }
+    return &it->second;
+}
+
+TileOp make_op(uint32_t w_off, uint32_t stage_bytes, int n_stages, int kb_per_stage, int n, uint32_t d_col, bool ring, bool acc,
+               bool wait_a, int commit) {
+    TileOp o{};
+    o.w_off = w_off;
+    o.w_stage_bytes = stage_bytes;
+    o.n_stages = (uint16_t)n_stages;
+    o.kb_per_stage = (uint16_t)kb_per_stage;
+    o.n = (uint16_t)n;
+    o.d_col = (uint16_t)d_col;
+    o.a_from_ring = ring;
+    o.accumulate = acc;
+    o.wait_a = wait_a;
+    o.commit = (uint8_t)commit;
+    return o;
+}
+
+void free_workspace(dc_handle* h) {
+    void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q, h->kv, h->A_sa, h->A_ca, h->length,
+                    h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    h->xp = nullptr, h->zimg = nullptr, h->aemb = nullptr, h->hbuf = nullptr, h->q = nullptr, h->kv = nullptr;
+    h->A_sa = nullptr, h->A_ca = nullptr, h->length = nullptr, h->te_b = nullptr, h->xwork = nullptr, h->x0work = nullptr;
+    h->in_proj = nullptr, h->in_out = nullptr;
+    h->cap_tokens = 0, h->cap_B = 0;
+}
+
+void drop_graph(dc_handle* h) {
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    h->gexec = nullptr;
+    h->gkey = GraphKey{};
+}
+
+int ensure_workspace(dc_handle* h, int B, int T) {
+    const size_t M = (size_t)B * T;
+    const size_t tiles = (M + kTileRows - 1) / kTileRows;
+    if (M <= h->cap_tokens && B <= h->cap_B) return 0;
+    drop_graph(h);
+    free_workspace(h);
+    const size_t Mpad = tiles * kTileRows;
+    const int L = h->cfg.num_layers;
+    DC_CUDA(h, cudaMalloc((void**)&h->xp, Mpad * kE * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->zimg, tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMalloc((void**)&h->aemb, tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMalloc((void**)&h->hbuf, Mpad * kD * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->q, Mpad * kD * 2));
+    DC_CUDA(h, cudaMalloc((void**)&h->kv, Mpad * 256 * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->A_sa, (size_t)B * kH * 256 * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->A_ca, (size_t)B * L * kH * 256 * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
+    DC_CUDA(h, cudaMalloc((void**)&h->te_b, (size_t)B * kE * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->xwork, Mpad * kP * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->x0work, Mpad * kP * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->in_proj, M * kMusic * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->in_out, M * kMusic * 4));
+    // padded rows of the operand images must hold finite values
+    DC_CUDA(h, cudaMemset(h->zimg, 0, tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMemset(h->aemb, 0, tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMemset(h->q, 0, Mpad * kD * 2));
+    h->cap_tokens = M;
+    h->cap_B = B;
+    return 0;
+}
+
+int init_kernel_attrs(dc_handle* h) {
+    DC_CUDA(h, cudaFuncSetAttribute(gemm_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(gemm_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    return 0;
+}
+
+template <bool kBf16>
+int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream_t st) {
+    gemm_rows_kernel<kBf16><<<tiles, kTileThreads, kGemmSmemBytes, st>>>(ga);
+    return 0;
+}
+
+template <bool kBf16>
+int launch_layer(dc_handle* h, const LayerArgs& la, int tiles, cudaStream_t st) {
+    layer_kernel<kBf16><<<tiles, kTileThreads, kLayerSmemBytes, st>>>(la);
+    return 0;
+}
+
+// Build the launch arguments of the tile kernel that finishes layer `l` (l = -1: only the q/k/v
+// head of layer 0) and starts layer l+1.
+LayerArgs layer_args(dc_handle* h, int l) {
+    const int L = h->cfg.num_layers;
+    LayerArgs a{};
+    a.do_main = l >= 0;
+    a.do_sa1 = l + 1 < L;
+    int n = 0;
+    if (a.do_main) {
+        const uint32_t base = (uint32_t)l * kLayerSlab;
+        a.ops[n++] = make_op(base + kOffWeSa, 32768, 8, 1, 256, kColS, true, false, false, 0);
+        a.ops[n++] = make_op(base + kOffWoSa, 32768, 1, 2, 128, kColH, false, true, true, 1);
+        a.ops[n++] = make_op(base + kOffWeCa, 32768, 8, 1, 256, kColS, true, false, false, 0);
+        a.ops[n++] = make_op(base + kOffWqCa, 32768, 1, 2, 128, kColW, false, false, true, 2);
+        a.ops[n++] = make_op(base + kOffWoCa, 32768, 1, 2, 128, kColH, false, true, true, 1);
+        a.ops[n++] = make_op(base + kOffWeFf, 32768, 8, 1, 256, kColS, true, false, false, 0);
+        a.ops[n++] = make_op(base + kOffW1, 16384, 1, 2, 64, kColW, false, false, true, 2);
+        a.ops[n++] = make_op(base + kOffW2, 16384, 1, 1, 128, kColW, false, false, true, 2);
+        a.ops[n++] = make_op(base + kOffWoFf, 32768, 1, 2, 128, kColH, false, true, true, 1);
+    }
+    if (a.do_sa1) {
+        const uint32_t base = (uint32_t)(l + 1) * kLayerSlab;
+        a.ops[n++] = make_op(base + kOffWq, 32768, 1, 2, 128, kColS, false, false, true, 255);
+        a.ops[n++] = make_op(base + kOffWk, 32768, 1, 2, 128, kColS + 128, false, false, false, 255);
+        a.ops[n++] = make_op(base + kOffWv, 32768, 1, 2, 128, kColW, false, false, false, 2);
+    }
+    a.n_ops = n;
+    a.M = h->M;
+    a.T = h->T;
+    a.wbuf = h->wbuf;
+    a.aemb = h->aemb;
+    a.prm = h->prm + (size_t)(l >= 0 ? l : 0) * kPrmFloats;
+    a.prm_next = h->prm + (size_t)(l + 1 < L ? l + 1 : 0) * kPrmFloats;
+    a.h = h->hbuf;
+    a.q = h->q;
+    a.kv = h->kv;
+    a.A_sa = h->A_sa;
+    a.A_ca = h->A_ca + (size_t)(l >= 0 ? l : 0) * kH * 256;
+    a.a_ca_stride = L * kH * 256;
+    a.length = h->has_length ? h->length : nullptr;
+    return a;
+}
+
+// One denoise step: A_emb + h0, L+1 tile launches with the time-axis reductions in between, output
+// head (+ sampler update).  te/te_stride select the per-sample or per-step time embedding.
+int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride, bool te_from_ctr, int mode, float* x_upd,
+                 float* x0_out, const float* noise, size_t noise_stride, size_t trace_stride, float* trace_x, cudaStream_t st) {
+    const int L = h->cfg.num_layers;
+    const int M = h->M;
+    const int blocks8 = (M + 7) / 8;
+    if (h->bf16)
+        step_begin_kernel<true><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
+                                                         h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
+    else
+        step_begin_kernel<false><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
+                                                          h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
+    h->launches++;
+    for (int l = -1; l < L; ++l) {
+        const LayerArgs la = layer_args(h, l);
+        const int rc = h->bf16 ? launch_layer<true>(h, la, h->tiles, st) : launch_layer<false>(h, la, h->tiles, st);
+        if (rc) return rc;
+        h->launches++;
+        if (l + 1 < L) {
+            kv_reduce_kernel<<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->A_sa, kH * 256);
+            h->launches++;
+        }
+    }
+    out_update_kernel<<<blocks8, 256, 0, st>>>(h->hbuf, h->WoT, h->bo, M, mode, h->coef, h->step_ctr, noise, x_upd, x0_out);
+    h->launches++;
+    (void)noise_stride, (void)trace_stride, (void)trace_x;
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* dc_last_error(const dc_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int dc_create(const dc_config* cfg, dc_handle** out) {
+    if (!cfg || !out) return fail(nullptr, DC_ERR_INVALID, "dc_create: null argument");
+    *out = nullptr;
+    if (cfg->latent_dim != kD || cfg->num_heads != kH || cfg->ff_size != kF || cfg->input_feats != kP)
+        return fail(nullptr, DC_ERR_UNSUPPORTED,
+                    "dc_create: kernels are specialised for latent_dim=128, num_heads=8, ff_size=64, input_feats=26 "
+                    "(got %d, %d, %d, %d)",
+                    cfg->latent_dim, cfg->num_heads, cfg->ff_size, cfg->input_feats);
+    if (cfg->num_layers < 1 || cfg->num_frames < 1) return fail(nullptr, DC_ERR_INVALID, "dc_create: bad num_layers / num_frames");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, DC_ERR_CUDA, "dc_create: CUDA device %d unavailable (%s); there is no CPU fallback", cfg->device,
+                    e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) return fail(nullptr, DC_ERR_UNSUPPORTED, "dc_create: device is sm_%d%d, this library is sm_100a only", prop.major, prop.minor);
+    dc_handle* h = new dc_handle();
+    h->cfg = *cfg;
+    h->bf16 = cfg->operand != DC_OPERAND_FP16;
+    DC_CUDA(h, cudaSetDevice(cfg->device));
+    if (int rc = init_kernel_attrs(h)) return rc;
+    DC_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    DC_CUDA(h, cudaMalloc((void**)&h->step_ctr, 4));
+    DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
+    const char* ng = getenv("DC_NO_GRAPH");
+    if (ng && ng[0] == '1') h->use_graphs = false;
+    *out = h;
+    return 0;
+}
+
+void dc_destroy(dc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    drop_graph(h);
+    free_workspace(h);
+    void* ptrs[] = {h->wbuf, h->prm, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
+                    h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    delete h;
+}
+
+int dc_set_weight(dc_handle* h, const char* key, const void* data, const int64_t* shape, int ndim) {
+    if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, DC_ERR_INVALID, "dc_set_weight: bad argument");
+    const std::string k(key);
+    if (k.rfind("music_encoder.", 0) == 0 || k.rfind("proj.", 0) == 0) return 0;   // not on the denoise path
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        n *= (size_t)shape[i];
+    }
+    t.v.resize(n);
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    DC_CUDA(h, cudaMemcpy(t.v.data(), data, n * 4, cudaMemcpyDefault));
+    h->w[k] = std::move(t);
+    h->finalized = false;
+    return 0;
+}
+
+int dc_finalize_weights(dc_handle* h) {
+    if (!h) return fail(h, DC_ERR_INVALID, "null handle");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int L = h->cfg.num_layers;
+    const bool bf = h->bf16;
+#define GET(var, key, ...)                          \
+    const HostTensor* var = get(h, key, {__VA_ARGS__}); \
+    if (!var) return DC_ERR_INVALID;
+
+    std::vector<uint8_t> wbuf((size_t)L * kLayerSlab, 0);
+    std::vector<float> prm((size_t)L * kPrmFloats, 0.f);
+    std::vector<uint8_t> wkv((size_t)L * 8 * 32768, 0);
+    std::vector<float> bkv((size_t)L * 256, 0.f);
+
+    int film_rows[256];   // accumulator column n <- emb_layers.1 row: [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]
+    for (int n = 0; n < 256; ++n) film_rows[n] = n < 64 ? n : n < 128 ? n + 64 : n < 192 ? n - 64 : n;
+
+    auto fold_bias = [](const HostTensor* W, const HostTensor* b, const HostTensor* beta, float* out) {
+        const int N = (int)W->shape[0], K = (int)W->shape[1];
+        for (int n = 0; n < N; ++n) {
+            double acc = 0.0;
+            for (int k = 0; k < K; ++k) acc += (double)W->v[(size_t)n * K + k] * beta->v[k];
+            out[n] = b->v[n] + (float)acc;
+        }
+    };
+
+    for (int l = 0; l < L; ++l) {
+        const std::string p = "temporal_decoder_blocks." + std::to_string(l) + ".";
+        uint8_t* slab = wbuf.data() + (size_t)l * kLayerSlab;
+        float* pr = prm.data() + (size_t)l * kPrmFloats;
+
+        auto stylization = [&](const std::string& sp, uint32_t off_we, uint32_t off_wo, int prm_off) -> int {
+            GET(we, sp + "emb_layers.1.weight", 2 * kD, kE);
+            GET(be, sp + "emb_layers.1.bias", 2 * kD);
+            GET(g, sp + "norm.weight", kD);
+            GET(bt, sp + "norm.bias", kD);
+            GET(wo, sp + "out_layers.2.weight", kD, kD);
+            GET(bo, sp + "out_layers.2.bias", kD);
+            pack_image(slab + off_we, we->v.data(), kE, kE, film_rows, nullptr, 256, 8, bf);
+            pack_image(slab + off_wo, wo->v.data(), kD, kD, nullptr, nullptr, kD, 2, bf);
+            for (int n = 0; n < 256; ++n) pr[prm_off + kStBe + n] = be->v[film_rows[n]] + (film_rows[n] < kD ? 1.f : 0.f);
+            for (int i = 0; i < kD; ++i) {
+                pr[prm_off + kStG + i] = g->v[i];
+                pr[prm_off + kStB + i] = bt->v[i];
+                pr[prm_off + kStBo + i] = bo->v[i];
+            }
+            return 0;
+        };
+
+        // self-attention: LayerNorm affine folded into q/k/v
+        {
+            GET(g, p + "sa_block.norm.weight", kD);
+            GET(bt, p + "sa_block.norm.bias", kD);
+            const char* names[3] = {"query", "key", "value"};
+            const uint32_t offs[3] = {kOffWq, kOffWk, kOffWv};
+            const int poffs[3] = {kPrmSaBq, kPrmSaBk, kPrmSaBv};
+            for (int i = 0; i < 3; ++i) {
+                GET(W, p + "sa_block." + names[i] + ".weight", kD, kD);
+                GET(b, p + "sa_block." + names[i] + ".bias", kD);
+                pack_image(slab + offs[i], W->v.data(), kD, kD, nullptr, g->v.data(), kD, 2, bf);
+                fold_bias(W, b, bt, pr + poffs[i]);
+            }
+            if (stylization(p + "sa_block.proj_out.", kOffWeSa, kOffWoSa, kPrmStSa)) return DC_ERR_INVALID;
+        }
+        // cross-attention: query side per step, key/value side step-invariant (text_norm folded)
+        {
+            GET(g, p + "ca_block.norm.weight", kD);
+            GET(bt, p + "ca_block.norm.bias", kD);
+            GET(Wq, p + "ca_block.query.weight", kD, kD);
+            GET(bq, p + "ca_block.query.bias", kD);
+            pack_image(slab + kOffWqCa, Wq->v.data(), kD, kD, nullptr, g->v.data(), kD, 2, bf);
+            fold_bias(Wq, bq, bt, pr + kPrmCaBq);
+            GET(tg, p + "ca_block.text_norm.weight", kE);
+            GET(tb, p + "ca_block.text_norm.bias", kE);
+            GET(Wk, p + "ca_block.key.weight", kD, kE);
+            GET(bk, p + "ca_block.key.bias", kD);
+            GET(Wv, p + "ca_block.value.weight", kD, kE);
+            GET(bv, p + "ca_block.value.bias", kD);
+            std::vector<float> Wcat((size_t)256 * kE);
+            memcpy(Wcat.data(), Wk->v.data(), (size_t)kD * kE * 4);
+            memcpy(Wcat.data() + (size_t)kD * kE, Wv->v.data(), (size_t)kD * kE * 4);
+            pack_image(wkv.data() + (size_t)l * 8 * 32768, Wcat.data(), kE, kE, nullptr, tg->v.data(), 256, 8, bf);
+            fold_bias(Wk, bk, tb, bkv.data() + (size_t)l * 256);
+            fold_bias(Wv, bv, tb, bkv.data() + (size_t)l * 256 + kD);
+            if (stylization(p + "ca_block.proj_out.", kOffWeCa, kOffWoCa, kPrmStCa)) return DC_ERR_INVALID;
+        }
+        // FFN
+        {
+            GET(W1, p + "ffn.linear1.weight", kF, kD);
+            GET(b1, p + "ffn.linear1.bias", kF);
+            GET(W2, p + "ffn.linear2.weight", kD, kF);
+            GET(b2, p + "ffn.linear2.bias", kD);
+            pack_image(slab + kOffW1, W1->v.data(), kD, kD, nullptr, nullptr, kF, 2, bf);
+            pack_image(slab + kOffW2, W2->v.data(), kF, kF, nullptr, nullptr, kD, 1, bf);
+            for (int i = 0; i < kF; ++i) pr[kPrmFfB1 + i] = b1->v[i];
+            for (int i = 0; i < kD; ++i) pr[kPrmFfB2 + i] = b2->v[i];
+            if (stylization(p + "ffn.proj_out.", kOffWeFf, kOffWoFf, kPrmStFf)) return DC_ERR_INVALID;
+        }
+    }
+    if (upload(h, &h->wbuf, wbuf.data(), wbuf.size())) return DC_ERR_CUDA;
+    if (upload(h, &h->prm, prm.data(), prm.size() * 4)) return DC_ERR_CUDA;
+    if (upload(h, &h->wkv, wkv.data(), wkv.size())) return DC_ERR_CUDA;
+    if (upload(h, &h->bkv, bkv.data(), bkv.size() * 4)) return DC_ERR_CUDA;
+
+    // embeddings, output head, conditioning projection, time MLP
+    {
+        GET(Wj, "joint_embed.weight", kD, kP);
+        GET(bj, "joint_embed.bias", kD);
+        GET(pos, "sequence_embedding", h->cfg.num_frames, kD);
+        GET(Wo, "out.weight", kP, kD);
+        GET(bo, "out.bias", kP);
+        GET(Wl, "linear.weight", kE, kMusic);
+        GET(bl, "linear.bias", kE);
+        GET(W0, "time_embed.0.weight", kE, kD);
+        GET(b0, "time_embed.0.bias", kE);
+        GET(W2, "time_embed.2.weight", kE, kE);
+        GET(b2, "time_embed.2.bias", kE);
+        std::vector<float> WjT((size_t)kP * kD), WoT((size_t)kD * 32, 0.f), WlT((size_t)kMusic * kE), bo32(32, 0.f);
+        for (int j = 0; j < kD; ++j)
+            for (int c = 0; c < kP; ++c) WjT[(size_t)c * kD + j] = Wj->v[(size_t)j * kP + c];
+        for (int pI = 0; pI < kP; ++pI)
+            for (int j = 0; j < kD; ++j) WoT[(size_t)j * 32 + pI] = Wo->v[(size_t)pI * kD + j];
+        for (int pI = 0; pI < kP; ++pI) bo32[pI] = bo->v[pI];
+        for (int e = 0; e < kE; ++e)
+            for (int c = 0; c < kMusic; ++c) WlT[(size_t)c * kE + e] = Wl->v[(size_t)e * kMusic + c];
+        std::vector<float> freqs(kD / 2);
+        auto itf = h->w.find("aux.timestep_freqs");
+        if (itf != h->w.end() && itf->second.v.size() == (size_t)kD / 2) {
+            freqs = itf->second.v;
+        } else {
+            const float nl = -logf(10000.f);
+            for (int i = 0; i < kD / 2; ++i) freqs[i] = expf(nl * (float)i / (float)(kD / 2));
+        }
+        if (upload(h, &h->WjT, WjT.data(), WjT.size() * 4) || upload(h, &h->bj, bj->v.data(), kD * 4) ||
+            upload(h, &h->pos, pos->v.data(), pos->v.size() * 4) || upload(h, &h->WoT, WoT.data(), WoT.size() * 4) ||
+            upload(h, &h->bo, bo32.data(), 32 * 4) || upload(h, &h->WlinT, WlT.data(), WlT.size() * 4) ||
+            upload(h, &h->blin, bl->v.data(), kE * 4) || upload(h, &h->teW0, W0->v.data(), W0->v.size() * 4) ||
+            upload(h, &h->teb0, b0->v.data(), kE * 4) || upload(h, &h->teW2, W2->v.data(), W2->v.size() * 4) ||
+            upload(h, &h->teb2, b2->v.data(), kE * 4) || upload(h, &h->freqs, freqs.data(), freqs.size() * 4))
+            return DC_ERR_CUDA;
+    }
+#undef GET
+    h->finalized = true;
+    h->prepared = false;
+    drop_graph(h);
+    // a re-finalize after a schedule was set must refresh the time-embedding table
+    if (h->S > 0) {
+        time_embed_kernel<<<h->S, kE>>>(nullptr, 0, h->freqs, h->teW0, h->teb0, h->teW2, h->teb2, h->te_table);
+        DC_CUDA(h, cudaDeviceSynchronize());
+    }
+    return 0;
+}
+
+int dc_set_schedule(dc_handle* h, int num_steps, const float* coef) {
+    if (!h || num_steps < 1 || !coef) return fail(h, DC_ERR_INVALID, "dc_set_schedule: bad argument");
+    if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_set_schedule: call dc_finalize_weights first");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    drop_graph(h);
+    if (upload(h, &h->coef, coef, (size_t)num_steps * 8 * 4)) return DC_ERR_CUDA;
+    if (h->te_table) cudaFree(h->te_table);
+    h->te_table = nullptr;
+    DC_CUDA(h, cudaMalloc((void**)&h->te_table, (size_t)num_steps * kE * 4));
+    h->S = num_steps;
+    time_embed_kernel<<<num_steps, kE>>>(nullptr, 0, h->freqs, h->teW0, h->teb0, h->teW2, h->teb2, h->te_table);
+    h->launches++;
+    DC_CUDA(h, cudaGetLastError());
+    DC_CUDA(h, cudaDeviceSynchronize());
+    return 0;
+}
+
+int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, const int64_t* length, int B, int T, void* stream) {
+    if (!h || !xf_proj || !xf_out || B < 1 || T < 1) return fail(h, DC_ERR_INVALID, "dc_prepare_cond: bad argument");
+    if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_prepare_cond: weights not finalized");
+    if (T > h->cfg.num_frames)
+        return fail(h, DC_ERR_INVALID, "dc_prepare_cond: T=%d exceeds num_frames=%d (rows of sequence_embedding)", T, h->cfg.num_frames);
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_workspace(h, B, T)) return rc;
+    if (h->B != B || h->T != T) drop_graph(h);
+    h->B = B, h->T = T, h->M = B * T, h->tiles = (h->M + kTileRows - 1) / kTileRows;
+    bool masked = false;
+    if (length) {
+        for (int i = 0; i < B; ++i) {
+            if (length[i] < 0) return fail(h, DC_ERR_INVALID, "dc_prepare_cond: negative length");
+            masked |= length[i] < T;
+        }
+    }
+    if (masked != h->has_length) drop_graph(h);
+    h->has_length = masked;
+    if (masked) DC_CUDA(h, cudaMemcpyAsync(h->length, length, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    const int L = h->cfg.num_layers;
+    const int blocks4 = (h->M + 3) / 4;
+    if (h->bf16)
+        cond_prep_kernel<true><<<blocks4, 128, 0, st>>>(xf_proj, xf_out, h->WlinT, h->blin, h->M, h->xp, h->zimg);
+    else
+        cond_prep_kernel<false><<<blocks4, 128, 0, st>>>(xf_proj, xf_out, h->WlinT, h->blin, h->M, h->xp, h->zimg);
+    h->launches++;
+    for (int l = 0; l < L; ++l) {
+        GemmRowsArgs ga{};
+        ga.a_img = h->zimg;
+        ga.w_img = h->wkv + (size_t)l * 8 * 32768;
+        ga.bias = h->bkv + (size_t)l * 256;
+        ga.out = h->kv;
+        ga.M = h->M, ga.N = 256, ga.kblocks = 8, ga.ldo = 256;
+        const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st) : launch_gemm_rows<false>(h, ga, h->tiles, st);
+        if (rc) return rc;
+        kv_reduce_kernel<<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->A_ca + (size_t)l * kH * 256, L * kH * 256);
+        h->launches += 2;
+    }
+    DC_CUDA(h, cudaGetLastError());
+    h->prepared = true;
+    return 0;
+}
+
+int dc_forward(dc_handle* h, const float* x, const int64_t* timesteps, float* out, void* stream) {
+    if (!h || !x || !timesteps || !out) return fail(h, DC_ERR_INVALID, "dc_forward: bad argument");
+    if (!h->prepared) return fail(h, DC_ERR_STATE, "dc_forward: call dc_prepare_cond first");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    time_embed_kernel<<<h->B, kE, 0, st>>>((const long long*)timesteps, 0, h->freqs, h->teW0, h->teb0, h->teW2, h->teb2, h->te_b);
+    h->launches++;
+    return enqueue_step(h, x, h->te_b, kE, false, DC_SAMPLER_NONE, nullptr, out, nullptr, 0, 0, nullptr, st);
+}
+
+static int check_sampling(dc_handle* h, int sampler, const char* who) {
+    if (!h) return fail(h, DC_ERR_INVALID, "%s: null handle", who);
+    if ((sampler & 0xF) != DC_SAMPLER_DDIM && (sampler & 0xF) != DC_SAMPLER_DDPM)
+        return fail(h, DC_ERR_INVALID, "%s: unknown sampler %d", who, sampler);
+    if (!h->prepared) return fail(h, DC_ERR_STATE, "%s: call dc_prepare_cond first", who);
+    if (h->S < 1) return fail(h, DC_ERR_STATE, "%s: call dc_set_schedule first", who);
+    return 0;
+}
+
+int dc_sample_step(dc_handle* h, int sampler, float* x, float* pred_x0, int step, const float* noise, void* stream) {
+    if (int rc = check_sampling(h, sampler, "dc_sample_step")) return rc;
+    if (!x || !pred_x0 || step < 0 || step >= h->S) return fail(h, DC_ERR_INVALID, "dc_sample_step: bad argument (step=%d, S=%d)", step, h->S);
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, step, 0);
+    h->launches++;
+    return enqueue_step(h, x, h->te_table, 0, true, sampler, x, pred_x0, noise, 0, 0, nullptr, st);
+}
+
+int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0, int step, const float* noise, int64_t n, void* stream) {
+    if (!h || !x || !pred_x0 || n < 0) return fail(h, DC_ERR_INVALID, "dc_sampler_update: bad argument");
+    if ((sampler & 0xF) != DC_SAMPLER_DDIM && (sampler & 0xF) != DC_SAMPLER_DDPM)
+        return fail(h, DC_ERR_INVALID, "dc_sampler_update: unknown sampler");
+    if (h->S < 1 || step < 0 || step >= h->S) return fail(h, DC_ERR_STATE, "dc_sampler_update: schedule not set or step out of range");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (n == 0) return 0;
+    sampler_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred_x0, (size_t)n, sampler, h->coef, step, noise, x);
+    h->launches++;
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise, float* trace_x0, float* trace_x, void* stream) {
+    if (int rc = check_sampling(h, sampler, "dc_sample_loop")) return rc;
+    if (!x) return fail(h, DC_ERR_INVALID, "dc_sample_loop: null x");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->M * kP;
+    const int S = h->S;
+    const bool traced = trace_x0 || trace_x || step_noise;
+
+    // The loop body reads its step index from device memory, so one captured step serves all S
+    // replays; per-step noise / trace slices are addressed by plain pointer arithmetic on the host,
+    // which forces the un-captured path when they are requested.
+    DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
+    set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
+    h->launches++;
+    const int64_t per_step = 2 * (int64_t)h->cfg.num_layers + 4;
+    if (h->use_graphs && !traced) {
+        GraphKey key;
+        key.sampler = sampler;
+        key.steps = (S % 5 == 0) ? 5 : 1;
+        if (!h->gexec || !(h->gkey == key)) {
+            drop_graph(h);
+            cudaGraph_t graph = nullptr;
+            DC_CUDA(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t before = h->launches;
+            int rc = 0;
+            for (int i = 0; i < key.steps && !rc; ++i) {
+                rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, 0, 0, nullptr, h->cap_stream);
+                set_step_kernel<<<1, 1, 0, h->cap_stream>>>(h->step_ctr, 0, -1);
+            }
+            h->launches = before;
+            cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            DC_CUDA(h, ce);
+            ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            DC_CUDA(h, ce);
+            h->gkey = key;
+        }
+        for (int i = 0; i < S / key.steps; ++i) DC_CUDA(h, cudaGraphLaunch(h->gexec, st));
+        h->launches += (int64_t)S * per_step;
+    } else {
+        for (int i = 0; i < S; ++i) {
+            const float* nz = step_noise ? step_noise + (size_t)i * n : nullptr;
+            float* x0dst = trace_x0 ? trace_x0 + (size_t)i * n : h->x0work;
+            if (int rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, x0dst, nz, 0, 0, nullptr, st)) return rc;
+            if (trace_x) DC_CUDA(h, cudaMemcpyAsync(trace_x + (size_t)i * n, h->xwork, n * 4, cudaMemcpyDeviceToDevice, st));
+            set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, 0, -1);
+            h->launches++;
+        }
+    }
+    DC_CUDA(h, cudaMemcpyAsync(x, h->xwork, n * 4, cudaMemcpyDeviceToDevice, st));
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const float* xf_out, const int64_t* length, const float* noise,
+                     float* motion_out, int B, int T, void* stream) {
+    if (!h || !xf_proj || !xf_out || !noise || !motion_out || B < 1 || T < 1) return fail(h, DC_ERR_INVALID, "dc_generate_host: bad argument");
+    if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_generate_host: weights not finalized");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_workspace(h, B, T)) return rc;
+    const size_t M = (size_t)B * T;
+    DC_CUDA(h, cudaMemcpyAsync(h->in_proj, xf_proj, M * kMusic * 4, cudaMemcpyHostToDevice, st));
+    DC_CUDA(h, cudaMemcpyAsync(h->in_out, xf_out, M * kMusic * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = dc_prepare_cond(h, h->in_proj, h->in_out, length, B, T, stream)) return rc;
+    // x0work doubles as the device-side motion buffer of this call
+    float* xdev = h->x0work;
+    DC_CUDA(h, cudaMemcpyAsync(xdev, noise, M * kP * 4, cudaMemcpyHostToDevice, st));
+    // dc_sample_loop copies x -> xwork first, so aliasing x0work as the in/out buffer is safe: the
+    // final copy back happens after the last step has written its pred_xstart.
+    if (int rc = dc_sample_loop(h, sampler, xdev, nullptr, nullptr, nullptr, stream)) return rc;
+    DC_CUDA(h, cudaMemcpyAsync(motion_out, xdev, M * kP * 4, cudaMemcpyDeviceToHost, st));
+    DC_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int64_t dc_kernel_launches(const dc_handle* h) { return h ? h->launches : 0; }
+
+int dc_set_graphs(dc_handle* h, int enabled) {
+    if (!h) return fail(h, DC_ERR_INVALID, "null handle");
+    h->use_graphs = enabled != 0;
+    return 0;
+}
+
+int dc_selftest_gemm(int device, int operand, int M, int N, int K, const float* A, const float* W, const float* bias, float* out) {
+    if (!A || !W || !out || M < 1 || N < 16 || N > 256 || N % 16 || K < 64 || K % 64)
+        return fail(nullptr, DC_ERR_INVALID, "dc_selftest_gemm: need K%%64==0, N%%16==0, 16<=N<=256");
+    DC_CUDA(nullptr, cudaSetDevice(device));
+    if (int rc = init_kernel_attrs(nullptr)) return rc;
+    const bool bf = operand != DC_OPERAND_FP16;
+    const int tiles = (M + kTileRows - 1) / kTileRows, kb = K / 64;
+    std::vector<uint8_t> aimg((size_t)tiles * kb * kABlockBytes, 0), wimg((size_t)kb * N * 128, 0);
+    for (int t = 0; t < tiles; ++t) {
+        const int rows = std::min(kTileRows, M - t * kTileRows);
+        for (int b = 0; b < kb; ++b) {
+            std::vector<uint8_t> blk(kABlockBytes, 0);
+            // one k-block of one tile: reuse pack_image with a 64-wide window
+            std::vector<int> rm(kTileRows);
+            for (int r = 0; r < kTileRows; ++r) rm[r] = r < rows ? t * kTileRows + r : -1;
+            pack_image(blk.data(), A + (size_t)b * 64, K, 64, rm.data(), nullptr, kTileRows, 1, bf);
+            memcpy(aimg.data() + ((size_t)t * kb + b) * kABlockBytes, blk.data(), kABlockBytes);
+        }
+    }
+    pack_image(wimg.data(), W, K, K, nullptr, nullptr, N, kb, bf);
+    uint8_t *da = nullptr, *dw = nullptr;
+    float *db = nullptr, *dout = nullptr;
+    DC_CUDA(nullptr, cudaMalloc((void**)&da, aimg.size()));
+    DC_CUDA(nullptr, cudaMalloc((void**)&dw, wimg.size()));
+    DC_CUDA(nullptr, cudaMalloc((void**)&dout, (size_t)M * N * 4));
+    DC_CUDA(nullptr, cudaMemcpy(da, aimg.data(), aimg.size(), cudaMemcpyHostToDevice));
+    DC_CUDA(nullptr, cudaMemcpy(dw, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
+    if (bias) {
+        DC_CUDA(nullptr, cudaMalloc((void**)&db, (size_t)N * 4));
+        DC_CUDA(nullptr, cudaMemcpy(db, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+    }
+    GemmRowsArgs ga{};
+    ga.a_img = da, ga.w_img = dw, ga.bias = db, ga.out = dout, ga.M = M, ga.N = N, ga.kblocks = kb, ga.ldo = N;
+    const int rc = bf ? launch_gemm_rows<true>(nullptr, ga, tiles, 0) : launch_gemm_rows<false>(nullptr, ga, tiles, 0);
+    if (rc) return rc;
+    DC_CUDA(nullptr, cudaGetLastError());
+    DC_CUDA(nullptr, cudaDeviceSynchronize());
+    DC_CUDA(nullptr, cudaMemcpy(out, dout, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da), cudaFree(dw), cudaFree(dout);
+    if (db) cudaFree(db);
+    return 0;
+}
+
+}  // extern "C"

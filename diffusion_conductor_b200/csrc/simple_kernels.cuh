@@ -1,0 +1,364 @@
+// CUDA-core kernels of the denoise step: weight packing, timestep embedding, per-step
+// conditioning (SiLU(te + xp) as a packed A-operand image), joint embedding, the time-axis
+// softmax + K^T V reduction, the output head fused with the x0-parameterised DDIM / DDPM update.
+// All of them are HBM/L2-bound elementwise or reduction work (SURVEY.md §8(d) "HBM side").
+#pragma once
+#include "tc_common.cuh"
+
+namespace dc {
+
+constexpr int kD = 128;     // latent_dim
+constexpr int kE = 512;     // time_embed_dim == music latent dim (reference transformer.py:385,405)
+constexpr int kH = 8;       // heads
+constexpr int kHd = 16;     // head dim
+constexpr int kF = 64;      // ff_size
+constexpr int kP = 26;      // input_feats (13 joints x 2)
+constexpr int kMusic = 64;  // music-encoder feature width
+constexpr float kLnEps = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: fp32 [N_src, K_src] (torch Linear layout) -> 16-bit K-major SW128 image
+//   dst[kb][n][...] with kb = k / 64, one block = Nrows x 128 bytes.
+// rowmap (optional) permutes / pads output rows; colscale (optional) folds a LayerNorm gamma.
+// ---------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void pack_weight_kernel(const float* __restrict__ W, int ldw, int Ksrc, const int* __restrict__ rowmap,
+                                   const float* __restrict__ colscale, int Nrows, int Kblocks, uint16_t* __restrict__ dst) {
+    const int total = Nrows * Kblocks * 64;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int k = idx % (Kblocks * 64);
+        const int n = idx / (Kblocks * 64);
+        const int src = rowmap ? rowmap[n] : n;
+        float v = 0.f;
+        if (src >= 0 && k < Ksrc) {
+            v = W[(size_t)src * ldw + k];
+            if (colscale) v *= colscale[k];
+        }
+        const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+        const size_t off = (size_t)kb * Nrows * 128 + sw128_offset(n, c) + e * 2;
+        dst[off >> 1] = pack1<kBf16>(v);
+    }
+}
+
+// b'[n] = b[n] + sum_k W[n][k] * beta[k]   (LayerNorm beta folded through the following Linear)
+__global__ void fold_bias_kernel(const float* __restrict__ W, int K, const float* __restrict__ beta,
+                                 const float* __restrict__ b, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(W[(size_t)n * K + k], beta[k], acc);
+    out[n] = b[n] + acc;
+}
+
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * C) return;
+    const int r = idx / C, c = idx % C;
+    out[(size_t)c * R + r] = in[idx];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timestep embedding + time MLP (reference transformer.py:8-25, 410-414, 482):
+//   te[n] = W2 . SiLU(W0 . [cos(t f) | sin(t f)] + b0) + b2 ,  f built on the host exactly as the
+//   reference builds it (fp32 exp on CPU).  t == nullptr -> t = first_t + blockIdx.x (schedule table).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) time_embed_kernel(const long long* __restrict__ t, int first_t,
+                                                          const float* __restrict__ freqs, const float* __restrict__ W0,
+                                                          const float* __restrict__ b0, const float* __restrict__ W2,
+                                                          const float* __restrict__ b2, float* __restrict__ out) {
+    __shared__ float emb[kD];
+    __shared__ float hid[kE];
+    const int j = threadIdx.x;
+    const float tv = static_cast<float>(t ? t[blockIdx.x] : (long long)(first_t + blockIdx.x));
+    if (j < kD / 2) {
+        const float arg = __fmul_rn(tv, freqs[j]);
+        emb[j] = cosf(arg);
+        emb[j + kD / 2] = sinf(arg);
+    }
+    __syncthreads();
+    float acc = b0[j];
+    const float* w = W0 + (size_t)j * kD;
+#pragma unroll 8
+    for (int i = 0; i < kD; ++i) acc = fmaf(emb[i], w[i], acc);
+    hid[j] = acc / (1.f + expf(-acc));
+    __syncthreads();
+    acc = b2[j];
+    w = W2 + (size_t)j * kE;
+#pragma unroll 8
+    for (int i = 0; i < kE; ++i) acc = fmaf(hid[i], w[i], acc);
+    out[(size_t)blockIdx.x * kE + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning, once per batch of clips (step-invariant; reference recomputes it every step at
+// transformer.py:479-480): xp = linear(xf_proj) kept fp32; xf = linear(xf_out) is LayerNorm-
+// normalised (text_norm without its affine, which is folded into each layer's K/V weights) and
+// written as a packed 16-bit A-operand image Z[tile][kb][128 x 64].
+// One block = 4 tokens, thread j owns output features j, j+128, j+256, j+384.
+// ---------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(128) cond_prep_kernel(const float* __restrict__ xf_proj, const float* __restrict__ xf_out,
+                                                         const float* __restrict__ WlinT /*[64][512]*/,
+                                                         const float* __restrict__ blin, int M, float* __restrict__ xp,
+                                                         uint8_t* __restrict__ zimg) {
+    constexpr int TOK = 4;
+    __shared__ float in_p[TOK][kMusic], in_o[TOK][kMusic];
+    __shared__ float red[TOK][2][4];
+    const int j = threadIdx.x;
+    const long g0 = (long)blockIdx.x * TOK;
+    for (int i = j; i < TOK * kMusic; i += 128) {
+        const int tk = i / kMusic, c = i % kMusic;
+        const long g = g0 + tk;
+        in_p[tk][c] = g < M ? xf_proj[g * kMusic + c] : 0.f;
+        in_o[tk][c] = g < M ? xf_out[g * kMusic + c] : 0.f;
+    }
+    __syncthreads();
+    float ap[TOK][4], ao[TOK][4];
+#pragma unroll
+    for (int tk = 0; tk < TOK; ++tk)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ap[tk][q] = ao[tk][q] = blin[j + 128 * q];
+    for (int c = 0; c < kMusic; ++c) {
+        float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = WlinT[c * kE + j + 128 * q];
+#pragma unroll
+        for (int tk = 0; tk < TOK; ++tk)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ap[tk][q] = fmaf(in_p[tk][c], w[q], ap[tk][q]);
+                ao[tk][q] = fmaf(in_o[tk][c], w[q], ao[tk][q]);
+            }
+    }
+    // LayerNorm statistics of xf rows (two-pass: mean, then centred sum of squares)
+    const int lane = j & 31, wid = j >> 5;
+    float mean[TOK], rstd[TOK];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int tk = 0; tk < TOK; ++tk) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float d = pass ? ao[tk][q] - mean[tk] : ao[tk][q];
+                s += pass ? d * d : d;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[tk][pass][wid] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tk = 0; tk < TOK; ++tk) {
+            const float s = red[tk][pass][0] + red[tk][pass][1] + red[tk][pass][2] + red[tk][pass][3];
+            if (pass == 0) mean[tk] = s * (1.f / kE);
+            else rstd[tk] = rsqrtf(s * (1.f / kE) + kLnEps);
+        }
+    }
+#pragma unroll
+    for (int tk = 0; tk < TOK; ++tk) {
+        const long g = g0 + tk;
+        if (g >= M) continue;
+        const long tile = g >> 7;
+        const uint32_t r = (uint32_t)(g & 127);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = j + 128 * q;
+            xp[g * kE + e] = ap[tk][q];
+            const int kb = e >> 6, c = (e & 63) >> 3;
+            const size_t off = ((size_t)tile * 8 + kb) * kABlockBytes + sw128_offset(r, c) + (e & 7) * 2;
+            reinterpret_cast<uint16_t*>(zimg)[off >> 1] = pack1<kBf16>((ao[tk][q] - mean[tk]) * rstd[tk]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Start of a denoise step (reference transformer.py:482, 488-490):
+//   A_emb = SiLU(te[b] + xp[b,t])  -> packed 16-bit image  (the operand of all 24 FiLM projections;
+//           the reference re-evaluates this SiLU 24 times per step)
+//   h0    = joint_embed(x) + sequence_embedding[t]
+// One block = 8 tokens x 128 threads.  te row: te + te_row0*512 + b*te_stride (stride 0 = one
+// timestep shared by the batch, read from the device-side step counter).
+// ---------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict__ x, const float* __restrict__ xp,
+                                                          const float* __restrict__ te, const int* __restrict__ step_ctr,
+                                                          int te_stride, const float* __restrict__ WjT /*[26][128]*/,
+                                                          const float* __restrict__ bj, const float* __restrict__ pos,
+                                                          int M, int T, uint8_t* __restrict__ aemb, float* __restrict__ h) {
+    constexpr int TOK = 8;
+    __shared__ float xs[TOK][kP + 2];
+    const int j = threadIdx.x;
+    const long g0 = (long)blockIdx.x * TOK;
+    const float* te0 = te + (step_ctr ? (size_t)(*step_ctr) * kE : 0);
+    for (int i = j; i < TOK * kP; i += 128) {
+        const int tk = i / kP, c = i % kP;
+        const long g = g0 + tk;
+        xs[tk][c] = g < M ? x[g * kP + c] : 0.f;
+    }
+    // ---- A_emb: 8 tokens x 64 chunks of 8 features
+#pragma unroll
+    for (int it = 0; it < TOK * 64 / 128; ++it) {
+        const int task = it * 128 + j;
+        const int tk = task >> 6, ch = task & 63;
+        const long g = g0 + tk;
+        if (g < M) {
+            const int b = (int)(g / T);
+            const float4* xr = reinterpret_cast<const float4*>(xp + g * kE + ch * 8);
+            const float4* tr = reinterpret_cast<const float4*>(te0 + (size_t)b * te_stride + ch * 8);
+            const float4 a0 = __ldg(xr), a1 = __ldg(xr + 1), t0 = __ldg(tr), t1 = __ldg(tr + 1);
+            float v[8] = {a0.x + t0.x, a0.y + t0.y, a0.z + t0.z, a0.w + t0.w, a1.x + t1.x, a1.y + t1.y, a1.z + t1.z, a1.w + t1.w};
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float s0 = v[2 * i] / (1.f + __expf(-v[2 * i]));
+                const float s1 = v[2 * i + 1] / (1.f + __expf(-v[2 * i + 1]));
+                p[i] = pack2<kBf16>(s0, s1);
+            }
+            const long tile = g >> 7;
+            const uint32_t r = (uint32_t)(g & 127);
+            const int kb = ch >> 3, c = ch & 7;
+            uint4* dst = reinterpret_cast<uint4*>(aemb + ((size_t)tile * 8 + kb) * kABlockBytes + sw128_offset(r, c));
+            *dst = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+    }
+    __syncthreads();
+    // ---- h0
+    float acc[TOK];
+    const float bjv = bj[j];
+#pragma unroll
+    for (int tk = 0; tk < TOK; ++tk) acc[tk] = bjv;
+    for (int c = 0; c < kP; ++c) {
+        const float w = WjT[c * kD + j];
+#pragma unroll
+        for (int tk = 0; tk < TOK; ++tk) acc[tk] = fmaf(xs[tk][c], w, acc[tk]);
+    }
+#pragma unroll
+    for (int tk = 0; tk < TOK; ++tk) {
+        const long g = g0 + tk;
+        if (g < M) h[g * kD + j] = acc[tk] + pos[(size_t)(g % T) * kD + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Time-axis softmax and K^T V (reference transformer.py:111,117 / 151,155):
+//   A[b,h,d,l] = sum_t softmax_t(k[b,t,h,d]) * v[b,t,h,l]
+// kv is [M][ld] fp32 with k in columns [0,128) and v in [128,256).  One block per (clip, head),
+// 256 threads = (d,l) pairs.  Two passes over the clip's 16 key columns: max, then exp/sum/outer
+// product through shared memory.  All fp32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv, int ld, int T,
+                                                         float* __restrict__ A /*[B][8][16][16]*/, int a_stride_b) {
+    constexpr int TT = 64;
+    __shared__ float ek[TT][kHd + 1];
+    __shared__ float vv[TT][kHd + 1];
+    __shared__ float red[16][kHd + 1];
+    __shared__ float cmax[kHd];
+    const int b = blockIdx.x / kH, hh = blockIdx.x % kH;
+    const int tid = threadIdx.x;
+    const int c = tid & 15, tl = tid >> 4;
+    const float* base = kv + (size_t)b * T * ld + hh * kHd;
+    // pass 1: column max
+    float m = -INFINITY;
+    for (int t = tl; t < T; t += 16) m = fmaxf(m, base[(size_t)t * ld + c]);
+    red[tl][c] = m;
+    __syncthreads();
+    if (tid < kHd) {
+        float mm = red[0][tid];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) mm = fmaxf(mm, red[i][tid]);
+        cmax[tid] = mm;
+    }
+    __syncthreads();
+    // pass 2
+    const int d = tid >> 4, l = tid & 15;
+    float acc = 0.f, se = 0.f;
+    const float mc = cmax[c];
+    for (int t0 = 0; t0 < T; t0 += TT) {
+#pragma unroll
+        for (int i = 0; i < TT / 16; ++i) {
+            const int tt = tl + 16 * i, t = t0 + tt;
+            float e = 0.f, v = 0.f;
+            if (t < T) {
+                e = expf(base[(size_t)t * ld + c] - mc);
+                v = base[(size_t)t * ld + kD + c];
+            }
+            ek[tt][c] = e;
+            vv[tt][c] = v;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int tt = 0; tt < TT; ++tt) {
+            const float e = ek[tt][d];
+            acc = fmaf(e, vv[tt][l], acc);
+            se += e;
+        }
+        __syncthreads();
+    }
+    A[(size_t)b * a_stride_b + hh * 256 + d * 16 + l] = acc / se;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output head + sampler update (reference transformer.py:496; gaussian_diffusion.py:812-830 DDIM,
+// :426-429,:656-664 DDPM).  coef row (8 floats, built on the host from the fp64 tables exactly as
+// the reference gathers them):
+//   [0] sqrt_recip_alphas_cumprod  [1] sqrt_recipm1_alphas_cumprod  [2] sqrt(alpha_bar_prev)
+//   [3] sqrt(1 - alpha_bar_prev - sigma^2)  [4] (t!=0)*sigma
+//   [5] posterior_mean_coef1  [6] posterior_mean_coef2  [7] (t!=0)*exp(0.5*posterior_log_variance_clipped)
+// The update uses explicitly rounded mul/add/div (no FMA contraction) so that, given the same x0, it
+// is bit-identical to the reference's chain of separate torch ops.
+// mode 0: model output only; 1: DDIM; 2: DDPM; | 0x10: clamp pred_xstart to [-1, 1] first.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ddim_rule(float x, float x0, const float* cf, float nz) {
+    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(cf[0], x), x0), cf[1]);
+    const float mean = __fadd_rn(__fmul_rn(x0, cf[2]), __fmul_rn(cf[3], eps));
+    return __fadd_rn(mean, __fmul_rn(cf[4], nz));
+}
+__device__ __forceinline__ float ddpm_rule(float x, float x0, const float* cf, float nz) {
+    const float mean = __fadd_rn(__fmul_rn(cf[5], x0), __fmul_rn(cf[6], x));
+    return __fadd_rn(mean, __fmul_rn(cf[7], nz));
+}
+
+__global__ void __launch_bounds__(256) out_update_kernel(const float* __restrict__ h, const float* __restrict__ WoT /*[128][32]*/,
+                                                          const float* __restrict__ bo, int M, int mode,
+                                                          const float* __restrict__ coef, const int* __restrict__ step_ctr,
+                                                          const float* __restrict__ noise, float* __restrict__ x,
+                                                          float* __restrict__ x0_out) {
+    constexpr int TOK = 8;
+    __shared__ float hs[TOK][kD];
+    const long g0 = (long)blockIdx.x * TOK;
+    for (int i = threadIdx.x; i < TOK * kD; i += 256) {
+        const long g = g0 + i / kD;
+        hs[i / kD][i % kD] = g < M ? h[g * kD + (i % kD)] : 0.f;
+    }
+    __syncthreads();
+    const int tk = threadIdx.x >> 5, p = threadIdx.x & 31;
+    const long g = g0 + tk;
+    if (p >= kP || g >= M) return;
+    float acc = bo[p];
+#pragma unroll 16
+    for (int j = 0; j < kD; ++j) acc = fmaf(hs[tk][j], WoT[j * 32 + p], acc);
+    const size_t idx = (size_t)g * kP + p;
+    if (mode & 0x10) acc = fminf(fmaxf(acc, -1.f), 1.f);          // clip_denoised (gaussian_diffusion.py:506-507)
+    x0_out[idx] = acc;
+    if ((mode & 0xF) == 0) return;
+    const float* cf = coef + (size_t)(*step_ctr) * 8;
+    const float nz = noise ? noise[idx] : 0.f;
+    x[idx] = (mode & 0xF) == 1 ? ddim_rule(x[idx], acc, cf, nz) : ddpm_rule(x[idx], acc, cf, nz);
+}
+
+// Stand-alone sampler update on a caller-supplied x0 (bit-exactness tests; also the ddim_sample /
+// p_sample entry when the caller wants the reference's two-output dict).
+__global__ void sampler_update_kernel(const float* __restrict__ x0, size_t n, int mode, const float* __restrict__ coef, int step,
+                                      const float* __restrict__ noise, float* __restrict__ x) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* cf = coef + (size_t)step * 8;
+    const float nz = noise ? noise[i] : 0.f;
+    x[i] = (mode & 0xF) == 1 ? ddim_rule(x[i], x0[i], cf, nz) : ddpm_rule(x[i], x0[i], cf, nz);
+}
+
+__global__ void set_step_kernel(int* ctr, int value, int delta) { *ctr = delta ? *ctr + delta : value; }
+
+}  // namespace dc

@@ -1,0 +1,194 @@
+// sm_100a building blocks: mbarrier, bulk async copy (TMA unit, non-tensor form), TMEM
+// allocation / load / store, tcgen05.mma with shared-memory matrix descriptors.
+//
+// Layout convention used everywhere in this library ("K-major SW128 image"):
+//   an operand block is [rows x 64] 16-bit elements, one row = 128 bytes, rows contiguous;
+//   inside each 8-row group (1024 B) the 16-byte chunk c of row r lives at chunk c ^ (r & 7).
+//   This is exactly what tcgen05.mma expects for a K-major SWIZZLE_128B operand with
+//   SBO = 1024 B, so a block that was written to global memory in this image can be brought
+//   in with one linear cp.async.bulk -- no tensor map needed.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dc {
+
+constexpr int kTileRows = 128;            // tokens per tile == TMEM lanes
+constexpr int kBlockK = 64;               // 16-bit elements per 128-byte swizzle row
+constexpr int kABlockBytes = kTileRows * 128;   // one [128 x 64] operand block
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------- bulk async copy global -> smem
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05.mma
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, canonical value 1)
+//   bits [32,46) SBO>>4 | [46,48) version=1 (sm_100) | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
+//   [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt (0=f16, 1=bf16) | [17,23) N>>3 | [24,29) M>>4
+template <bool kBf16>
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((kBf16 ? 1u : 0u) << 7) | ((kBf16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; one elected thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// One [128 x 64] x [N x 64]^T k-block = 4 instructions of K=16 (32 bytes along the swizzled row).
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool accumulate_first) {
+    const uint64_t ad = make_desc_kmajor_sw128(a_smem);
+    const uint64_t bd = make_desc_kmajor_sw128(b_smem);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accumulate_first || k > 0) ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------- operand element type
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (kBf16) {
+        __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&p);
+    } else {
+        __half2 p = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&p);
+    }
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if constexpr (kBf16) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    } else {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint16_t pack1(float v) {
+    if constexpr (kBf16) {
+        __nv_bfloat16 p = __float2bfloat16_rn(v);
+        return *reinterpret_cast<uint16_t*>(&p);
+    } else {
+        __half p = __float2half_rn(v);
+        return *reinterpret_cast<uint16_t*>(&p);
+    }
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a [rows x 64] K-major SW128 block
+__device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+// write 16 consecutive fp32 (columns col0..col0+15 of the 128-wide row, col0 % 16 == 0) of row r
+// into the A-operand buffer made of [128 x 64] blocks.
+template <bool kBf16>
+__device__ __forceinline__ void store_a16(uint32_t a_base, uint32_t r, uint32_t col0, const float* v) {
+    const uint32_t kb = col0 >> 6, c = (col0 & 63u) >> 3;
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = pack2<kBf16>(v[2 * i], v[2 * i + 1]);
+    const uint32_t a0 = a_base + kb * kABlockBytes + sw128_offset(r, c);
+    const uint32_t a1 = a_base + kb * kABlockBytes + sw128_offset(r, c + 1);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
+}
+
+}  // namespace dc

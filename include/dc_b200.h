@@ -1,0 +1,122 @@
+/* dc_b200.h -- C ABI of the B200-native Diffusion-Conductor denoising path.
+ *
+ * The reference (viiika/Diffusion-Conductor) is pure Python and has no FFI: the boundary it
+ * exposes for this path is the call surface used by DDPMTrainer.generate_music_motion
+ * (Diffusion_Stage/trainers/ddpm_trainer.py:183-201).  Each entry point below names the reference
+ * interface it stands in for; the Python shim in diffusion_conductor_b200/ binds them with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative dc_status; the message is available from
+ *     dc_last_error(handle) (or dc_last_error(NULL) when no handle exists yet).  Nothing throws,
+ *     nothing calls exit().
+ *   - tensors are plain pointers + sizes, fp32 row-major contiguous unless stated; "dev" pointers
+ *     live on the handle's CUDA device and are BORROWED for the duration of the call only.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it.
+ *   - a handle is not thread-safe: one handle per GPU per process.
+ *   - there is no CPU fallback: without a CUDA device dc_create fails.
+ */
+#ifndef DC_B200_H
+#define DC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dc_handle dc_handle;
+
+typedef enum {
+    DC_OK = 0,
+    DC_ERR_INVALID = -1,      /* bad argument / shape / missing weight */
+    DC_ERR_UNSUPPORTED = -2,  /* configuration outside the supported fast path */
+    DC_ERR_CUDA = -3,         /* CUDA runtime error (message carries cudaGetErrorString) */
+    DC_ERR_STATE = -4         /* call order violated (e.g. sampling before dc_prepare_cond) */
+} dc_status;
+
+typedef enum { DC_OPERAND_BF16 = 0, DC_OPERAND_FP16 = 1 } dc_operand;
+typedef enum { DC_SAMPLER_NONE = 0, DC_SAMPLER_DDIM = 1, DC_SAMPLER_DDPM = 2 } dc_sampler;
+/* OR-ed into a `sampler` argument: clamp pred_xstart to [-1,1] (clip_denoised=True,
+ * gaussian_diffusion.py:503-507). */
+#define DC_FLAG_CLIP 0x10
+
+/* Mirrors the MotionTransformer constructor arguments that reach the kernels
+ * (reference Diffusion_Stage/models/transformer.py:361-374). */
+typedef struct {
+    int input_feats;   /* 26  */
+    int num_frames;    /* max sequence length (rows of sequence_embedding), e.g. 1800 */
+    int latent_dim;    /* 128 (4*latent_dim must equal 512, reference quirk Q1) */
+    int ff_size;       /* 64  */
+    int num_layers;    /* >= 1 */
+    int num_heads;     /* 8   */
+    int device;        /* CUDA ordinal */
+    int operand;       /* dc_operand: 16-bit type of the tensor-core operands (fp32 accumulate) */
+} dc_config;
+
+const char* dc_last_error(const dc_handle* h);
+
+/* MotionTransformer.__init__ (transformer.py:361-445) */
+int dc_create(const dc_config* cfg, dc_handle** out);
+void dc_destroy(dc_handle* h);
+
+/* load_state_dict (ddpm_trainer.py:303-319): one call per state_dict key; `data` may be a host or a
+ * device pointer to fp32 (copied immediately).  Keys outside the hot path (music_encoder.*, proj.*)
+ * are accepted and ignored.  "aux.timestep_freqs" [latent_dim/2] overrides the built-in frequency
+ * table of timestep_embedding (transformer.py:18-20) with the host-computed one. */
+int dc_set_weight(dc_handle* h, const char* key, const void* data, const int64_t* shape, int ndim);
+/* Folds LayerNorm affines, permutes FiLM rows, converts and packs every matrix into tcgen05
+ * operand images.  Fails listing the first missing key. */
+int dc_finalize_weights(dc_handle* h);
+
+/* GaussianDiffusion.__init__ (gaussian_diffusion.py:328-379): `coef` is a HOST array [S][8] of the
+ * fp32-rounded per-step coefficients the samplers gather (see simple_kernels.cuh for the columns);
+ * also tabulates time_embed(timestep_embedding(s)) for s in [0,S) (transformer.py:482). */
+int dc_set_schedule(dc_handle* h, int num_steps, const float* coef);
+
+/* Step-invariant half of MotionTransformer.forward (transformer.py:479-480 and the K/V side of
+ * LinearTemporalCrossAttention, :149-155): xf_proj, xf_out are DEVICE [B][T][64] (encode_music
+ * outputs); length is a HOST int64 [B] or NULL (= all T frames valid, reference quirk Q3). */
+int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, const int64_t* length, int B, int T,
+                    void* stream);
+
+/* MotionTransformer.forward(x, timesteps, ...) (transformer.py:469-497) on the prepared condition:
+ * x DEVICE [B][T][26], timesteps DEVICE int64 [B] (arbitrary per sample), out DEVICE [B][T][26]. */
+int dc_forward(dc_handle* h, const float* x, const int64_t* timesteps, float* out, void* stream);
+
+/* GaussianDiffusion.ddim_sample / p_sample for one step with t = step for the whole batch
+ * (gaussian_diffusion.py:783-831 / 605-665): x is updated in place to the sample, pred_x0 receives
+ * pred_xstart.  noise: DEVICE [B][T][26] or NULL (treated as zeros; exact when sigma == 0). */
+int dc_sample_step(dc_handle* h, int sampler, float* x, float* pred_x0, int step, const float* noise, void* stream);
+
+/* The sampler update alone on a caller-supplied pred_xstart (n elements). */
+int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0, int step, const float* noise, int64_t n,
+                      void* stream);
+
+/* GaussianDiffusion.ddim_sample_loop / p_sample_loop (gaussian_diffusion.py:871-965 / 667-781):
+ * runs steps S-1 .. 0 from x (initial noise, updated in place to the final sample), replaying a
+ * captured CUDA graph.  step_noise: DEVICE [S][B][T][26] in loop order or NULL.  trace_x0 / trace_x:
+ * DEVICE [S][B][T][26] receiving pred_xstart / sample of every step, or NULL. */
+int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise, float* trace_x0, float* trace_x,
+                   void* stream);
+
+/* generate_music_motion (ddpm_trainer.py:183-201) with HOST buffers: uploads the encode_music
+ * features and the initial noise, runs dc_prepare_cond + dc_sample_loop, downloads the motion and
+ * synchronises the stream.  Host buffers should be pinned for asynchronous copies. */
+int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const float* xf_out, const int64_t* length,
+                     const float* noise, float* motion_out, int B, int T, void* stream);
+
+/* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
+int64_t dc_kernel_launches(const dc_handle* h);
+/* 1 = replay captured CUDA graphs in dc_sample_loop (default), 0 = plain launches (profiling). */
+int dc_set_graphs(dc_handle* h, int enabled);
+
+/* Stand-alone check of the tcgen05 GEMM building block: out[M][N] = A[M][K] . W[N][K]^T + bias with
+ * A, W rounded to the 16-bit operand type; all pointers HOST.  K % 64 == 0, N % 16 == 0, N <= 256. */
+int dc_selftest_gemm(int device, int operand, int M, int N, int K, const float* A, const float* W, const float* bias,
+                     float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DC_B200_H */
