@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the DDIM denoising hot path (BASELINE.json metric: motion-seconds generated per second,
+50-step DDIM).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete 50-step DDIM sampling loop over one batch of synthetic clips (C2: 64 clips x
+6 s = 180 frames x 26 keypoint coordinates, conditioned on 64-d music features per frame).  Every rank
+generates its own batch (weak scaling, no data-path collective); for N > 1 the generated motion is
+all-gathered over NCCL inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_TOKEN_STEP = 8_500_224           # BASELINE.md §3 (algorithmic, step-invariant work excluded)
+LAYER_MAC_PER_TOKEN = 200_704 + 165_888 + 163_840
+WORKLOADS = {  # name: (B, T, S, sampler)
+    "C1": (1, 180, 25, "ddim"),
+    "C2": (64, 180, 50, "ddim"),
+    "C3": (32, 1800, 50, "ddim"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, timed on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(B, T, S, n_steps_sample, batch_sample=None):
+    """motion-s/s of the reference algorithm on this host: times `n_steps_sample` denoise steps (after one
+    warm-up step) of a `batch_sample`-clip batch with all host threads and extrapolates to the S-step loop."""
+    import torch
+
+    from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict
+    from oracle import motion_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = batch_sample or B
+    sd = synth_state_dict(0, num_layers=8)
+    xf_proj, xf_out = synth_features(Bs, T, seed=1)
+    _, noise = synth_inputs(Bs, T, seed=1)
+    tb = O.Tables(O.linear_betas(S))
+    O.sample_loop(sd, tb, noise, [T] * Bs, xf_proj, xf_out, max_steps=1)
+    t0 = time.perf_counter()
+    O.sample_loop(sd, tb, noise, [T] * Bs, xf_proj, xf_out, max_steps=n_steps_sample)
+    dt = (time.perf_counter() - t0) / n_steps_sample
+    rate = (Bs * T / 30.0) / (dt * S)
+    return rate, cores, dt, f"{n_steps_sample} denoise steps of a {Bs}x{T}-frame batch after 1 warm-up step, x{S} extrapolated"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    B, T, S, _ = WORKLOADS[args.workload]
+    vals = []
+    for _ in range(max(1, args.warmup) - 1):
+        cpu_reference_rate(B, T, S, 1)
+    for _ in range(args.steps):
+        rate, cores, dt, sample = cpu_reference_rate(B, T, S, 2)
+        vals.append((rate, dt))
+    rate = sum(v[0] for v in vals) / len(vals)
+    dt = sum(v[1] for v in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "motion-seconds generated/sec (50-step DDIM)", "value": round(rate, 3),
+        "unit": "motion-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt * S * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {S}-step DDIM, batch {B} x {T} frames (26 coords), 8-layer MotionTransformer D=128",
+                   "where": "host CPU, torch fp32, oracle port of the reference path (the reference tree itself does not travel to the GPU box)"},
+        "cpu_baseline": {"value": round(rate, 3), "unit": "motion-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(rate, 3), "unit": "motion-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--operand", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from diffusion_conductor_b200 import GaussianDiffusion, MotionTransformer, _lib
+    from diffusion_conductor_b200.gaussian_diffusion import LossType, ModelMeanType, ModelVarType, get_named_beta_schedule
+    from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    B, T, S, _ = WORKLOADS[args.workload]
+
+    model = MotionTransformer(26, num_frames=1800, num_layers=8, latent_dim=128, device=dev, music_model_path=None,
+                              operand_dtype=args.operand)
+    model.load_state_dict(synth_state_dict(0, num_layers=8), strict=True)
+    model = model.to(dev).eval()
+    diff = GaussianDiffusion(betas=get_named_beta_schedule("linear", S), model_mean_type=ModelMeanType.START_X,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+    xf_proj, xf_out = synth_features(B, T, seed=100 + rank)
+    _, noise = synth_inputs(B, T, seed=100 + rank)
+    xf_proj_d, xf_out_d, noise_d = xf_proj.to(dev), xf_out.to(dev), noise.to(dev)
+    kw = dict(xf_proj=xf_proj_d, xf_out=xf_out_d, length=[T] * B)
+    eng = model.engine(dev)
+    gathered = [torch.empty(B, T, 26, device=dev) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def one_loop():
+        out = diff.ddim_sample_loop(model, (B, T, 26), noise=noise_d, clip_denoised=False, model_kwargs=kw)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        one_loop()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evs:
+        flush.fill_(1)
+        e0.record()
+        one_loop()
+        e1.record()
+    barrier()
+    launches = eng.kernel_launches() - launches0
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    motion_seconds = world * B * T / 30.0
+    value = motion_seconds / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D features + noise, conditioning
+    # precompute, the loop, D2H of the generated motion -- every step
+    hp, ho, hn = xf_proj.pin_memory(), xf_out.pin_memory(), noise.pin_memory()
+    hout = torch.empty(B, T, 26).pin_memory()
+    flags = _lib.DC_SAMPLER_DDIM
+
+    def one_e2e():
+        eng.generate_host(flags, hp, ho, [T] * B, hn, hout, B, T)
+        if world > 1:
+            dist.all_gather(gathered, hout.to(dev, non_blocking=True))
+            torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        one_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = motion_seconds / (float(t.item()) / args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (the tcgen05 layer kernel), timed live with CUDA events
+    pk = peaks()
+    x = noise_d.clone()
+    eng.prepare(xf_proj_d, xf_out_d, [T] * B, B, T)
+    agg, cnt = {}, {}
+    reps = 5
+    for i in range(reps + 2):
+        ms, c = eng.profile_step(_lib.DC_SAMPLER_DDIM, x, S - 1 - (i % S))
+        if i >= 2:
+            for k in ms:
+                agg[k] = agg.get(k, 0.0) + ms[k] / reps
+                cnt[k] = c[k]
+    layer_ms = agg["layer"] / max(cnt["layer"], 1)
+    flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * B * T / max(cnt["layer"], 1)
+    achieved = flop_per_launch / (layer_ms * 1e-3) / 1e12
+    step_ms = sum(agg.values())
+    roofline = {"bound": "tensor", "kernel": "dc::layer_kernel", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None,
+                "peak_source": pk["source"], "launch_ms": round(layer_ms, 4), "launches_per_denoise_step": cnt["layer"],
+                "share_of_denoise_step": round(agg["layer"] / step_ms, 3),
+                "denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()},
+                "whole_loop_frac_of_peak": round(B * T * S * FLOP_PER_TOKEN_STEP / (ms_per_step / 1e3) / 1e12 / pk["bf16_tflops"], 4)}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, dt, sample = cpu_reference_rate(B, T, S, 3)
+            cpu = {"value": round(rate, 3), "unit": "motion-s/s", "cores": cores, "kind": "port", "sample": sample}
+        n_in = (hp.numel() + ho.numel() + hn.numel()) * 4
+        line = {
+            "metric": "motion-seconds generated/sec (50-step DDIM)", "value": round(value, 2), "unit": "motion-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.operand, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {S}-step DDIM, batch {B} x {T} frames (26 coords) per GPU, 8-layer "
+                                   f"MotionTransformer D=128, random-init weights, eta=0",
+                       "token_steps_per_step": B * T * S, "l2": "256 MiB buffer written between timed iterations",
+                       "collective": "NCCL all_gather of the generated motion" if world > 1 else "none"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "motion-s/s", "h2d_bytes_per_step": n_in, "d2h_bytes_per_step": hout.numel() * 4},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

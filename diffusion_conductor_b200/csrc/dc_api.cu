@@ -106,6 +106,11 @@ struct dc_handle {
     cudaGraphExec_t gexec = nullptr;
     GraphKey gkey;
     int64_t launches = 0;
+
+    // per-kernel-class event timing (dc_profile_step)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cls;
 };
 
 namespace {
@@ -319,6 +324,15 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
     const int L = h->cfg.num_layers;
     const int M = h->M;
     const int blocks8 = (M + 7) / 8;
+    auto mark = [&](int cls) {
+        if (!h->prof) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        h->prof_ev.push_back(ev);
+        h->prof_cls.push_back(cls);
+    };
+    mark(-1);
     if (h->bf16)
         step_begin_kernel<true><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
                                                          h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
@@ -326,18 +340,22 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         step_begin_kernel<false><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
                                                           h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
     h->launches++;
+    mark(0);
     for (int l = -1; l < L; ++l) {
         const LayerArgs la = layer_args(h, l);
         const int rc = h->bf16 ? launch_layer<true>(h, la, h->tiles, st) : launch_layer<false>(h, la, h->tiles, st);
         if (rc) return rc;
         h->launches++;
+        mark(1);
         if (l + 1 < L) {
             kv_reduce_kernel<<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->A_sa, kH * 256);
             h->launches++;
+            mark(2);
         }
     }
     out_update_kernel<<<blocks8, 256, 0, st>>>(h->hbuf, h->WoT, h->bo, M, mode, h->coef, h->step_ctr, noise, x_upd, x0_out);
     h->launches++;
+    mark(3);
     (void)noise_stride, (void)trace_stride, (void)trace_x;
     DC_CUDA(h, cudaGetLastError());
     return 0;
@@ -746,6 +764,34 @@ int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const floa
     if (int rc = dc_sample_loop(h, sampler, xdev, nullptr, nullptr, nullptr, stream)) return rc;
     DC_CUDA(h, cudaMemcpyAsync(motion_out, xdev, M * kP * 4, cudaMemcpyDeviceToHost, st));
     DC_CUDA(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out, int* count_out, void* stream) {
+    if (int rc = check_sampling(h, sampler, "dc_profile_step")) return rc;
+    if (!x || !ms_out || !count_out || step < 0 || step >= h->S) return fail(h, DC_ERR_INVALID, "dc_profile_step: bad argument");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, step, 0);
+    h->launches++;
+    h->prof = true;
+    h->prof_ev.clear();
+    h->prof_cls.clear();
+    const int rc = enqueue_step(h, x, h->te_table, 0, true, sampler, x, h->x0work, nullptr, 0, 0, nullptr, st);
+    h->prof = false;
+    cudaError_t e = cudaStreamSynchronize(st);
+    for (int i = 0; i < 4; ++i) ms_out[i] = 0.f, count_out[i] = 0;
+    for (size_t i = 1; i < h->prof_ev.size(); ++i) {
+        float ms = 0.f;
+        if (e == cudaSuccess) cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]);
+        const int c = h->prof_cls[i];
+        if (c >= 0 && c < 4) ms_out[c] += ms, count_out[c]++;
+    }
+    for (cudaEvent_t ev : h->prof_ev) cudaEventDestroy(ev);
+    h->prof_ev.clear();
+    h->prof_cls.clear();
+    if (rc) return rc;
+    DC_CUDA(h, e);
     return 0;
 }
 

@@ -1,0 +1,93 @@
+"""Batched, multi-GPU generation driver: the B200 counterpart of DDPMTrainer.generate_music_motion
+(reference Diffusion_Stage/trainers/ddpm_trainer.py:183-201, which handles one clip, B = 1).
+
+Clips are independent through the whole sampling loop (no cross-batch op in the reference path), so
+the batch is split contiguously across ranks, every rank runs the captured loop on its shard with no
+communication, and the generated motion is collected with ONE all_gather (NCCL over NVLink on GPUs,
+gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, stop) of rank's items; the first n_items % world ranks get one extra."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_shards(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """all_gather of per-rank shards with (possibly) unequal leading sizes -> (n_items, ...) on every rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    sizes = [shard_range(n_items, r, world) for r in range(world)]
+    cap = max(b - a for a, b in sizes)
+    pad = local.new_zeros((cap,) + tuple(local.shape[1:]))
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+
+
+def sharded_sample(sample_fn: Callable[[torch.Tensor, torch.Tensor, torch.Tensor, List[int]], torch.Tensor],
+                   xf_proj: torch.Tensor, xf_out: torch.Tensor, noise: torch.Tensor, length: Sequence[int],
+                   group=None) -> torch.Tensor:
+    """Split (xf_proj, xf_out, noise, length) along the clip dimension, run `sample_fn` on this rank's
+    shard, all_gather.  `sample_fn(xf_proj, xf_out, noise, length) -> (b, T, P)`."""
+    B = noise.shape[0]
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    a, b = shard_range(B, rank, world)
+    length = [int(v) for v in length]
+    if b > a:
+        local = sample_fn(xf_proj[a:b], xf_out[a:b], noise[a:b], length[a:b])
+    else:
+        local = noise.new_zeros((0,) + tuple(noise.shape[1:]))
+    return gather_shards(local, B, group)
+
+
+def generate_music_motion(model, diffusion, music_mel, dim_pose: int = 26, length: Optional[Sequence[int]] = None,
+                          noise: Optional[torch.Tensor] = None, sampler: str = "ddim", eta: float = 0.0,
+                          idxs: Sequence[int] = (), progress: bool = False, device=None, group=None):
+    """mel (B, 3T, 128) or (3T, 128) -> motion (B, T, dim_pose).
+
+    Mirrors ddpm_trainer.py:183-201 (encode_music, then ddim_sample_loop with clip_denoised=False and
+    model_kwargs {xf_proj, xf_out, length}) and extends it to batches, ragged `length`, and sharding over
+    the ranks of an initialised process group."""
+    if device is None:
+        device = next(model.parameters()).device
+    mel = torch.as_tensor(music_mel)
+    if mel.dim() == 2:
+        mel = mel.unsqueeze(0)
+    mel = mel.to(device=device, dtype=torch.float32)
+    B, T = mel.shape[0], mel.shape[1] // 3
+    length = [T] * B if length is None else [int(v) for v in length]
+    if noise is None:
+        noise = torch.randn(B, T, dim_pose, device=device)
+    if len(idxs) and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        raise NotImplementedError("idxs (intermediate samples) is single-process only")
+
+    def sample_fn(mel_s, _unused, noise_s, length_s):
+        with torch.no_grad():
+            xf_proj, xf_out = model.encode_music(mel_s, device)
+        kw = {"xf_proj": xf_proj, "xf_out": xf_out, "length": length_s}
+        shape = tuple(noise_s.shape)
+        if sampler == "ddim":
+            return diffusion.ddim_sample_loop(model, shape, noise=noise_s, clip_denoised=False, progress=progress,
+                                              model_kwargs=kw, eta=eta, idxs=list(idxs))
+        return diffusion.p_sample_loop(model, shape, noise=noise_s, clip_denoised=False, progress=progress,
+                                       model_kwargs=kw, idxs=list(idxs))
+
+    if len(idxs):
+        return sample_fn(mel, None, noise, length)
+    return sharded_sample(sample_fn, mel, mel, noise, length, group)

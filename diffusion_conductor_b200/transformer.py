@@ -137,9 +137,11 @@ class MusicEncoder(nn.Module):
 
     def forward(self, x):
         mel = x.unsqueeze(1).to(self.device)
-        h = self.conv3(self.conv2(self.conv1(mel)))
-        h = h.transpose(1, 2).flatten(start_dim=2).transpose(1, 2)
-        return self.conv4(h).transpose(1, 2)
+        # keep the CNN in true fp32 (no TF32 convolutions): the reference's features are fp32
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            h = self.conv3(self.conv2(self.conv1(mel)))
+            h = h.transpose(1, 2).flatten(start_dim=2).transpose(1, 2)
+            return self.conv4(h).transpose(1, 2)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -359,6 +361,14 @@ class _Engine:
                                            arr, C.c_void_p(noise.data_ptr()), C.c_void_p(out.data_ptr()), B, T, self.stream()))
         self._cond_key = None
         self.B, self.T = B, T
+
+    def profile_step(self, sampler: int, x: torch.Tensor, step: int):
+        """One denoise step with per-kernel-class event timing: ({class: ms}, {class: launches})."""
+        ms = (C.c_float * 4)()
+        cnt = (C.c_int * 4)()
+        self._ck(self.lib.dc_profile_step(self.handle, sampler, C.c_void_p(x.data_ptr()), step, ms, cnt, self.stream()))
+        names = ("step_begin", "layer", "kv_reduce", "out_update")
+        return {n: float(ms[i]) for i, n in enumerate(names)}, {n: int(cnt[i]) for i, n in enumerate(names)}
 
     def kernel_launches(self) -> int:
         return int(self.lib.dc_kernel_launches(self.handle))

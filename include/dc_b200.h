@@ -106,6 +106,12 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
 int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const float* xf_out, const int64_t* length,
                      const float* noise, float* motion_out, int B, int T, void* stream);
 
+/* Measurement aid for bench.py: runs ONE denoise step (t = step) with CUDA events between the
+ * kernels on `stream`, synchronises, and returns per kernel class the summed device time in ms and
+ * the number of launches: [0] step_begin, [1] layer (tcgen05 tile kernel), [2] kv_reduce,
+ * [3] out_update.  x is updated in place like dc_sample_step. */
+int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out, int* count_out, void* stream);
+
 /* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
 int64_t dc_kernel_launches(const dc_handle* h);
 /* 1 = replay captured CUDA graphs in dc_sample_loop (default), 0 = plain launches (profiling). */

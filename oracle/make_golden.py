@@ -56,6 +56,15 @@ def run_loop(m, d, noise, kw, kind, eta=0.0):
     return np.stack(x0s), np.stack(samples)
 
 
+def write_state_dict_layout():
+    """tests/golden/state_dict_layout.json: key -> [shape, dtype] of a fresh reference model (checkpoint contract)."""
+    import json
+    m = MotionTransformer(26, num_frames=1800, num_layers=8, latent_dim=128, device="cpu", music_model_path=None)
+    d = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    json.dump(d, open(os.path.join(OUT, "state_dict_layout.json"), "w"), indent=0)
+
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -107,6 +116,7 @@ def main():
         x0s, smp = run_loop(m8, d25, noise, kw, "ddim")
     np.savez_compressed(os.path.join(OUT, "c1.npz"), xf_proj=xp.numpy(), xf_out=xo.numpy(), ddim_x0=x0s,
                         final=smp[-1])
+    write_state_dict_layout()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,0 +1,273 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI (ctypes shim), against
+ (a) the committed golden vectors produced by the unmodified reference, and
+ (b) the CPU oracle on the same seeded inputs,
+plus size-independent properties at the BASELINE.json sizes.
+
+Tolerances (stated per operand type; fp32 accumulate everywhere, LayerNorm / softmax / update rule fp32).
+Reference floors measured on the reference itself: fp32-vs-fp64 7.5e-7; bf16 Linear layers
+7.7e-3 max-abs per step, 4.5e-3 relative RMS on the final keypoints.
+    bf16 operands: per-step pred_xstart  rel-RMS <= 8e-3,  max-abs <= 4e-2 * max(1, rms)
+    fp16 operands: per-step pred_xstart  rel-RMS <= 1.5e-3, max-abs <= 6e-3 * max(1, rms)
+    whole trajectory (final keypoints): same bounds as a single step (errors do not compound under DDIM's
+    contraction towards x0; measured 2.6e-3 / 3.3e-4 rel-RMS).
+Index handling, coefficient tables and the sampler update given x0 are bit-exact.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusion_conductor_b200 import GaussianDiffusion, MotionTransformer, _lib
+from diffusion_conductor_b200.gaussian_diffusion import LossType, ModelMeanType, ModelVarType, get_named_beta_schedule
+from diffusion_conductor_b200.generate import generate_music_motion
+from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict
+from oracle import motion_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16": dict(rel=8e-3, mx=4e-2), "fp16": dict(rel=1.5e-3, mx=6e-3)}
+
+
+def make_model(num_layers, seed, operand="bf16", num_frames=1800):
+    m = MotionTransformer(26, num_frames=num_frames, num_layers=num_layers, latent_dim=128, device="cuda",
+                          music_model_path=None, operand_dtype=operand)
+    sd = synth_state_dict(seed, num_layers=num_layers, num_frames=num_frames)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+def diffusion(S):
+    return GaussianDiffusion(betas=get_named_beta_schedule("linear", S), model_mean_type=ModelMeanType.START_X,
+                             model_var_type=ModelVarType.FIXED_SMALL, loss_type=LossType.MSE)
+
+
+def close(a, b, operand, what=""):
+    a = a.detach().float().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert np.isfinite(a).all(), what
+    rms = float(np.sqrt((b ** 2).mean()))
+    rel = float(np.sqrt(((a - b) ** 2).mean())) / max(rms, 1e-12)
+    mx = float(np.abs(a - b).max())
+    t = TOL[operand]
+    assert rel <= t["rel"], f"{what}: rel-RMS {rel:.3e} > {t['rel']:.1e}"
+    assert mx <= t["mx"] * max(1.0, rms), f"{what}: max-abs {mx:.3e} > {t['mx'] * max(1.0, rms):.1e}"
+    return rel, mx
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_is_the_native_one():
+    lib = _lib.load()
+    assert os.path.samefile(lib._name, _lib.LIB_PATH)
+
+
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+def test_tcgen05_gemm_selftest(operand):
+    """The tcgen05/TMEM GEMM building block against numpy on 16-bit-rounded inputs: only fp32 accumulation
+    order differs, so the bound is ~1e-5 relative.  Covers ragged M, N in {16..256}, K in {64..512}."""
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    dt = torch.bfloat16 if operand == "bf16" else torch.float16
+    r16 = lambda a: torch.from_numpy(a).to(dt).double().numpy()  # noqa: E731
+    for (M, N, K) in [(128, 128, 64), (128, 256, 512), (300, 64, 128), (1, 16, 64), (257, 240, 192), (1024, 256, 512)]:
+        A = rng.standard_normal((M, K), dtype=np.float32)
+        W = rng.standard_normal((N, K), dtype=np.float32) * 0.1
+        b = rng.standard_normal(N, dtype=np.float32)
+        out = np.full((M, N), np.nan, dtype=np.float32)
+        rc = lib.dc_selftest_gemm(0, 0 if operand == "bf16" else 1, M, N, K, A.ctypes.data, W.ctypes.data, b.ctypes.data,
+                                  out.ctypes.data)
+        assert rc == 0, lib.dc_last_error(None)
+        ref = r16(A) @ r16(W).T + b
+        assert np.abs(out - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (M, N, K)
+    assert lib.dc_selftest_gemm(0, 0, 8, 24, 64, A.ctypes.data, W.ctypes.data, None, out.ctypes.data) == -1
+
+
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+def test_forward_small_masked_vs_reference_golden(golden_dir, operand):
+    """forward(x, t, length, xf_proj, xf_out) with per-sample timesteps and ragged lengths (33 and 1 of 40)."""
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    m, sd = make_model(2, 7, operand)
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    length = [int(v) for v in g["length"]]
+    y = m(x.cuda(), torch.from_numpy(g["t"]).cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    assert y.shape == (B, T, 26) and y.is_cuda
+    close(y, g["forward"], operand, "forward vs reference golden")
+    # (B,T,13,2) input is flattened like the reference (quirk Q4)
+    y4 = m(x.view(B, T, 13, 2).cuda(), torch.from_numpy(g["t"]).cuda(), length=length, xf_proj=xf_proj.cuda(),
+           xf_out=xf_out.cuda())
+    assert torch.equal(y4, y)
+
+
+def test_sampler_update_bit_exact(golden_dir):
+    """DDIM / DDPM update given the reference's own pred_xstart: bit-identical samples for all 25 steps."""
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    m, _ = make_model(2, 7)
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    d = diffusion(25)
+    eng = d._bind(m, x.cuda(), dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B))
+    nz = torch.from_numpy(g["ddpm_noise"]).cuda()
+    for sampler, key in ((_lib.DC_SAMPLER_DDIM, "ddim"), (_lib.DC_SAMPLER_DDPM, "ddpm")):
+        img = x.cuda().clone()
+        for n, i in enumerate(range(24, -1, -1)):
+            eng.sampler_update(sampler, img, torch.from_numpy(g[key + "_x0"][n]).cuda(), i,
+                               nz[n] if key == "ddpm" else None)
+            assert np.array_equal(img.cpu().numpy(), g[key + "_sample"][n]), (key, i)
+            img = torch.from_numpy(g[key + "_sample"][n]).cuda()
+
+
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+def test_sampling_loops_small(golden_dir, operand):
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    m, sd = make_model(2, 7, operand)
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    length = [int(v) for v in g["length"]]
+    d = diffusion(25)
+    kw = dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=length)
+    outs = list(d.ddim_sample_loop_progressive(m, x.shape, noise=x.cuda(), clip_denoised=False, model_kwargs=kw))
+    assert len(outs) == 25 and set(outs[0]) == {"sample", "pred_xstart"}
+    for n, o in enumerate(outs):                                   # per-step tolerance on predicted x0
+        close(o["pred_xstart"], g["ddim_x0"][n], operand, f"pred_xstart step {24 - n}")
+    close(outs[-1]["sample"], g["ddim_sample"][-1], operand, "trajectory final")
+    # t = 0: alpha_bar_prev = 1 -> sample == pred_xstart bit for bit (quirk Q11)
+    assert torch.equal(outs[-1]["sample"], outs[-1]["pred_xstart"])
+    # graph-replayed whole loop == step-by-step generator, bit for bit
+    fin = d.ddim_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False, model_kwargs=kw)
+    assert torch.equal(fin, outs[-1]["sample"])
+    # idxs -> dict {i: sample after step counter i} plus {S: final} (quirk Q12)
+    tr = d.ddim_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False, model_kwargs=kw, idxs=[0, 5, 24])
+    assert sorted(tr) == [0, 5, 24, 25]
+    assert torch.equal(tr[5], outs[5]["sample"]) and torch.equal(tr[25], fin)
+    # DDPM with the reference's own noise stream
+    eng = m.engine(torch.device("cuda", 0))
+    xs = x.cuda().clone()
+    eng.sample_loop(_lib.DC_SAMPLER_DDPM, xs, step_noise=torch.from_numpy(g["ddpm_noise"]).cuda())
+    close(xs, g["ddpm_sample"][-1], operand, "ddpm final")
+    # clip_denoised=True clamps pred_xstart
+    o = d.ddim_sample(m, x.cuda(), torch.tensor([24] * B).cuda(), clip_denoised=True, model_kwargs=kw)
+    assert float(o["pred_xstart"].abs().max()) <= 1.0
+    ref = torch.from_numpy(g["ddim_x0"][0]).clamp(-1, 1)
+    close(o["pred_xstart"], ref, operand, "clipped x0")
+    # per-sample (non-uniform) timesteps through ddim_sample
+    tt = torch.from_numpy(g["t"]).cuda()
+    o = d.ddim_sample(m, x.cuda(), tt, clip_denoised=False, model_kwargs=kw)
+    close(o["pred_xstart"], g["forward"], operand, "ddim_sample non-uniform t")
+    ref = O.ddim_update(O.Tables(O.linear_betas(25)), x, torch.from_numpy(g["t"]), o["pred_xstart"].cpu())
+    assert torch.allclose(o["sample"].cpu(), ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+def test_c1_trajectory_vs_reference_golden(golden_dir, operand):
+    """BASELINE.json configs[0]: 25-step DDIM, batch 1, 6 s clip, 8 layers, through the music encoder."""
+    g = np.load(os.path.join(golden_dir, "c1.npz"))
+    m, sd = make_model(8, 0, operand)
+    mel, noise = synth_inputs(1, 180, seed=0)
+    with torch.no_grad():
+        xp, xo = m.encode_music(mel.cuda(), "cuda")
+    assert np.abs(xo.cpu().numpy() - g["xf_out"]).max() < 5e-3          # cuDNN (TF32-free fp32) vs CPU conv
+    d = diffusion(25)
+    kw = dict(xf_proj=torch.from_numpy(g["xf_proj"]).cuda(), xf_out=torch.from_numpy(g["xf_out"]).cuda(), length=[180])
+    for n, o in enumerate(d.ddim_sample_loop_progressive(m, noise.shape, noise=noise.cuda(), clip_denoised=False,
+                                                         model_kwargs=kw)):
+        close(o["pred_xstart"], g["ddim_x0"][n], operand, f"C1 pred_xstart step {24 - n}")
+    fin = d.ddim_sample_loop(m, noise.shape, noise=noise.cuda(), clip_denoised=False, model_kwargs=kw)
+    close(fin, g["final"], operand, "C1 final keypoints")
+    # generate_music_motion-equivalent driver from the mel itself
+    out = generate_music_motion(m, d, mel[0].numpy(), 26, noise=noise.cuda())
+    assert out.shape == (1, 180, 26)
+    close(out, g["final"], operand, "C1 via generate_music_motion")
+
+
+def test_oracle_agreement_mid_size_and_edge_shapes():
+    """Seeded inputs vs the CPU oracle at shapes that exercise tile boundaries: clips straddling 128-row tiles,
+    a ragged last tile, T = 1, a zero-length clip, and the maximum T = num_frames."""
+    m, sd = make_model(2, 21, "fp16", num_frames=300)
+    for (B, T, length) in [(5, 77, [77, 10, 77, 0, 76]), (1, 1, [1]), (3, 128, [128, 128, 64]), (2, 300, [300, 299])]:
+        xf_proj, xf_out = synth_features(B, T, seed=B * 1000 + T)
+        _, x = synth_inputs(B, T, seed=B * 1000 + T)
+        t = torch.arange(B) * 3 % 25
+        y = m(x.cuda(), t.cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+        with torch.no_grad():
+            ref = O.motion_transformer_forward(sd, x, t, length, xf_proj, xf_out)
+        close(y, ref, "fp16", f"forward B={B} T={T}")
+    with pytest.raises(RuntimeError):            # T beyond the positional table must fail loudly
+        xf_proj, xf_out = synth_features(1, 301, seed=1)
+        m(torch.zeros(1, 301, 26).cuda(), torch.zeros(1, dtype=torch.long).cuda(), length=[301], xf_proj=xf_proj.cuda(),
+          xf_out=xf_out.cuda())
+    with pytest.raises(ValueError):              # music frames must equal motion frames (quirk Q2)
+        m(torch.zeros(1, 10, 26).cuda(), torch.zeros(1, dtype=torch.long).cuda(), length=[10],
+          xf_proj=torch.zeros(1, 11, 64).cuda(), xf_out=torch.zeros(1, 11, 64).cuda())
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 10, 26).cuda(), torch.zeros(1, dtype=torch.long).cuda(), xf_proj=torch.zeros(1, 10, 64).cuda(),
+          xf_out=torch.zeros(1, 10, 64).cuda())
+
+
+def test_call_order_errors():
+    lib = _lib.load()
+    cfg = _lib.DcConfig(26, 64, 128, 64, 1, 8, 0, 0)
+    h = C.c_void_p()
+    assert lib.dc_create(C.byref(cfg), C.byref(h)) == 0
+    x = torch.zeros(1, 8, 26, device="cuda")
+    assert lib.dc_finalize_weights(h) == -1 and b"missing weight" in lib.dc_last_error(h)
+    assert lib.dc_sample_loop(h, 1, C.c_void_p(x.data_ptr()), None, None, None, None) == -4
+    assert lib.dc_prepare_cond(h, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), None, 1, 8, None) == -4
+    lib.dc_destroy(h)
+
+
+def test_full_size_properties_c2():
+    """BASELINE.json configs[1] size (batch 64 x 180 frames, 50-step DDIM, 8 layers): properties that hold at
+    any size -- determinism, clip independence (a clip's motion does not depend on its batch neighbours or its
+    position in the batch), permutation equivariance, final sample == final pred_xstart -- plus agreement of a
+    few clips with the oracle over the first steps."""
+    m, sd = make_model(8, 0, "bf16")
+    B, T, S = 64, 180, 50
+    xf_proj, xf_out = synth_features(B, T, seed=1)
+    _, noise = synth_inputs(B, T, seed=1)
+    d = diffusion(S)
+    kw = dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B)
+    a = d.ddim_sample_loop(m, noise.shape, noise=noise.cuda(), clip_denoised=False, model_kwargs=kw)
+    b = d.ddim_sample_loop(m, noise.shape, noise=noise.cuda(), clip_denoised=False, model_kwargs=kw)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    kwp = dict(xf_proj=xf_proj[perm].cuda(), xf_out=xf_out[perm].cuda(), length=[T] * B)
+    p = d.ddim_sample_loop(m, noise.shape, noise=noise[perm].cuda(), clip_denoised=False, model_kwargs=kwp)
+    assert torch.equal(p, a[perm.cuda()])
+    sub = [3, 17, 40]
+    kws = dict(xf_proj=xf_proj[sub].cuda(), xf_out=xf_out[sub].cuda(), length=[T] * 3)
+    s = d.ddim_sample_loop(m, (3, T, 26), noise=noise[sub].cuda(), clip_denoised=False, model_kwargs=kws)
+    assert torch.equal(s, a[sub])
+    # oracle on the 3-clip sub-batch, first 2 steps
+    _, x0s, _ = O.sample_loop(sd, O.Tables(O.linear_betas(S)), noise[sub], [T] * 3, xf_proj[sub], xf_out[sub], max_steps=2)
+    gen = d.ddim_sample_loop_progressive(m, (3, T, 26), noise=noise[sub].cuda(), clip_denoised=False, model_kwargs=kws)
+    for n in range(2):
+        close(next(gen)["pred_xstart"], x0s[n], "bf16", f"C2 sub-batch step {n}")
+
+
+def test_full_size_properties_c3_long_sequence():
+    """BASELINE.json configs[2] shape (60 s clips, 1800 frames, mel 5400x128): a 4-clip batch over 5 of the 50
+    steps against the oracle, plus masking semantics (frames >= length do not influence frames < length)."""
+    m, sd = make_model(8, 0, "bf16")
+    B, T, S = 4, 1800, 50
+    xf_proj, xf_out = synth_features(B, T, seed=2)
+    _, noise = synth_inputs(B, T, seed=2)
+    d = diffusion(S)
+    length = [1800, 1800, 1000, 1800]
+    kw = dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=length)
+    _, x0s, _ = O.sample_loop(sd, O.Tables(O.linear_betas(S)), noise, length, xf_proj, xf_out, max_steps=3)
+    gen = d.ddim_sample_loop_progressive(m, noise.shape, noise=noise.cuda(), clip_denoised=False, model_kwargs=kw)
+    for n in range(3):
+        close(next(gen)["pred_xstart"], x0s[n], "bf16", f"C3 step {n}")
+    # masked tail of clip 2: changing the noise there must not change the valid frames' prediction
+    x2 = noise.clone()
+    x2[2, 1000:] += 5.0
+    t = torch.tensor([49] * B).cuda()
+    y1 = m(noise.cuda(), t, **kw)
+    y2 = m(x2.cuda(), t, **kw)
+    assert torch.equal(y1[2, :1000], y2[2, :1000]) and torch.equal(y1[[0, 1, 3]], y2[[0, 1, 3]])

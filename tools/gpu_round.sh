@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# One GPU visit: parity tests, smoke, bench (both arms), ncu launch list + full capture of the layer kernel.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25
+echo "=== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5
+echo "=== bench ours"; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_ours.json
+echo "=== bench C3"; timeout 900 python bench.py --steps 3 --warmup 3 --workload C3 --no-cpu-baseline 2>&1 | tail -2 | tee gpurun_out/bench_c3.json
+echo "=== bench reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref.json
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+echo "=== ncu launches"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2100 -c 80 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
+tail -3 gpurun_out/ncu_launch_run.log
+echo "=== ncu full (layer kernel)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:layer_kernel -s 30 -c 2 -f -o gpurun_out/layer_full \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
+tail -3 gpurun_out/ncu_full_run.log
+ls -la gpurun_out | head -30
+fi
