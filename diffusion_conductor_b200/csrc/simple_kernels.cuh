@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv, int ld, int T,
                                                          float* __restrict__ A /*[B][8][16][16]*/, int a_stride_b) {
-    constexpr int TT = 64;
+    constexpr int TT = 128;                 // tokens per shared-memory chunk
+    constexpr int U = TT / 16;              // independent loads per thread per chunk
     __shared__ float ek[TT][kHd + 1];
     __shared__ float vv[TT][kHd + 1];
     __shared__ float red[16][kHd + 1];
@@ -258,10 +259,19 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
     const int b = blockIdx.x / kH, hh = blockIdx.x % kH;
     const int tid = threadIdx.x;
     const int c = tid & 15, tl = tid >> 4;
-    const float* base = kv + (size_t)b * T * ld + hh * kHd;
-    // pass 1: column max
+    const float* base = kv + (size_t)b * T * ld + hh * kHd + c;
+    // pass 1: column max over the clip (U independent loads in flight per thread)
     float m = -INFINITY;
-    for (int t = tl; t < T; t += 16) m = fmaxf(m, base[(size_t)t * ld + c]);
+    for (int t0 = 0; t0 < T; t0 += TT) {
+        float x[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            const int t = t0 + tl + 16 * i;
+            x[i] = t < T ? __ldg(base + (size_t)t * ld) : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) m = fmaxf(m, x[i]);
+    }
     red[tl][c] = m;
     __syncthreads();
     if (tid < kHd) {
@@ -271,25 +281,27 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
         cmax[tid] = mm;
     }
     __syncthreads();
-    // pass 2
+    // pass 2: exp, column sums and the 16x16 outer-product accumulation through shared memory
     const int d = tid >> 4, l = tid & 15;
     float acc = 0.f, se = 0.f;
     const float mc = cmax[c];
     for (int t0 = 0; t0 < T; t0 += TT) {
+        float xk[U], xv[U];
 #pragma unroll
-        for (int i = 0; i < TT / 16; ++i) {
-            const int tt = tl + 16 * i, t = t0 + tt;
-            float e = 0.f, v = 0.f;
-            if (t < T) {
-                e = expf(base[(size_t)t * ld + c] - mc);
-                v = base[(size_t)t * ld + kD + c];
-            }
-            ek[tt][c] = e;
-            vv[tt][c] = v;
+        for (int i = 0; i < U; ++i) {
+            const int t = t0 + tl + 16 * i;
+            xk[i] = t < T ? __ldg(base + (size_t)t * ld) : -INFINITY;
+            xv[i] = t < T ? __ldg(base + (size_t)t * ld + kD) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            ek[tl + 16 * i][c] = expf(xk[i] - mc);          // exp(-inf) = 0 for the padded tail
+            vv[tl + 16 * i][c] = xv[i];
         }
         __syncthreads();
-#pragma unroll 16
-        for (int tt = 0; tt < TT; ++tt) {
+        const int n = min(TT, T - t0);
+#pragma unroll 8
+        for (int tt = 0; tt < n; ++tt) {
             const float e = ek[tt][d];
             acc = fmaf(e, vv[tt][l], acc);
             se += e;

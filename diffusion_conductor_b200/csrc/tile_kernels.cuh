@@ -1,13 +1,16 @@
 // tcgen05 / TMEM tile kernels.
 //
-// One CTA owns a tile of 128 tokens (= 128 TMEM lanes).  Warp roles:
-//   warps 0-3 : "row" threads -- thread r owns token row r: reads accumulators from its TMEM lane,
-//               does every row-wise op (LayerNorm, softmax over head-dim, q.A, FiLM, SiLU, GELU)
-//               in registers, and writes the next GEMM's A operand to shared memory (K-major SW128)
-//   warp 4    : producer -- streams packed operand blocks global/L2 -> smem ring with cp.async.bulk
-//   warp 5    : MMA issuer (one elected lane) + TMEM allocator
-// Synchronisation is mbarrier-only inside the main loop: full/empty per ring stage, a_ready
-// (row threads -> MMA), d_ready per accumulator (tcgen05.commit -> row threads).
+// One CTA owns a tile of 128 tokens (= 128 TMEM lanes).  Warp roles (18 warps, 576 threads):
+//   warps 0-15 : "row" threads.  Warp w works on TMEM lanes 32*(w%4).. (rows of the tile) and on
+//                the column quarter cq = w/4 (32 of the 128 features, i.e. two attention heads).
+//                They read accumulators from TMEM, do every row-wise op (LayerNorm, softmax over
+//                head-dim, q.A, FiLM, SiLU, GELU) in registers and write the next GEMM's A operand
+//                to shared memory (K-major SW128).  The four warps that share a row exchange
+//                LayerNorm partial statistics through shared memory + a 128-thread named barrier.
+//   warp 16    : producer -- streams packed operand blocks global/L2 -> smem ring with cp.async.bulk
+//   warp 17    : MMA issuer (one elected lane) + TMEM allocator
+// Synchronisation in the main loop is mbarrier-only between roles: full/empty per ring stage,
+// a_ready (row threads -> MMA), d_ready per accumulator (tcgen05.commit -> row threads).
 #pragma once
 #include "simple_kernels.cuh"
 
@@ -18,7 +21,10 @@ constexpr int kStageABytes = kABlockBytes;        // 16 KB: one [128 x 64] A blo
 constexpr int kStageWBytes = 32 * 1024;           // up to [256 x 64] weight block, or a whole small weight
 constexpr int kStageBytes = kStageABytes + kStageWBytes;
 constexpr int kAworkBytes = 2 * kABlockBytes;     // [128 x 128] A operand written by the row threads
-constexpr int kTileThreads = 192;
+constexpr int kRowWarps = 16;
+constexpr int kRowThreads = kRowWarps * 32;       // 512
+constexpr int kProducerWarp = 16, kMmaWarp = 17;
+constexpr int kTileThreads = kRowThreads + 64;    // 576
 
 // TMEM column map (512 columns x 128 lanes x fp32)
 constexpr uint32_t kColH = 0;      // residual stream h            [128]
@@ -52,23 +58,17 @@ constexpr int kMaxOps = 12;
 // ---------------------------------------------------------------------------------------------
 // shared pieces
 // ---------------------------------------------------------------------------------------------
-struct TileSmem {
-    uint8_t* ring;
-    uint8_t* awork;
-    TileBarriers* bars;
-};
-
 __device__ __forceinline__ void tile_setup(TileBarriers* bars, int warp, int lane) {
-    if (warp == 4 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(smem_u32(&bars->full[i]), 1);
             mbar_init(smem_u32(&bars->empty[i]), 1);
         }
-        mbar_init(smem_u32(&bars->a_ready), kTileRows);
+        mbar_init(smem_u32(&bars->a_ready), kRowThreads);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
         mbar_fence_init();
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tmem_alloc(smem_u32(&bars->tmem_base), 512);
         tmem_relinquish();
     }
@@ -80,7 +80,7 @@ __device__ __forceinline__ void tile_setup(TileBarriers* bars, int warp, int lan
 __device__ __forceinline__ void tile_teardown(TileBarriers* bars, int warp) {
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(bars->tmem_base, 512);
     }
@@ -172,18 +172,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
     }
     __syncthreads();
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         if (lane == 0)
             producer_loop(&op, 1, a.w_img, a.a_img + (size_t)blockIdx.x * a.kblocks * kStageABytes, ring, bars);
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) mma_loop<kBf16>(&op, 1, ring, nullptr, bars, tmem_base);
     } else {
-        const int r = threadIdx.x;
-        const long g = (long)blockIdx.x * kTileRows + r;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int lq = warp & 3, cq = warp >> 2;
+        const long g = (long)blockIdx.x * kTileRows + lq * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
         mbar_wait(smem_u32(&bars->d_ready[0]), 0);
         tc_fence_after();
-        for (int c = 0; c < a.N; c += 16) {
+        // column quarter cq covers columns [64 cq, 64 cq + 64) in 16-column pieces
+        for (int c = 64 * cq; c < min(a.N, 64 * cq + 64); c += 16) {
             float v[16];
             tmem_ld16(trow + c, v);
             tmem_wait_ld();
@@ -240,79 +241,17 @@ struct LayerArgs {
     const long long* length;  // [B] or null (all frames valid)
 };
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+template <bool kFast>
+__device__ __forceinline__ float silu_f(float v) {
+    if constexpr (kFast) {      // x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)) : one MUFU
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v));
+        return v * fmaf(0.5f, th, 0.5f);
+    } else {
+        return __fdividef(v, 1.f + __expf(-v));
+    }
+}
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
-
-// mean / rstd of the 128 columns at `col` of this thread's TMEM lane; optionally adds a bias vector
-// first and writes the sum back (deferred bias of the preceding accumulate-GEMM).
-__device__ __forceinline__ void row_stats(uint32_t taddr, const float* bias_smem, float& mean, float& rstd) {
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v[16];
-        tmem_ld16(taddr + 16 * c, v);
-        tmem_wait_ld();
-        if (bias_smem) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += bias_smem[16 * c + i];
-            tmem_st16(taddr + 16 * c, v);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sum += v[i];
-    }
-    if (bias_smem) tmem_wait_st();
-    mean = sum * (1.f / kD);
-    float ss = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v[16];
-        tmem_ld16(taddr + 16 * c, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float d = v[i] - mean;
-            ss = fmaf(d, d, ss);
-        }
-    }
-    rstd = rsqrtf(ss * (1.f / kD) + kLnEps);
-}
-
-// A operand <- (row - mean) * rstd          (LayerNorm without affine; affine folded downstream)
-template <bool kBf16>
-__device__ __forceinline__ void row_normalize_to_a(uint32_t taddr, float mean, float rstd, uint32_t awork, uint32_t r) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v[16];
-        tmem_ld16(taddr + 16 * c, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd;
-        store_a16<kBf16>(awork, r, 16 * c, v);
-    }
-}
-
-// A operand <- SiLU( LN(y) * (1 + scale) + shift )   (reference transformer.py:77-80)
-// y in TMEM columns kColW, scale|shift accumulator in kColS laid out
-//   [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]; st = stylization params in smem.
-template <bool kBf16>
-__device__ __forceinline__ void row_film_to_a(uint32_t trow, float mean, float rstd, const float* st, uint32_t awork, uint32_t r) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int kb = c >> 2, j = (c & 3) * 16;
-        float y[16], sc[16], sh[16];
-        tmem_ld16(trow + kColW + 16 * c, y);
-        tmem_ld16(trow + kColS + kb * 128 + j, sc);
-        tmem_ld16(trow + kColS + kb * 128 + 64 + j, sh);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float n = fmaf((y[i] - mean) * rstd, st[kStG + 16 * c + i], st[kStB + 16 * c + i]);
-            const float v = fmaf(n, sc[i] + st[kStBe + kb * 128 + j + i], sh[i] + st[kStBe + kb * 128 + 64 + j + i]);
-            y[i] = silu_f(v);
-        }
-        store_a16<kBf16>(awork, r, 16 * c, y);
-    }
-}
 
 // y[16] = q[16] . A[16][16]  (A row-major [d][l] in global memory, read through L1)
 __device__ __forceinline__ void head_apply(const float* q, const float* __restrict__ Ah, float* y) {
@@ -347,6 +286,82 @@ __device__ __forceinline__ void softmax16(float* q) {
     for (int i = 0; i < 16; ++i) q[i] *= inv;
 }
 
+// Row statistics over 128 features held as 4 x 32 registers by the 4 warps that share a row:
+// local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.  `buf` alternates
+// between two exchange buffers so consecutive calls need no second barrier.
+struct RowStats {
+    float2* xchg;      // [2][4][128]
+    uint32_t bar_id;   // 1 + lq
+    uint32_t r;        // row within the tile
+    uint32_t cq;
+    uint32_t flip;
+};
+
+__device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += v[i];
+    const float lm = s * (1.f / 32.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float d = v[i] - lm;
+        m2 = fmaf(d, d, m2);
+    }
+    float2* buf = rs.xchg + rs.flip * 512;
+    rs.flip ^= 1u;
+    buf[rs.cq * 128 + rs.r] = make_float2(lm, m2);
+    named_bar_sync(rs.bar_id, 128);
+    const float2 p0 = buf[rs.r], p1 = buf[128 + rs.r], p2 = buf[256 + rs.r], p3 = buf[384 + rs.r];
+    mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
+    const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+    const float M2 = (p0.y + p1.y) + (p2.y + p3.y) + 32.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    rstd = rsqrtf(M2 * (1.f / kD) + kLnEps);
+}
+
+// A operand <- SiLU( LN(y) * (1 + scale) + shift ) for this thread's 32 features [c0, c0+32)
+// (reference transformer.py:77-80).  The scale|shift accumulator in TMEM columns kColS is laid out
+//   [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]; st = stylization params in smem.
+template <bool kBf16>
+__device__ __forceinline__ void film_to_a(uint32_t trow, const float* y, float mean, float rstd, const float* st, uint32_t awork,
+                                          uint32_t r, uint32_t c0) {
+    const uint32_t sbase = trow + kColS + (c0 >> 6) * 128 + (c0 & 63);     // scale column of feature c0
+    const float* be = st + kStBe + (c0 >> 6) * 128 + (c0 & 63);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        float sc[16], sh[16], o[16];
+        tmem_ld16(sbase + 16 * hf, sc);
+        tmem_ld16(sbase + 64 + 16 * hf, sh);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(st + kStG + c0 + 16 * hf + 4 * i4);
+            const float4 b4 = *reinterpret_cast<const float4*>(st + kStB + c0 + 16 * hf + 4 * i4);
+            const float4 es = *reinterpret_cast<const float4*>(be + 16 * hf + 4 * i4);
+            const float4 eh = *reinterpret_cast<const float4*>(be + 64 + 16 * hf + 4 * i4);
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float ss[4] = {es.x, es.y, es.z, es.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * i4 + k;
+                const float n = fmaf((y[16 * hf + i] - mean) * rstd, gg[k], bb[k]);
+                const float v = fmaf(n, sc[i] + ss[k], sh[i] + hh[k]);
+                o[i] = silu_f<kBf16>(v);
+            }
+        }
+        store_a16<kBf16>(awork, r, c0 + 16 * hf, o);
+    }
+}
+
+// v[32] += bias[c0 .. c0+32) from shared memory
+__device__ __forceinline__ void add_bias32(float* v, const float* bias) {
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * i4);
+        v[4 * i4] += b4.x, v[4 * i4 + 1] += b4.y, v[4 * i4 + 2] += b4.z, v[4 * i4 + 3] += b4.w;
+    }
+}
+
 // row threads signal "A operand (and any TMEM writes) ready"
 __device__ __forceinline__ void rows_publish(TileBarriers* bars) {
     fence_async_smem();
@@ -360,14 +375,15 @@ __device__ __forceinline__ void rows_wait(TileBarriers* bars, int which, uint32_
 }
 
 template <bool kBf16>
-__global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
+__global__ void __maxnreg__(112) layer_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smem;
     uint8_t* awork_p = smem + kStages * kStageBytes;
     float* prm = reinterpret_cast<float*>(awork_p + kAworkBytes);          // [kPrmFloats]
     float* prm_sa = prm + kPrmFloats;                                      // [384] SA biases of layer l+1
-    TileBarriers* bars = reinterpret_cast<TileBarriers*>(prm_sa + 384);
+    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);                // [2][4][128]
+    TileBarriers* bars = reinterpret_cast<TileBarriers*>(xchg + 1024);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (a.do_main)
@@ -377,46 +393,45 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     tile_setup(bars, warp, lane);
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         if (lane == 0) producer_loop(a.ops, a.n_ops, a.wbuf, a.aemb + (size_t)blockIdx.x * 8 * kStageABytes, ring, bars);
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) mma_loop<kBf16>(a.ops, a.n_ops, ring, awork_p, bars, tmem_base);
     } else {
-        const uint32_t r = threadIdx.x;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lq = warp & 3, cq = warp >> 2;
+        const uint32_t r = lq * 32 + lane;            // row of the tile == TMEM lane
+        const uint32_t c0 = cq * 32;                  // first of this thread's 32 features (heads 2cq, 2cq+1)
+        const uint32_t trow = tmem_base + ((lq * 32) << 16);
         const uint32_t awork = smem_u32(awork_p);
         const long g = (long)blockIdx.x * kTileRows + r;
         const bool valid = g < a.M;
         const int b = valid ? (int)(g / a.T) : 0;
         const int t = valid ? (int)(g - (long)b * a.T) : 0;
         uint32_t ph[3] = {0, 0, 0};
+        RowStats rs{xchg, 1 + lq, r, cq, 0};
         float mean, rstd;
+        float v[32];
 
         // ---- residual stream -> TMEM
         {
-            const float4* src = reinterpret_cast<const float4*>(a.h + (size_t)g * kD);
+            const float4* src = reinterpret_cast<const float4*>(a.h + (size_t)g * kD + c0);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 f = valid ? src[4 * c + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
-                }
-                tmem_st16(trow + kColH + 16 * c, v);
+            for (int i = 0; i < 8; ++i) {
+                const float4 f = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
             }
+            tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
         }
 
         if (a.do_main) {
             // ================= self-attention tail: y = q . A_sa ; h += Styl(y)
             {
-                const uint4* qrow = reinterpret_cast<const uint4*>(a.q + (size_t)g * kD);
-                const float* Ab = a.A_sa + (size_t)b * (kH * 256);
-                float sum = 0.f;
-#pragma unroll 1
-                for (int hh = 0; hh < kH; ++hh) {
-                    float qv[16], y[16];
+                const uint4* qrow = reinterpret_cast<const uint4*>(a.q + (size_t)g * kD + c0);
+                const float* Ab = a.A_sa + (size_t)b * (kH * 256) + (2 * cq) * 256;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float qv[16];
                     uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
                     if (valid) u0 = qrow[2 * hh], u1 = qrow[2 * hh + 1];
                     const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -425,167 +440,131 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         const float2 f = unpack2<kBf16>(uu[i]);
                         qv[2 * i] = f.x, qv[2 * i + 1] = f.y;
                     }
-                    head_apply(qv, Ab + hh * 256, y);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sum += y[i];
-                    tmem_st16(trow + kColW + 16 * hh, y);
+                    head_apply(qv, Ab + hh * 256, v + 16 * hh);
                 }
-                tmem_wait_st();
-                mean = sum * (1.f / kD);
-                float ss = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float v[16];
-                    tmem_ld16(trow + kColW + 16 * c, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float d = v[i] - mean;
-                        ss = fmaf(d, d, ss);
-                    }
-                }
-                rstd = rsqrtf(ss * (1.f / kD) + kLnEps);
             }
+            row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_sa
-            row_film_to_a<kBf16>(trow, mean, rstd, prm + kPrmStSa, awork, r);
+            film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
             rows_publish(bars);                                          // -> h += A . Wo_sa
 
             // ================= cross-attention
             rows_wait(bars, 1, ph[1]);
-            row_stats(trow + kColH, prm + kPrmStSa + kStBo, mean, rstd);  // h += bo_sa ; LN stats
-            row_normalize_to_a<kBf16>(trow + kColH, mean, rstd, awork, r);
+            tmem_ld32(trow + kColH + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm + kPrmStSa + kStBo + c0);                  // deferred bias of Wo_sa
+            tmem_st32(trow + kColH + c0, v);
+            row_stats32(rs, v, mean, rstd);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq_ca
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+            tmem_wait_st();
             rows_publish(bars);                                          // -> W = LN(h) . Wq_ca
             rows_wait(bars, 2, ph[2]);
             {
-                const float* Ab = a.A_ca + (size_t)b * a.a_ca_stride;
-                float sum = 0.f;
-#pragma unroll 1
-                for (int hh = 0; hh < kH; ++hh) {
-                    float qv[16], y[16];
-                    tmem_ld16(trow + kColW + 16 * hh, qv);
-                    tmem_wait_ld();
+                float qv[32];
+                tmem_ld32(trow + kColW + c0, qv);
+                tmem_wait_ld();
+                add_bias32(qv, prm + kPrmCaBq + c0);
+                const float* Ab = a.A_ca + (size_t)b * a.a_ca_stride + (2 * cq) * 256;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) qv[i] += prm[kPrmCaBq + 16 * hh + i];
-                    softmax16(qv);
-                    head_apply(qv, Ab + hh * 256, y);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sum += y[i];
-                    tmem_st16(trow + kColW + 16 * hh, y);
+                for (int hh = 0; hh < 2; ++hh) {
+                    softmax16(qv + 16 * hh);
+                    head_apply(qv + 16 * hh, Ab + hh * 256, v + 16 * hh);
                 }
-                tmem_wait_st();
-                mean = sum * (1.f / kD);
-                float ss = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float v[16];
-                    tmem_ld16(trow + kColW + 16 * c, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float d = v[i] - mean;
-                        ss = fmaf(d, d, ss);
-                    }
-                }
-                rstd = rsqrtf(ss * (1.f / kD) + kLnEps);
             }
+            row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_ca
-            row_film_to_a<kBf16>(trow, mean, rstd, prm + kPrmStCa, awork, r);
+            film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
             rows_publish(bars);                                          // -> h += A . Wo_ca
 
             // ================= FFN (no pre-norm, reference transformer.py:170-173)
             rows_wait(bars, 1, ph[1]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v[16];
-                tmem_ld16(trow + kColH + 16 * c, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += prm[kPrmStCa + kStBo + 16 * c + i];
-                tmem_st16(trow + kColH + 16 * c, v);
-                store_a16<kBf16>(awork, r, 16 * c, v);
-            }
+            tmem_ld32(trow + kColH + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm + kPrmStCa + kStBo + c0);                  // deferred bias of Wo_ca
+            tmem_st32(trow + kColH + c0, v);
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
             rows_publish(bars);                                          // -> W[0:64] = h . W1
             rows_wait(bars, 2, ph[2]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float v[16];
-                tmem_ld16(trow + kColW + 16 * c, v);
+            {
+                float u[16];                                             // hidden 64 = 4 quarters of 16
+                tmem_ld16(trow + kColW + 16 * cq, u);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = gelu_erf_f(v[i] + prm[kPrmFfB1 + 16 * c + i]);
-                store_a16<kBf16>(awork, r, 16 * c, v);
+                for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
+                store_a16<kBf16>(awork, r, 16 * cq, u);
             }
             rows_publish(bars);                                          // -> W = GELU(.) . W2
             rows_wait(bars, 2, ph[2]);
-            row_stats(trow + kColW, prm + kPrmFfB2, mean, rstd);          // y = W + b2 ; LN stats
+            tmem_ld32(trow + kColW + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm + kPrmFfB2 + c0);
+            row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_ffn
-            row_film_to_a<kBf16>(trow, mean, rstd, prm + kPrmStFf, awork, r);
+            film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
             rows_publish(bars);                                          // -> h += A . Wo_ffn
             rows_wait(bars, 1, ph[1]);
         }
 
+        // ---- final value of the residual stream for this launch (deferred bias of the last FFN block)
+        tmem_ld32(trow + kColH + c0, v);
+        tmem_wait_ld();
+        if (a.do_main) add_bias32(v, prm + kPrmStFf + kStBo + c0);
+        if (valid) {
+            float4* dst = reinterpret_cast<float4*>(a.h + (size_t)g * kD + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+
         if (a.do_sa1) {
             // ================= next layer's self-attention head: LN -> q | k | v
-            row_stats(trow + kColH, a.do_main ? prm + kPrmStFf + kStBo : nullptr, mean, rstd);
-            row_normalize_to_a<kBf16>(trow + kColH, mean, rstd, awork, r);
+            row_stats32(rs, v, mean, rstd);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq/Wk/Wv
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             rows_publish(bars);
             rows_wait(bars, 2, ph[2]);
             const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
-#pragma unroll 1
-            for (int hh = 0; hh < kH; ++hh) {
-                float qv[16];
-                tmem_ld16(trow + kColS + 16 * hh, qv);
-                tmem_wait_ld();
+            // q: softmax over head-dim, stored 16-bit
+            tmem_ld32(trow + kColS + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm_sa + kPrmSaBq + c0);
+            softmax16(v);
+            softmax16(v + 16);
+            if (valid) {
+                uint32_t p[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) qv[i] += prm_sa[kPrmSaBq + 16 * hh + i];
-                softmax16(qv);
-                if (valid) {
-                    uint32_t p[8];
+                for (int i = 0; i < 16; ++i) p[i] = pack2<kBf16>(v[2 * i], v[2 * i + 1]);
+                uint4* dst = reinterpret_cast<uint4*>(a.q + (size_t)g * kD + c0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) p[i] = pack2<kBf16>(qv[2 * i], qv[2 * i + 1]);
-                    uint4* dst = reinterpret_cast<uint4*>(a.q + (size_t)g * kD + 16 * hh);
-                    dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+            }
+            // k (masked frames get -1e6 before the time softmax), v (masked frames zeroed): reference :107,:114
+            tmem_ld32(trow + kColS + 128 + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm_sa + kPrmSaBk + c0);
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.kv + (size_t)g * 256 + c0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    if (!keep) o.x += -1000000.f, o.y += -1000000.f, o.z += -1000000.f, o.w += -1000000.f;
+                    dst[i] = o;
                 }
             }
-#pragma unroll 1
-            for (int c = 0; c < 16; ++c) {                               // k: cols 0..127 of kv ; v: cols 128..255
-                const bool is_v = c >= 8;
-                float v[16];
-                tmem_ld16(trow + (is_v ? kColW + 16 * (c - 8) : kColS + 128 + 16 * c), v);
-                tmem_wait_ld();
-                if (valid) {
-                    const float* bias = prm_sa + (is_v ? kPrmSaBv + 16 * (c - 8) : kPrmSaBk + 16 * c);
+            tmem_ld32(trow + kColW + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm_sa + kPrmSaBv + c0);
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.kv + (size_t)g * 256 + kD + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] += bias[i];
-                        if (!keep) v[i] = is_v ? 0.f : v[i] + -1000000.f;   // reference transformer.py:107,114
-                    }
-                    float4* dst = reinterpret_cast<float4*>(a.kv + (size_t)g * 256 + 16 * c);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-            }
-        }
-
-        // ---- residual stream -> global (deferred bias of the last FFN block added here if not yet)
-        {
-            const bool add_bias = a.do_main && !a.do_sa1;
-            float4* dst = reinterpret_cast<float4*>(a.h + (size_t)g * kD);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v[16];
-                tmem_ld16(trow + kColH + 16 * c, v);
-                tmem_wait_ld();
-                if (add_bias) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += prm[kPrmStFf + kStBo + 16 * c + i];
-                }
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[4 * c + i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     }
@@ -593,6 +572,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
 }
 
 constexpr int kGemmSmemBytes = kStages * kStageBytes + sizeof(TileBarriers) + 1024;
-constexpr int kLayerSmemBytes = kStages * kStageBytes + kAworkBytes + (kPrmFloats + 384) * 4 + sizeof(TileBarriers) + 1024;
+constexpr int kLayerSmemBytes =
+    kStages * kStageBytes + kAworkBytes + (kPrmFloats + 384) * 4 + 1024 * 8 + sizeof(TileBarriers) + 1024;
 
 }  // namespace dc
