@@ -375,7 +375,7 @@ __device__ __forceinline__ void rows_wait(TileBarriers* bars, int which, uint32_
 }
 
 template <bool kBf16>
-__global__ void __maxnreg__(112) layer_kernel(const __grid_constant__ LayerArgs a) {
+__global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smem;
