@@ -87,10 +87,11 @@ struct dc_handle {
     uint8_t* zimg = nullptr;
     uint8_t* aemb = nullptr;
     float* hbuf = nullptr;
-    uint16_t* q = nullptr;
+    uint8_t* q_img = nullptr;     // [tiles][32 KB] packed softmax_hd(Q) image
     float* kv = nullptr;
-    float* A_sa = nullptr;
-    float* A_ca = nullptr;
+    uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
+    uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
+    int mask_invert = 0;
     long long* length = nullptr;
     bool has_length = false;
     float* te_b = nullptr;        // [B][512]
@@ -190,29 +191,29 @@ const HostTensor* get(dc_handle* h, const std::string& key, std::initializer_lis
     return &it->second;
 }
 
-TileOp make_op(uint32_t w_off, uint32_t stage_bytes, int n_stages, int kb_per_stage, int n, uint32_t d_col, bool ring, bool acc,
-               bool wait_a, int commit) {
-    TileOp o{};
+DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bool acc, int wait, int commit, int seg = 0,
+             bool releases_s = false) {
+    DOp o{};
     o.w_off = w_off;
-    o.w_stage_bytes = stage_bytes;
-    o.n_stages = (uint16_t)n_stages;
-    o.kb_per_stage = (uint16_t)kb_per_stage;
+    o.w_bytes = w_bytes;
     o.n = (uint16_t)n;
     o.d_col = (uint16_t)d_col;
-    o.a_from_ring = ring;
+    o.kb = (uint8_t)kb;
     o.accumulate = acc;
-    o.wait_a = wait_a;
+    o.wait = (uint8_t)wait;
     o.commit = (uint8_t)commit;
+    o.seg = (uint8_t)seg;
+    o.releases_s = releases_s;
     return o;
 }
 
 void free_workspace(dc_handle* h) {
-    void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q, h->kv, h->A_sa, h->A_ca, h->length,
+    void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q_img, h->kv, h->bd_sa, h->bd_ca, h->length,
                     h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    h->xp = nullptr, h->zimg = nullptr, h->aemb = nullptr, h->hbuf = nullptr, h->q = nullptr, h->kv = nullptr;
-    h->A_sa = nullptr, h->A_ca = nullptr, h->length = nullptr, h->te_b = nullptr, h->xwork = nullptr, h->x0work = nullptr;
+    h->xp = nullptr, h->zimg = nullptr, h->aemb = nullptr, h->hbuf = nullptr, h->q_img = nullptr, h->kv = nullptr;
+    h->bd_sa = nullptr, h->bd_ca = nullptr, h->length = nullptr, h->te_b = nullptr, h->xwork = nullptr, h->x0work = nullptr;
     h->in_proj = nullptr, h->in_out = nullptr;
     h->cap_tokens = 0, h->cap_B = 0;
 }
@@ -235,10 +236,10 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->zimg, tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->aemb, tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->hbuf, Mpad * kD * 4));
-    DC_CUDA(h, cudaMalloc((void**)&h->q, Mpad * kD * 2));
+    DC_CUDA(h, cudaMalloc((void**)&h->q_img, tiles * (size_t)kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->kv, Mpad * 256 * 4));
-    DC_CUDA(h, cudaMalloc((void**)&h->A_sa, (size_t)B * kH * 256 * 4));
-    DC_CUDA(h, cudaMalloc((void**)&h->A_ca, (size_t)B * L * kH * 256 * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->bd_sa, (size_t)B * kAworkBytes));
+    DC_CUDA(h, cudaMalloc((void**)&h->bd_ca, (size_t)B * L * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
     DC_CUDA(h, cudaMalloc((void**)&h->te_b, (size_t)B * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->xwork, Mpad * kP * 4));
@@ -248,7 +249,10 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     // padded rows of the operand images must hold finite values
     DC_CUDA(h, cudaMemset(h->zimg, 0, tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMemset(h->aemb, 0, tiles * 8 * (size_t)kABlockBytes));
-    DC_CUDA(h, cudaMemset(h->q, 0, Mpad * kD * 2));
+    DC_CUDA(h, cudaMemset(h->q_img, 0, tiles * (size_t)kAworkBytes));
+    // off-diagonal head blocks of the attention images are never written: they must be zero
+    DC_CUDA(h, cudaMemset(h->bd_sa, 0, (size_t)B * kAworkBytes));
+    DC_CUDA(h, cudaMemset(h->bd_ca, 0, (size_t)B * L * kAworkBytes));
     h->cap_tokens = M;
     h->cap_B = B;
     return 0;
@@ -284,35 +288,39 @@ LayerArgs layer_args(dc_handle* h, int l) {
     int n = 0;
     if (a.do_main) {
         const uint32_t base = (uint32_t)l * kLayerSlab;
-        a.ops[n++] = make_op(base + kOffWeSa, 32768, 8, 1, 256, kColS, true, false, false, 0);
-        a.ops[n++] = make_op(base + kOffWoSa, 32768, 1, 2, 128, kColH, false, true, true, 1);
-        a.ops[n++] = make_op(base + kOffWeCa, 32768, 8, 1, 256, kColS, true, false, false, 0);
-        a.ops[n++] = make_op(base + kOffWqCa, 32768, 1, 2, 128, kColW, false, false, true, 2);
-        a.ops[n++] = make_op(base + kOffWoCa, 32768, 1, 2, 128, kColH, false, true, true, 1);
-        a.ops[n++] = make_op(base + kOffWeFf, 32768, 8, 1, 256, kColS, true, false, false, 0);
-        a.ops[n++] = make_op(base + kOffW1, 16384, 1, 2, 64, kColW, false, false, true, 2);
-        a.ops[n++] = make_op(base + kOffW2, 16384, 1, 1, 128, kColW, false, false, true, 2);
-        a.ops[n++] = make_op(base + kOffWoFf, 32768, 1, 2, 128, kColH, false, true, true, 1);
+        a.sop_w_off[0] = base + kOffWeSa;
+        a.sop_w_off[1] = base + kOffWeCa;
+        a.sop_w_off[2] = base + kOffWeFf;
+        a.n_s = 3;
+        a.dops[n++] = make_dop(0, 32768, 2, 128, kColW, false, 2, 2, 1);                       // y = q . blockdiag(A_sa)
+        a.dops[n++] = make_dop(base + kOffWoSa, 32768, 2, 128, kColH, true, 1, 1, 0, true);    // h += . Wo_sa
+        a.dops[n++] = make_dop(base + kOffWqCa, 32768, 2, 128, kColW, false, 1, 2);            // q_ca
+        a.dops[n++] = make_dop(0, 32768, 2, 128, kColW, false, 1, 2, 2);                       // y = softmax(q) . blockdiag(A_ca)
+        a.dops[n++] = make_dop(base + kOffWoCa, 32768, 2, 128, kColH, true, 1, 1, 0, true);    // h += . Wo_ca
+        a.dops[n++] = make_dop(base + kOffW1, 16384, 2, 64, kColW, false, 1, 2);               // FFN up
+        a.dops[n++] = make_dop(base + kOffW2, 16384, 1, 128, kColW, false, 1, 2);              // FFN down
+        a.dops[n++] = make_dop(base + kOffWoFf, 32768, 2, 128, kColH, true, 1, 1);             // h += . Wo_ffn
     }
     if (a.do_sa1) {
         const uint32_t base = (uint32_t)(l + 1) * kLayerSlab;
-        a.ops[n++] = make_op(base + kOffWq, 32768, 1, 2, 128, kColS, false, false, true, 255);
-        a.ops[n++] = make_op(base + kOffWk, 32768, 1, 2, 128, kColS + 128, false, false, false, 255);
-        a.ops[n++] = make_op(base + kOffWv, 32768, 1, 2, 128, kColW, false, false, false, 2);
+        a.dops[n++] = make_dop(base + kOffWq, 32768, 2, 128, kColS, false, 1, 255);
+        a.dops[n++] = make_dop(base + kOffWk, 32768, 2, 128, kColS + 128, false, 0, 255);
+        a.dops[n++] = make_dop(base + kOffWv, 32768, 2, 128, kColW, false, 0, 2);
     }
-    a.n_ops = n;
+    a.n_d = n;
     a.M = h->M;
     a.T = h->T;
+    a.mask_invert = h->mask_invert;
     a.wbuf = h->wbuf;
     a.aemb = h->aemb;
     a.prm = h->prm + (size_t)(l >= 0 ? l : 0) * kPrmFloats;
     a.prm_next = h->prm + (size_t)(l + 1 < L ? l + 1 : 0) * kPrmFloats;
     a.h = h->hbuf;
-    a.q = h->q;
+    a.q_img = h->q_img;
     a.kv = h->kv;
-    a.A_sa = h->A_sa;
-    a.A_ca = h->A_ca + (size_t)(l >= 0 ? l : 0) * kH * 256;
-    a.a_ca_stride = L * kH * 256;
+    a.bd_sa = h->bd_sa;
+    a.bd_ca = h->bd_ca + (size_t)(l >= 0 ? l : 0) * kAworkBytes;
+    a.bd_ca_stride = (size_t)L * kAworkBytes;
     a.length = h->has_length ? h->length : nullptr;
     return a;
 }
@@ -348,7 +356,8 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         h->launches++;
         mark(1);
         if (l + 1 < L) {
-            kv_reduce_kernel<<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->A_sa, kH * 256);
+            if (h->bf16) kv_reduce_kernel<true><<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->bd_sa, (size_t)kAworkBytes);
+            else kv_reduce_kernel<false><<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->bd_sa, (size_t)kAworkBytes);
             h->launches++;
             mark(2);
         }
@@ -393,6 +402,8 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     DC_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     DC_CUDA(h, cudaMalloc((void**)&h->step_ctr, 4));
     DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
+    const char* mi = getenv("DC_MASK_INVERT");
+    if (mi && mi[0] == '1') h->mask_invert = 1;
     const char* ng = getenv("DC_NO_GRAPH");
     if (ng && ng[0] == '1') h->use_graphs = false;
     *out = h;
@@ -636,7 +647,10 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         ga.M = h->M, ga.N = 256, ga.kblocks = 8, ga.ldo = 256;
         const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st) : launch_gemm_rows<false>(h, ga, h->tiles, st);
         if (rc) return rc;
-        kv_reduce_kernel<<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->A_ca + (size_t)l * kH * 256, L * kH * 256);
+        if (h->bf16)
+            kv_reduce_kernel<true><<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
+        else
+            kv_reduce_kernel<false><<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
         h->launches += 2;
     }
     DC_CUDA(h, cudaGetLastError());

@@ -246,10 +246,13 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 //   A[b,h,d,l] = sum_t softmax_t(k[b,t,h,d]) * v[b,t,h,l]
 // kv is [M][ld] fp32 with k in columns [0,128) and v in [128,256).  One block per (clip, head),
 // 256 threads = (d,l) pairs.  Two passes over the clip's 16 key columns: max, then exp/sum/outer
-// product through shared memory.  All fp32.
+// product through shared memory.  All fp32.  The result is written as the 16x16 diagonal block of
+// head h in a packed 16-bit B-operand image Bd[n = 16h+l][k = 16h+d] (off-diagonal blocks stay zero),
+// so that y = q . blockdiag(A) runs on the tensor cores in the layer kernel.
 // ---------------------------------------------------------------------------------------------
+template <bool kBf16>
 __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv, int ld, int T,
-                                                         float* __restrict__ A /*[B][8][16][16]*/, int a_stride_b) {
+                                                         uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride) {
     constexpr int TT = 128;                 // tokens per shared-memory chunk
     constexpr int U = TT / 16;              // independent loads per thread per chunk
     __shared__ float ek[TT][kHd + 1];
@@ -308,7 +311,9 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
         }
         __syncthreads();
     }
-    A[(size_t)b * a_stride_b + hh * 256 + d * 16 + l] = acc / se;
+    const int ki = hh * kHd + d, nj = hh * kHd + l;
+    const size_t off = (size_t)b * bd_stride + (size_t)(ki >> 6) * kABlockBytes + sw128_offset(nj, (ki & 63) >> 3) + (ki & 7) * 2;
+    *reinterpret_cast<uint16_t*>(bd + off) = pack1<kBf16>(acc / se);
 }
 
 // ---------------------------------------------------------------------------------------------

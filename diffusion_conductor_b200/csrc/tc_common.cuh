@@ -47,6 +47,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// non-blocking probe
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -165,6 +177,17 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with a 128-bit "disable output lane" mask: bit r set -> row r (TMEM lane r) of D is left
+// untouched.  Lets one A operand be multiplied by a different B per row segment.
+__device__ __forceinline__ void umma_f16_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                                const uint32_t* mask) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(mask[0]), "r"(mask[1]), "r"(mask[2]), "r"(mask[3])
+        : "memory");
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -177,6 +200,14 @@ __device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a_smem, ui
     const uint64_t bd = make_desc_kmajor_sw128(b_smem);
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accumulate_first || k > 0) ? 1u : 0u);
+}
+
+__device__ __forceinline__ void umma_kblock_masked(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool accumulate_first,
+                                                   const uint32_t* mask) {
+    const uint64_t ad = make_desc_kmajor_sw128(a_smem);
+    const uint64_t bd = make_desc_kmajor_sw128(b_smem);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16_masked(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (accumulate_first || k > 0) ? 1u : 0u, mask);
 }
 
 // ---------------------------------------------------------------- operand element type

@@ -23,8 +23,8 @@ constexpr int kStageBytes = kStageABytes + kStageWBytes;
 constexpr int kAworkBytes = 2 * kABlockBytes;     // [128 x 128] A operand written by the row threads
 constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;       // 512
-constexpr int kProducerWarp = 16, kMmaWarp = 17;
-constexpr int kTileThreads = kRowThreads + 64;    // 576
+constexpr int kProducerWarp = 16, kMmaWarp = 17, kProducerBWarp = 18;
+constexpr int kTileThreads = kRowThreads + 96;    // 608
 
 // TMEM column map (512 columns x 128 lanes x fp32)
 constexpr uint32_t kColH = 0;      // residual stream h            [128]
@@ -150,7 +150,7 @@ struct GemmRowsArgs {
 template <bool kBf16>
 __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid_constant__ GemmRowsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring = smem;
     TileBarriers* bars = reinterpret_cast<TileBarriers*>(smem + kStages * kStageBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,22 +222,65 @@ constexpr int kPrmStFf = 1984;
 constexpr int kPrmFloats = 2624;
 constexpr int kStBe = 0, kStG = 256, kStB = 384, kStBo = 512;
 
+// Two operand streams feed the MMA issuer:
+//   ring A : the FiLM projections S = A_emb . We (K = 512, N = 256), 8 stages of (16 KB A_emb k-block +
+//            32 KB weight k-block) each.  They depend on no row-thread result, only on the S accumulator
+//            being free, so they fill every gap of the tensor pipe.
+//   ring B : the dependent GEMMs (<= 32 KB of weights each, A operand written by the row threads) and the
+//            per-clip block-diagonal attention matrices.
+// The issuer polls both (dependent work first), so a short dependent GEMM never queues behind a long
+// FiLM projection.
+constexpr int kRingAStages = 2;
+constexpr int kRingBStages = 2;
+constexpr int kRingBStageBytes = 32 * 1024;
+constexpr int kSopStages = 8;
+
+struct DOp {
+    uint32_t w_off;        // byte offset in the packed weight buffer (seg == 0)
+    uint32_t w_bytes;      // bytes of the ring-B stage
+    uint16_t n;            // UMMA N
+    uint16_t d_col;        // accumulator column
+    uint8_t kb;            // k-blocks of 64
+    uint8_t accumulate;    // D += (residual add into h)
+    uint8_t wait;          // 0: none, 1: a_ready (row threads), 2: q_full (bulk copy of the q image)
+    uint8_t commit;        // 0/1/2: arrive d_ready[commit] when done, 255: none
+    uint8_t seg;           // 0: plain; 1 / 2: one lane-masked GEMM per clip segment of the tile with that clip's
+                           //    block-diagonal self- / cross-attention matrix as B operand
+    uint8_t releases_s;    // passing this op's wait means the row threads are done with the S accumulator
+    uint8_t pad[2];
+};
+
+constexpr int kMaxDOps = 12;
+constexpr int kMaxSOps = 3;
+
+struct LayerBarriers {
+    uint64_t fullA[kRingAStages], emptyA[kRingAStages];
+    uint64_t fullB[kRingBStages], emptyB[kRingBStages];
+    uint64_t a_ready;
+    uint64_t q_full;
+    uint64_t d_ready[3];   // 0: S, 1: H, 2: W
+    uint32_t tmem_base;
+};
+
 struct LayerArgs {
-    TileOp ops[kMaxOps];
-    int n_ops;
+    uint32_t sop_w_off[kMaxSOps];
+    int n_s;
+    DOp dops[kMaxDOps];
+    int n_d;
     int do_main;            // SA tail (q.A + stylization), cross-attention, FFN of layer l
     int do_sa1;             // LayerNorm + q/k/v projections of layer l+1
     int M, T;
+    int mask_invert;        // debug: flip the meaning of the MMA lane mask
     const uint8_t* wbuf;    // packed weights (whole model)
     const uint8_t* aemb;    // A_emb image [tiles][8][16 KB]
     const float* prm;       // parameter block of layer l (do_main)
     const float* prm_next;  // parameter block of layer l+1 (do_sa1; only the SA biases are read)
     float* h;               // [Mpad][128] residual stream (in/out)
-    uint16_t* q;            // [Mpad][128] softmax_hd(Q) of the self-attention (16-bit)
-    float* kv;              // [Mpad][256] k | v of the self-attention
-    const float* A_sa;      // [B][8][16][16]   softmax_T(K)^T V of layer l self-attention
-    const float* A_ca;      // [B][...]: cross-attention K^T V of layer l, clip stride a_ca_stride
-    int a_ca_stride;
+    uint8_t* q_img;         // [tiles][32 KB] softmax_hd(Q) of the self-attention as a packed A-operand image (in/out)
+    float* kv;              // [Mpad][256] k | v of the self-attention (out)
+    const uint8_t* bd_sa;   // [B][32 KB] block-diagonal softmax_T(K)^T V of layer l self-attention
+    const uint8_t* bd_ca;   // cross-attention counterpart of layer l; clip stride bd_ca_stride bytes
+    size_t bd_ca_stride;
     const long long* length;  // [B] or null (all frames valid)
 };
 
@@ -252,24 +295,6 @@ __device__ __forceinline__ float silu_f(float v) {
     }
 }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
-
-// y[16] = q[16] . A[16][16]  (A row-major [d][l] in global memory, read through L1)
-__device__ __forceinline__ void head_apply(const float* q, const float* __restrict__ Ah, float* y) {
-#pragma unroll
-    for (int l = 0; l < 16; ++l) y[l] = 0.f;
-    const float4* Ap = reinterpret_cast<const float4*>(Ah);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-#pragma unroll
-        for (int l4 = 0; l4 < 4; ++l4) {
-            const float4 av = __ldg(Ap + d * 4 + l4);
-            y[4 * l4 + 0] = fmaf(q[d], av.x, y[4 * l4 + 0]);
-            y[4 * l4 + 1] = fmaf(q[d], av.y, y[4 * l4 + 1]);
-            y[4 * l4 + 2] = fmaf(q[d], av.z, y[4 * l4 + 2]);
-            y[4 * l4 + 3] = fmaf(q[d], av.w, y[4 * l4 + 3]);
-        }
-    }
-}
 
 __device__ __forceinline__ void softmax16(float* q) {
     float mx = q[0];
@@ -287,7 +312,7 @@ __device__ __forceinline__ void softmax16(float* q) {
 }
 
 // Row statistics over 128 features held as 4 x 32 registers by the 4 warps that share a row:
-// local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.  `buf` alternates
+// local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.  `flip` alternates
 // between two exchange buffers so consecutive calls need no second barrier.
 struct RowStats {
     float2* xchg;      // [2][4][128]
@@ -363,40 +388,189 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias) {
 }
 
 // row threads signal "A operand (and any TMEM writes) ready"
-__device__ __forceinline__ void rows_publish(TileBarriers* bars) {
+__device__ __forceinline__ void rows_publish(LayerBarriers* bars) {
     fence_async_smem();
     tc_fence_before();
     mbar_arrive(smem_u32(&bars->a_ready));
 }
-__device__ __forceinline__ void rows_wait(TileBarriers* bars, int which, uint32_t& phase) {
+__device__ __forceinline__ void rows_wait(LayerBarriers* bars, int which, uint32_t& phase) {
     mbar_wait(smem_u32(&bars->d_ready[which]), phase & 1u);
     ++phase;
     tc_fence_after();
 }
 
+// clip segments of a 128-row tile: rows [lo, hi) of the tile belong to clip first_clip + s
+struct TileSegs {
+    int first_clip, n_seg, tile_row0, T;
+    __device__ __forceinline__ void init(int tile, int M, int T_) {
+        T = T_;
+        tile_row0 = tile * kTileRows;
+        first_clip = tile_row0 / T;
+        const int last_row = min(tile_row0 + kTileRows - 1, M - 1);
+        n_seg = last_row / T - first_clip + 1;
+    }
+    // bit r set <=> row r is NOT in segment s (the tcgen05 "disable output lane" convention)
+    __device__ __forceinline__ void mask(int s, uint32_t* m, bool invert) const {
+        const int lo = max(0, (first_clip + s) * T - tile_row0);
+        const int hi = (s == n_seg - 1) ? kTileRows : min(kTileRows, (first_clip + s + 1) * T - tile_row0);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t in = 0;
+            const int a = max(lo, 32 * w), b = min(hi, 32 * w + 32);
+            if (b > a) in = ((b - a) == 32 ? 0xFFFFFFFFu : ((1u << (b - a)) - 1u)) << (a - 32 * w);
+            m[w] = invert ? in : ~in;
+        }
+    }
+};
+
 template <bool kBf16>
 __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ring = smem;
-    uint8_t* awork_p = smem + kStages * kStageBytes;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ringA = smem;
+    uint8_t* ringB = ringA + kRingAStages * kStageBytes;
+    uint8_t* awork_p = ringB + kRingBStages * kRingBStageBytes;
     float* prm = reinterpret_cast<float*>(awork_p + kAworkBytes);          // [kPrmFloats]
     float* prm_sa = prm + kPrmFloats;                                      // [384] SA biases of layer l+1
     float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);                // [2][4][128]
-    TileBarriers* bars = reinterpret_cast<TileBarriers*>(xchg + 1024);
+    LayerBarriers* bars = reinterpret_cast<LayerBarriers*>(xchg + 1024);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (a.do_main)
         for (int i = threadIdx.x; i < kPrmFloats; i += kTileThreads) prm[i] = a.prm[i];
     if (a.do_sa1)
         for (int i = threadIdx.x; i < 384; i += kTileThreads) prm_sa[i] = a.prm_next[i];
-    tile_setup(bars, warp, lane);
+    if (warp == kProducerWarp && lane == 0) {
+        for (int i = 0; i < kRingAStages; ++i) mbar_init(smem_u32(&bars->fullA[i]), 1), mbar_init(smem_u32(&bars->emptyA[i]), 1);
+        for (int i = 0; i < kRingBStages; ++i) mbar_init(smem_u32(&bars->fullB[i]), 1), mbar_init(smem_u32(&bars->emptyB[i]), 1);
+        mbar_init(smem_u32(&bars->a_ready), kRowThreads);
+        mbar_init(smem_u32(&bars->q_full), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == kProducerWarp) {
-        if (lane == 0) producer_loop(a.ops, a.n_ops, a.wbuf, a.aemb + (size_t)blockIdx.x * 8 * kStageABytes, ring, bars);
+        // ---------------- ring A: A_emb k-blocks + FiLM projection weights
+        if (lane == 0) {
+            const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
+            uint32_t it = 0;
+            for (int o = 0; o < a.n_s; ++o) {
+                const uint8_t* w = a.wbuf + a.sop_w_off[o];
+                for (int s = 0; s < kSopStages; ++s, ++it) {
+                    const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                    mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bars->fullA[st]);
+                    uint8_t* stage = ringA + st * kStageBytes;
+                    mbar_arrive_expect_tx(full, kStageBytes);
+                    bulk_g2s(smem_u32(stage), a_img + (size_t)s * kStageABytes, kStageABytes, full);
+                    bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kStageWBytes, full);
+                }
+            }
+        }
+    } else if (warp == kProducerBWarp) {
+        // ---------------- ring B: dependent-GEMM weights, per-clip attention matrices, the q image
+        if (lane == 0) {
+            TileSegs segs;
+            segs.init(blockIdx.x, a.M, a.T);
+            if (a.do_main) {
+                const uint32_t qf = smem_u32(&bars->q_full);
+                mbar_arrive_expect_tx(qf, kAworkBytes);
+                bulk_g2s(smem_u32(awork_p), a.q_img + (size_t)blockIdx.x * kAworkBytes, kAworkBytes, qf);
+            }
+            uint32_t it = 0;
+            for (int o = 0; o < a.n_d; ++o) {
+                const DOp op = a.dops[o];
+                const int n_st = op.seg ? segs.n_seg : 1;
+                for (int s = 0; s < n_st; ++s, ++it) {
+                    const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
+                    mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bars->fullB[st]);
+                    const uint8_t* src = op.seg == 0   ? a.wbuf + op.w_off
+                                         : op.seg == 1 ? a.bd_sa + (size_t)(segs.first_clip + s) * kAworkBytes
+                                                       : a.bd_ca + (size_t)(segs.first_clip + s) * a.bd_ca_stride;
+                    mbar_arrive_expect_tx(full, op.w_bytes);
+                    bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src, op.w_bytes, full);
+                }
+            }
+        }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) mma_loop<kBf16>(a.ops, a.n_ops, ring, awork_p, bars, tmem_base);
+        // ---------------- MMA issuer: dependent GEMMs first, FiLM projection stages in the gaps
+        if (lane == 0) {
+            TileSegs segs;
+            segs.init(blockIdx.x, a.M, a.T);
+            const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
+            const uint32_t awork = smem_u32(awork_p);
+            uint32_t itA = 0, itB = 0, a_phase = 0;
+            int d_idx = 0, d_seg = 0, s_idx = 0, s_stage = 0, s_allowed = 1;
+            bool d_waited = false;
+            while (d_idx < a.n_d || s_idx < a.n_s) {
+                bool progressed = false;
+                if (d_idx < a.n_d) {
+                    const DOp op = a.dops[d_idx];
+                    if (!d_waited) {
+                        if (op.wait == 0) d_waited = true;
+                        else if (op.wait == 1) {
+                            if (mbar_test(smem_u32(&bars->a_ready), a_phase & 1u)) ++a_phase, d_waited = true;
+                        } else if (mbar_test(smem_u32(&bars->q_full), 0)) d_waited = true;
+                        if (d_waited) {
+                            tc_fence_after();
+                            if (op.releases_s) ++s_allowed;
+                        }
+                    }
+                    if (d_waited) {
+                        const uint32_t st = itB % kRingBStages, ph = (itB / kRingBStages) & 1u;
+                        if (mbar_test(smem_u32(&bars->fullB[st]), ph)) {
+                            tc_fence_after();
+                            const uint32_t b_base = smem_u32(ringB + st * kRingBStageBytes);
+                            const uint32_t idesc = make_idesc<kBf16>(kTileRows, op.n);
+                            const int n_st = op.seg ? segs.n_seg : 1;
+                            if (op.seg) {
+                                uint32_t m[4];
+                                segs.mask(d_seg, m, a.mask_invert != 0);
+                                for (int kb = 0; kb < op.kb; ++kb)
+                                    umma_kblock_masked(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u,
+                                                       idesc, kb > 0, m);
+                            } else {
+                                for (int kb = 0; kb < op.kb; ++kb)
+                                    umma_kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u, idesc,
+                                                op.accumulate || kb > 0);
+                            }
+                            umma_commit(smem_u32(&bars->emptyB[st]));
+                            ++itB;
+                            if (++d_seg == n_st) {
+                                if (op.commit != 255) umma_commit(smem_u32(&bars->d_ready[op.commit]));
+                                ++d_idx, d_seg = 0, d_waited = false;
+                            }
+                            progressed = true;
+                        }
+                    }
+                }
+                if (!progressed && s_idx < a.n_s && s_idx < s_allowed) {
+                    const uint32_t st = itA % kRingAStages, ph = (itA / kRingAStages) & 1u;
+                    if (mbar_test(smem_u32(&bars->fullA[st]), ph)) {
+                        tc_fence_after();
+                        const uint32_t stage = smem_u32(ringA + st * kStageBytes);
+                        umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, s_stage > 0);
+                        umma_commit(smem_u32(&bars->emptyA[st]));
+                        ++itA;
+                        if (++s_stage == kSopStages) {
+                            umma_commit(smem_u32(&bars->d_ready[0]));
+                            ++s_idx, s_stage = 0;
+                        }
+                        progressed = true;
+                    }
+                }
+                if (!progressed) __nanosleep(20);
+            }
+        }
     } else {
         const uint32_t lq = warp & 3, cq = warp >> 2;
         const uint32_t r = lq * 32 + lane;            // row of the tile == TMEM lane
@@ -425,24 +599,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
         }
 
         if (a.do_main) {
-            // ================= self-attention tail: y = q . A_sa ; h += Styl(y)
-            {
-                const uint4* qrow = reinterpret_cast<const uint4*>(a.q + (size_t)g * kD + c0);
-                const float* Ab = a.A_sa + (size_t)b * (kH * 256) + (2 * cq) * 256;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float qv[16];
-                    uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
-                    if (valid) u0 = qrow[2 * hh], u1 = qrow[2 * hh + 1];
-                    const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 f = unpack2<kBf16>(uu[i]);
-                        qv[2 * i] = f.x, qv[2 * i + 1] = f.y;
-                    }
-                    head_apply(qv, Ab + hh * 256, v + 16 * hh);
-                }
-            }
+            // ================= self-attention tail: y = q . blockdiag(A_sa) (tensor cores) ; h += Styl(y)
+            rows_wait(bars, 2, ph[2]);
+            tmem_ld32(trow + kColW + c0, v);
+            tmem_wait_ld();
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_sa
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
@@ -462,18 +622,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             tmem_wait_st();
             rows_publish(bars);                                          // -> W = LN(h) . Wq_ca
             rows_wait(bars, 2, ph[2]);
-            {
-                float qv[32];
-                tmem_ld32(trow + kColW + c0, qv);
-                tmem_wait_ld();
-                add_bias32(qv, prm + kPrmCaBq + c0);
-                const float* Ab = a.A_ca + (size_t)b * a.a_ca_stride + (2 * cq) * 256;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    softmax16(qv + 16 * hh);
-                    head_apply(qv + 16 * hh, Ab + hh * 256, v + 16 * hh);
-                }
-            }
+            tmem_ld32(trow + kColW + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm + kPrmCaBq + c0);
+            softmax16(v);
+            softmax16(v + 16);
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+            rows_publish(bars);                                          // -> W = softmax(q) . blockdiag(A_ca)
+            rows_wait(bars, 2, ph[2]);
+            tmem_ld32(trow + kColW + c0, v);
+            tmem_wait_ld();
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_ca
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
@@ -530,19 +689,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             rows_publish(bars);
             rows_wait(bars, 2, ph[2]);
             const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
-            // q: softmax over head-dim, stored 16-bit
+            // q: softmax over head-dim, written as this tile's packed A-operand image for the next launch
             tmem_ld32(trow + kColS + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm_sa + kPrmSaBq + c0);
             softmax16(v);
             softmax16(v + 16);
             if (valid) {
-                uint32_t p[16];
+                uint8_t* qi = a.q_img + (size_t)blockIdx.x * kAworkBytes + (c0 >> 6) * kABlockBytes;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) p[i] = pack2<kBf16>(v[2 * i], v[2 * i + 1]);
-                uint4* dst = reinterpret_cast<uint4*>(a.q + (size_t)g * kD + c0);
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t p[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+                    for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(v[8 * ch + 2 * i], v[8 * ch + 2 * i + 1]);
+                    *reinterpret_cast<uint4*>(qi + sw128_offset(r, ((c0 & 63) >> 3) + ch)) = make_uint4(p[0], p[1], p[2], p[3]);
+                }
             }
             // k (masked frames get -1e6 before the time softmax), v (masked frames zeroed): reference :107,:114
             tmem_ld32(trow + kColS + 128 + c0, v);
@@ -568,11 +729,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             }
         }
     }
-    tile_teardown(bars, warp);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
 }
 
 constexpr int kGemmSmemBytes = kStages * kStageBytes + sizeof(TileBarriers) + 1024;
-constexpr int kLayerSmemBytes =
-    kStages * kStageBytes + kAworkBytes + (kPrmFloats + 384) * 4 + 1024 * 8 + sizeof(TileBarriers) + 1024;
+constexpr int kLayerSmemBytes = kRingAStages * kStageBytes + kRingBStages * kRingBStageBytes + kAworkBytes +
+                                (kPrmFloats + 384) * 4 + 1024 * 8 + sizeof(LayerBarriers) + 1024;
 
 }  // namespace dc

@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25
+if [ "${TRY_INVERT:-0}" = "1" ]; then echo "=== pytest small with DC_MASK_INVERT=1"; DC_MASK_INVERT=1 timeout 300 python -m pytest tests -x -q -m gpu -k "forward_small" 2>&1 | tail -5; fi
 echo "=== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5
 echo "=== bench ours"; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_ours.json
 echo "=== bench C3"; timeout 900 python bench.py --steps 3 --warmup 3 --workload C3 --no-cpu-baseline 2>&1 | tail -2 | tee gpurun_out/bench_c3.json
@@ -16,5 +17,7 @@ echo "=== ncu full (layer kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:layer_kernel -s 30 -c 2 -f -o gpurun_out/layer_full \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 tail -3 gpurun_out/ncu_full_run.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kv_reduce -s 30 -c 1 -f -o gpurun_out/kvreduce_full \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run2.log 2>&1
 ls -la gpurun_out | head -30
 fi
