@@ -19,7 +19,7 @@ DC_FLAG_CLIP = 0x10
 EXPORTS = [
     "dc_last_error", "dc_create", "dc_destroy", "dc_set_weight", "dc_finalize_weights", "dc_set_schedule",
     "dc_prepare_cond", "dc_forward", "dc_sample_step", "dc_sampler_update", "dc_sample_loop", "dc_generate_host",
-    "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step",
+    "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step", "dc_debug_timeline",
 ]
 
 
@@ -58,6 +58,7 @@ def load() -> C.CDLL:
     lib.dc_sample_loop.argtypes = [vp, i32, fp, fp, fp, fp, vp]
     lib.dc_generate_host.argtypes = [vp, i32, fp, fp, C.POINTER(i64), fp, fp, i32, i32, vp]
     lib.dc_profile_step.argtypes = [vp, i32, fp, i32, C.POINTER(C.c_float), C.POINTER(i32), vp]
+    lib.dc_debug_timeline.argtypes = [vp, fp, i32, C.POINTER(C.c_uint64), i32]
     lib.dc_kernel_launches.restype = i64
     lib.dc_kernel_launches.argtypes = [vp]
     lib.dc_set_graphs.argtypes = [vp, i32]

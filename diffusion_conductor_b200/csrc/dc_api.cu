@@ -92,6 +92,8 @@ struct dc_handle {
     uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
     uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
     int mask_invert = 0;
+    unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
+    bool timeline_on = false;
     long long* length = nullptr;
     bool has_length = false;
     float* te_b = nullptr;        // [B][512]
@@ -322,6 +324,7 @@ LayerArgs layer_args(dc_handle* h, int l) {
     a.bd_ca = h->bd_ca + (size_t)(l >= 0 ? l : 0) * kAworkBytes;
     a.bd_ca_stride = (size_t)L * kAworkBytes;
     a.length = h->has_length ? h->length : nullptr;
+    a.timeline = h->timeline_on ? h->timeline + (size_t)(l + 1) * 512 : nullptr;
     return a;
 }
 
@@ -416,7 +419,7 @@ void dc_destroy(dc_handle* h) {
     drop_graph(h);
     free_workspace(h);
     void* ptrs[] = {h->wbuf, h->prm, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
-                    h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr};
+                    h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -806,6 +809,23 @@ int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out
     h->prof_cls.clear();
     if (rc) return rc;
     DC_CUDA(h, e);
+    return 0;
+}
+
+int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out, int max_launches) {
+    if (int rc = check_sampling(h, DC_SAMPLER_DDIM, "dc_debug_timeline")) return rc;
+    if (!x || !out || max_launches < 1) return fail(h, DC_ERR_INVALID, "dc_debug_timeline: bad argument");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int n = std::min(max_launches, h->cfg.num_layers + 1);
+    if (!h->timeline) DC_CUDA(h, cudaMalloc((void**)&h->timeline, (size_t)(h->cfg.num_layers + 1) * 512 * 8));
+    DC_CUDA(h, cudaMemset(h->timeline, 0, (size_t)(h->cfg.num_layers + 1) * 512 * 8));
+    set_step_kernel<<<1, 1>>>(h->step_ctr, step, 0);
+    h->timeline_on = true;
+    const int rc = enqueue_step(h, x, h->te_table, 0, true, DC_SAMPLER_DDIM, x, h->x0work, nullptr, 0, 0, nullptr, 0);
+    h->timeline_on = false;
+    if (rc) return rc;
+    DC_CUDA(h, cudaDeviceSynchronize());
+    DC_CUDA(h, cudaMemcpy(out, h->timeline, (size_t)n * 512 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -253,12 +253,15 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 template <bool kBf16>
 __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv, int ld, int T,
                                                          uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride) {
+    // 256 threads = 4 token groups x 64 threads; each thread owns a 2x2 block (d0..d0+1, l0..l0+1) of the
+    // 16x16 result and a quarter of every 128-token chunk, so one LDS.64 pair feeds four FMAs.
     constexpr int TT = 128;                 // tokens per shared-memory chunk
-    constexpr int U = TT / 16;              // independent loads per thread per chunk
-    __shared__ float ek[TT][kHd + 1];
-    __shared__ float vv[TT][kHd + 1];
+    constexpr int U = TT / 16;              // independent global loads per thread per chunk
+    __shared__ __align__(16) float ek[TT][kHd];
+    __shared__ __align__(16) float vv[TT][kHd];
     __shared__ float red[16][kHd + 1];
     __shared__ float cmax[kHd];
+    __shared__ float part[4][kHd * kHd + kHd];
     const int b = blockIdx.x / kH, hh = blockIdx.x % kH;
     const int tid = threadIdx.x;
     const int c = tid & 15, tl = tid >> 4;
@@ -285,8 +288,9 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
     }
     __syncthreads();
     // pass 2: exp, column sums and the 16x16 outer-product accumulation through shared memory
-    const int d = tid >> 4, l = tid & 15;
-    float acc = 0.f, se = 0.f;
+    const int grp = tid >> 6, sub = tid & 63;
+    const int d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
     const float mc = cmax[c];
     for (int t0 = 0; t0 < T; t0 += TT) {
         float xk[U], xv[U];
@@ -303,14 +307,23 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
         }
         __syncthreads();
         const int n = min(TT, T - t0);
-#pragma unroll 8
-        for (int tt = 0; tt < n; ++tt) {
-            const float e = ek[tt][d];
-            acc = fmaf(e, vv[tt][l], acc);
-            se += e;
+#pragma unroll 4
+        for (int tt = grp; tt < n; tt += 4) {
+            const float2 e = *reinterpret_cast<const float2*>(&ek[tt][d0]);
+            const float2 v = *reinterpret_cast<const float2*>(&vv[tt][l0]);
+            a00 = fmaf(e.x, v.x, a00), a01 = fmaf(e.x, v.y, a01);
+            a10 = fmaf(e.y, v.x, a10), a11 = fmaf(e.y, v.y, a11);
+            s0 += e.x, s1 += e.y;
         }
         __syncthreads();
     }
+    float* pp = part[grp];
+    pp[d0 * 16 + l0] = a00, pp[d0 * 16 + l0 + 1] = a01, pp[(d0 + 1) * 16 + l0] = a10, pp[(d0 + 1) * 16 + l0 + 1] = a11;
+    if (l0 == 0) pp[256 + d0] = s0, pp[256 + d0 + 1] = s1;
+    __syncthreads();
+    const int d = tid >> 4, l = tid & 15;
+    const float acc = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    const float se = (part[0][256 + d] + part[1][256 + d]) + (part[2][256 + d] + part[3][256 + d]);
     const int ki = hh * kHd + d, nj = hh * kHd + l;
     const size_t off = (size_t)b * bd_stride + (size_t)(ki >> 6) * kABlockBytes + sw128_offset(nj, (ki & 63) >> 3) + (ki & 7) * 2;
     *reinterpret_cast<uint16_t*>(bd + off) = pack1<kBf16>(acc / se);

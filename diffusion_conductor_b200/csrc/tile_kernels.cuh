@@ -282,7 +282,19 @@ struct LayerArgs {
     const uint8_t* bd_ca;   // cross-attention counterpart of layer l; clip stride bd_ca_stride bytes
     size_t bd_ca_stride;
     const long long* length;  // [B] or null (all frames valid)
+    unsigned long long* timeline;   // debug: [0] = event count, then (clock64, id) pairs of CTA 0; null = off
 };
+
+// debug timeline of CTA 0 (one writer lane per role)
+__device__ __forceinline__ void tl_mark(const LayerArgs& a, unsigned long long id) {
+    if (a.timeline != nullptr && blockIdx.x == 0) {
+        const unsigned long long slot = atomicAdd(a.timeline, 1ull);
+        if (slot < 254) {
+            a.timeline[1 + 2 * slot] = (unsigned long long)clock64();
+            a.timeline[2 + 2 * slot] = id;
+        }
+    }
+}
 
 template <bool kFast>
 __device__ __forceinline__ float silu_f(float v) {
@@ -456,6 +468,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    if (threadIdx.x == 0) tl_mark(a, 1);
 
     if (warp == kProducerWarp) {
         // ---------------- ring A: A_emb k-blocks + FiLM projection weights
@@ -545,6 +558,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                             }
                             umma_commit(smem_u32(&bars->emptyB[st]));
                             ++itB;
+                            tl_mark(a, 200 + d_idx);
                             if (++d_seg == n_st) {
                                 if (op.commit != 255) umma_commit(smem_u32(&bars->d_ready[op.commit]));
                                 ++d_idx, d_seg = 0, d_waited = false;
@@ -561,7 +575,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, s_stage > 0);
                         umma_commit(smem_u32(&bars->emptyA[st]));
                         ++itA;
+                        if (s_stage == 0) tl_mark(a, 300 + s_idx);
                         if (++s_stage == kSopStages) {
+                            tl_mark(a, 310 + s_idx);
                             umma_commit(smem_u32(&bars->d_ready[0]));
                             ++s_idx, s_stage = 0;
                         }
@@ -600,16 +616,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
 
         if (a.do_main) {
             // ================= self-attention tail: y = q . blockdiag(A_sa) (tensor cores) ; h += Styl(y)
-            rows_wait(bars, 2, ph[2]);
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 101);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             row_stats32(rs, v, mean, rstd);
-            rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_sa
+            rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 102);                                   // S = A_emb . We_sa
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
-            rows_publish(bars);                                          // -> h += A . Wo_sa
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
 
             // ================= cross-attention
-            rows_wait(bars, 1, ph[1]);
+            rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
             tmem_ld32(trow + kColH + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm + kPrmStSa + kStBo + c0);                  // deferred bias of Wo_sa
@@ -620,8 +636,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(bars);                                          // -> W = LN(h) . Wq_ca
-            rows_wait(bars, 2, ph[2]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm + kPrmCaBq + c0);
@@ -629,17 +645,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             softmax16(v + 16);
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(bars);                                          // -> W = softmax(q) . blockdiag(A_ca)
-            rows_wait(bars, 2, ph[2]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             row_stats32(rs, v, mean, rstd);
-            rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_ca
+            rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 106);                                   // S = A_emb . We_ca
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
-            rows_publish(bars);                                          // -> h += A . Wo_ca
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
 
             // ================= FFN (no pre-norm, reference transformer.py:170-173)
-            rows_wait(bars, 1, ph[1]);
+            rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
             tmem_ld32(trow + kColH + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm + kPrmStCa + kStBo + c0);                  // deferred bias of Wo_ca
@@ -647,8 +663,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(bars);                                          // -> W[0:64] = h . W1
-            rows_wait(bars, 2, ph[2]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
             {
                 float u[16];                                             // hidden 64 = 4 quarters of 16
                 tmem_ld16(trow + kColW + 16 * cq, u);
@@ -657,16 +673,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
                 store_a16<kBf16>(awork, r, 16 * cq, u);
             }
-            rows_publish(bars);                                          // -> W = GELU(.) . W2
-            rows_wait(bars, 2, ph[2]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm + kPrmFfB2 + c0);
             row_stats32(rs, v, mean, rstd);
-            rows_wait(bars, 0, ph[0]);                                   // S = A_emb . We_ffn
+            rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
-            rows_publish(bars);                                          // -> h += A . Wo_ffn
-            rows_wait(bars, 1, ph[1]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
+            rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
         }
 
         // ---- final value of the residual stream for this launch (deferred bias of the last FFN block)
@@ -686,8 +702,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq/Wk/Wv
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(bars);
-            rows_wait(bars, 2, ph[2]);
+            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 158);
+            rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 112);
             const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
             // q: softmax over head-dim, written as this tile's packed A-operand image for the next launch
             tmem_ld32(trow + kColS + c0, v);
@@ -729,6 +745,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             }
         }
     }
+    if (threadIdx.x == 0) tl_mark(a, 2);
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {

@@ -112,6 +112,10 @@ int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const floa
  * [3] out_update.  x is updated in place like dc_sample_step. */
 int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out, int* count_out, void* stream);
 
+/* Debug aid: runs one denoise step with the layer kernel recording a (clock64, event id) timeline of its
+ * CTA 0; out is HOST [max_launches][512] u64: per launch [0] = event count, then (cycle, id) pairs. */
+int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out, int max_launches);
+
 /* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
 int64_t dc_kernel_launches(const dc_handle* h);
 /* 1 = replay captured CUDA graphs in dc_sample_loop (default), 0 = plain launches (profiling). */
