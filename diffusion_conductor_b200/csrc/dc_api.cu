@@ -194,7 +194,7 @@ const HostTensor* get(dc_handle* h, const std::string& key, std::initializer_lis
 }
 
 DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bool acc, int wait, int commit, int seg = 0,
-             bool releases_s = false) {
+             bool releases_s = false, bool ring_a = false) {
     DOp o{};
     o.w_off = w_off;
     o.w_bytes = w_bytes;
@@ -206,6 +206,7 @@ DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bo
     o.commit = (uint8_t)commit;
     o.seg = (uint8_t)seg;
     o.releases_s = releases_s;
+    o.ring_a = ring_a;
     return o;
 }
 
@@ -306,8 +307,8 @@ LayerArgs layer_args(dc_handle* h, int l) {
     if (a.do_sa1) {
         const uint32_t base = (uint32_t)(l + 1) * kLayerSlab;
         a.dops[n++] = make_dop(base + kOffWq, 32768, 2, 128, kColS, false, 1, 255);
-        a.dops[n++] = make_dop(base + kOffWk, 32768, 2, 128, kColS + 128, false, 0, 255);
-        a.dops[n++] = make_dop(base + kOffWv, 32768, 2, 128, kColW, false, 0, 2);
+        a.dops[n++] = make_dop(base + kOffWk, 32768, 2, 128, kColS + 128, false, 0, 255, 0, false, true);
+        a.dops[n++] = make_dop(base + kOffWv, 32768, 2, 128, kColW, false, 0, 2, 0, false, true);
     }
     a.n_d = n;
     a.M = h->M;
@@ -359,8 +360,8 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         h->launches++;
         mark(1);
         if (l + 1 < L) {
-            if (h->bf16) kv_reduce_kernel<true><<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->bd_sa, (size_t)kAworkBytes);
-            else kv_reduce_kernel<false><<<h->B * kH, 256, 0, st>>>(h->kv, 256, h->T, h->bd_sa, (size_t)kAworkBytes);
+            if (h->bf16) kv_reduce_kernel<true><<<h->B * kH, 256, 0, st>>>(h->kv, h->T, h->bd_sa, (size_t)kAworkBytes);
+            else kv_reduce_kernel<false><<<h->B * kH, 256, 0, st>>>(h->kv, h->T, h->bd_sa, (size_t)kAworkBytes);
             h->launches++;
             mark(2);
         }
@@ -647,13 +648,13 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         ga.w_img = h->wkv + (size_t)l * 8 * 32768;
         ga.bias = h->bkv + (size_t)l * 256;
         ga.out = h->kv;
-        ga.M = h->M, ga.N = 256, ga.kblocks = 8, ga.ldo = 256;
+        ga.M = h->M, ga.N = 256, ga.kblocks = 8, ga.ldo = 256, ga.blocked = 1;
         const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st) : launch_gemm_rows<false>(h, ga, h->tiles, st);
         if (rc) return rc;
         if (h->bf16)
-            kv_reduce_kernel<true><<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
+            kv_reduce_kernel<true><<<B * kH, 256, 0, st>>>(h->kv, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
         else
-            kv_reduce_kernel<false><<<B * kH, 256, 0, st>>>(h->kv, 256, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
+            kv_reduce_kernel<false><<<B * kH, 256, 0, st>>>(h->kv, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
         h->launches += 2;
     }
     DC_CUDA(h, cudaGetLastError());

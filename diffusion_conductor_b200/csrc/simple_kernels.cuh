@@ -16,6 +16,13 @@ constexpr int kP = 26;      // input_feats (13 joints x 2)
 constexpr int kMusic = 64;  // music-encoder feature width
 constexpr float kLnEps = 1e-5f;
 
+// "Blocked" activation layout used for h [*,128] and k|v [*,256]: per 128-token tile, 16-byte column chunks are
+// the slow index and rows the fast one -- [tile][ncols/4][128 rows][4 floats] -- so that a warp whose lanes are
+// 32 consecutive rows reads / writes 512 contiguous bytes per 128-bit instruction.
+__device__ __host__ __forceinline__ size_t blk_index(long g, int col, int ncols) {
+    return (size_t)(g >> 7) * (size_t)(128 * ncols) + (size_t)(col >> 2) * 512 + (size_t)(g & 127) * 4 + (col & 3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Weight packing: fp32 [N_src, K_src] (torch Linear layout) -> 16-bit K-major SW128 image
 //   dst[kb][n][...] with kb = k / 64, one block = Nrows x 128 bytes.
@@ -237,80 +244,87 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 #pragma unroll
     for (int tk = 0; tk < TOK; ++tk) {
         const long g = g0 + tk;
-        if (g < M) h[g * kD + j] = acc[tk] + pos[(size_t)(g % T) * kD + j];
+        if (g < M) h[blk_index(g, j, kD)] = acc[tk] + pos[(size_t)(g % T) * kD + j];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Time-axis softmax and K^T V (reference transformer.py:111,117 / 151,155):
 //   A[b,h,d,l] = sum_t softmax_t(k[b,t,h,d]) * v[b,t,h,l]
-// kv is [M][ld] fp32 with k in columns [0,128) and v in [128,256).  One block per (clip, head),
+// kv is fp32 [*,256] in the blocked layout with k in columns [0,128) and v in [128,256).  One block per (clip, head),
 // 256 threads = (d,l) pairs.  Two passes over the clip's 16 key columns: max, then exp/sum/outer
 // product through shared memory.  All fp32.  The result is written as the 16x16 diagonal block of
 // head h in a packed 16-bit B-operand image Bd[n = 16h+l][k = 16h+d] (off-diagonal blocks stay zero),
 // so that y = q . blockdiag(A) runs on the tensor cores in the layer kernel.
 // ---------------------------------------------------------------------------------------------
 template <bool kBf16>
-__global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv, int ld, int T,
+__global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv /*blocked [*,256]*/, int T,
                                                          uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride) {
-    // 256 threads = 4 token groups x 64 threads; each thread owns a 2x2 block (d0..d0+1, l0..l0+1) of the
-    // 16x16 result and a quarter of every 128-token chunk, so one LDS.64 pair feeds four FMAs.
-    constexpr int TT = 128;                 // tokens per shared-memory chunk
-    constexpr int U = TT / 16;              // independent global loads per thread per chunk
+    // loads: thread = (column chunk q of the head's 16 key/value columns, token lane) -> float4, 32 consecutive
+    //        tokens per warp = 512 contiguous bytes of the blocked layout.
+    // accumulation: 4 token groups x 64 threads, each thread a 2x2 block of the 16x16 result.
+    constexpr int TT = 128;
     __shared__ __align__(16) float ek[TT][kHd];
     __shared__ __align__(16) float vv[TT][kHd];
-    __shared__ float red[16][kHd + 1];
+    __shared__ float red[8][4];
     __shared__ float cmax[kHd];
     __shared__ float part[4][kHd * kHd + kHd];
     const int b = blockIdx.x / kH, hh = blockIdx.x % kH;
-    const int tid = threadIdx.x;
-    const int c = tid & 15, tl = tid >> 4;
-    const float* base = kv + (size_t)b * T * ld + hh * kHd + c;
-    // pass 1: column max over the clip (U independent loads in flight per thread)
-    float m = -INFINITY;
-    for (int t0 = 0; t0 < T; t0 += TT) {
-        float x[U];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q = tid >> 6, tt = tid & 63;
+    const long g0 = (long)b * T;
+    const int kcol = hh * kHd + 4 * q;
+    // pass 1: column max over the clip
+    float4 m4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        float4 x[4];
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const int t = t0 + tl + 16 * i;
-            x[i] = t < T ? __ldg(base + (size_t)t * ld) : -INFINITY;
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + tt + 64 * i;
+            x[i] = t < T ? __ldg(reinterpret_cast<const float4*>(kv + blk_index(g0 + t, kcol, 256))) : m4;
         }
 #pragma unroll
-        for (int i = 0; i < U; ++i) m = fmaxf(m, x[i]);
+        for (int i = 0; i < 4; ++i)
+            m4.x = fmaxf(m4.x, x[i].x), m4.y = fmaxf(m4.y, x[i].y), m4.z = fmaxf(m4.z, x[i].z), m4.w = fmaxf(m4.w, x[i].w);
     }
-    red[tl][c] = m;
-    __syncthreads();
-    if (tid < kHd) {
-        float mm = red[0][tid];
 #pragma unroll
-        for (int i = 1; i < 16; ++i) mm = fmaxf(mm, red[i][tid]);
-        cmax[tid] = mm;
+    for (int o = 16; o; o >>= 1) {
+        m4.x = fmaxf(m4.x, __shfl_xor_sync(0xffffffffu, m4.x, o));
+        m4.y = fmaxf(m4.y, __shfl_xor_sync(0xffffffffu, m4.y, o));
+        m4.z = fmaxf(m4.z, __shfl_xor_sync(0xffffffffu, m4.z, o));
+        m4.w = fmaxf(m4.w, __shfl_xor_sync(0xffffffffu, m4.w, o));
     }
+    if (lane == 0) red[wid][0] = m4.x, red[wid][1] = m4.y, red[wid][2] = m4.z, red[wid][3] = m4.w;
     __syncthreads();
+    if (tid < kHd) cmax[tid] = fmaxf(red[2 * (tid >> 2)][tid & 3], red[2 * (tid >> 2) + 1][tid & 3]);
+    __syncthreads();
+    const float4 mc = *reinterpret_cast<const float4*>(&cmax[4 * q]);
     // pass 2: exp, column sums and the 16x16 outer-product accumulation through shared memory
     const int grp = tid >> 6, sub = tid & 63;
     const int d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
-    const float mc = cmax[c];
     for (int t0 = 0; t0 < T; t0 += TT) {
-        float xk[U], xv[U];
+        float4 xk[2], xv[2];
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const int t = t0 + tl + 16 * i;
-            xk[i] = t < T ? __ldg(base + (size_t)t * ld) : -INFINITY;
-            xv[i] = t < T ? __ldg(base + (size_t)t * ld + kD) : 0.f;
+        for (int i = 0; i < 2; ++i) {
+            const int t = t0 + tt + 64 * i;
+            const bool ok = t < T;
+            const float* p = kv + blk_index(g0 + (ok ? t : 0), kcol, 256);
+            xk[i] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            xv[i] = ok ? __ldg(reinterpret_cast<const float4*>(p + 32 * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);   // v = column + 128
         }
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-            ek[tl + 16 * i][c] = expf(xk[i] - mc);          // exp(-inf) = 0 for the padded tail
-            vv[tl + 16 * i][c] = xv[i];
+        for (int i = 0; i < 2; ++i) {                            // exp(-inf) = 0 for the padded tail
+            *reinterpret_cast<float4*>(&ek[tt + 64 * i][4 * q]) =
+                make_float4(expf(xk[i].x - mc.x), expf(xk[i].y - mc.y), expf(xk[i].z - mc.z), expf(xk[i].w - mc.w));
+            *reinterpret_cast<float4*>(&vv[tt + 64 * i][4 * q]) = xv[i];
         }
         __syncthreads();
         const int n = min(TT, T - t0);
 #pragma unroll 4
-        for (int tt = grp; tt < n; tt += 4) {
-            const float2 e = *reinterpret_cast<const float2*>(&ek[tt][d0]);
-            const float2 v = *reinterpret_cast<const float2*>(&vv[tt][l0]);
+        for (int k = grp; k < n; k += 4) {
+            const float2 e = *reinterpret_cast<const float2*>(&ek[k][d0]);
+            const float2 v = *reinterpret_cast<const float2*>(&vv[k][l0]);
             a00 = fmaf(e.x, v.x, a00), a01 = fmaf(e.x, v.y, a01);
             a10 = fmaf(e.y, v.x, a10), a11 = fmaf(e.y, v.y, a11);
             s0 += e.x, s1 += e.y;
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(256) out_update_kernel(const float* __restrict
     const long g0 = (long)blockIdx.x * TOK;
     for (int i = threadIdx.x; i < TOK * kD; i += 256) {
         const long g = g0 + i / kD;
-        hs[i / kD][i % kD] = g < M ? h[g * kD + (i % kD)] : 0.f;
+        hs[i / kD][i % kD] = g < M ? h[blk_index(g, i % kD, kD)] : 0.f;
     }
     __syncthreads();
     const int tk = threadIdx.x >> 5, p = threadIdx.x & 31;

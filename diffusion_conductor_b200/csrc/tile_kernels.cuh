@@ -145,6 +145,7 @@ struct GemmRowsArgs {
     const float* bias;      // [N] or null
     float* out;
     int M, N, kblocks, ldo;
+    int blocked;            // 1: out is in the blocked activation layout with N columns (ldo ignored)
 };
 
 template <bool kBf16>
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
             tmem_ld16(trow + c, v);
             tmem_wait_ld();
             if (g < a.M) {
-                float4* dst = reinterpret_cast<float4*>(a.out + (size_t)g * a.ldo + c);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    float4* dst = reinterpret_cast<float4*>(a.blocked ? a.out + blk_index(g, c + 4 * i, a.N) : a.out + (size_t)g * a.ldo + c + 4 * i);
                     float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     if (a.bias) {
                         o.x += a.bias[c + 4 * i];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
                         o.z += a.bias[c + 4 * i + 2];
                         o.w += a.bias[c + 4 * i + 3];
                     }
-                    dst[i] = o;
+                    *dst = o;
                 }
             }
         }
@@ -247,7 +248,8 @@ struct DOp {
     uint8_t seg;           // 0: plain; 1 / 2: one lane-masked GEMM per clip segment of the tile with that clip's
                            //    block-diagonal self- / cross-attention matrix as B operand
     uint8_t releases_s;    // passing this op's wait means the row threads are done with the S accumulator
-    uint8_t pad[2];
+    uint8_t ring_a;        // 1: weights travel through ring A (idle once the FiLM projections are done) instead of ring B
+    uint8_t pad;
 };
 
 constexpr int kMaxDOps = 12;
@@ -487,6 +489,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                     bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kStageWBytes, full);
                 }
             }
+            for (int o = 0; o < a.n_d; ++o) {
+                const DOp op = a.dops[o];
+                if (!op.ring_a) continue;
+                const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                ++it;
+                mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bars->fullA[st]);
+                mbar_arrive_expect_tx(full, op.w_bytes);
+                bulk_g2s(smem_u32(ringA + st * kStageBytes + kStageABytes), a.wbuf + op.w_off, op.w_bytes, full);
+            }
         }
     } else if (warp == kProducerBWarp) {
         // ---------------- ring B: dependent-GEMM weights, per-clip attention matrices, the q image
@@ -501,6 +513,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             uint32_t it = 0;
             for (int o = 0; o < a.n_d; ++o) {
                 const DOp op = a.dops[o];
+                if (op.ring_a) continue;
                 const int n_st = op.seg ? segs.n_seg : 1;
                 for (int s = 0; s < n_st; ++s, ++it) {
                     const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
@@ -539,10 +552,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         }
                     }
                     if (d_waited) {
-                        const uint32_t st = itB % kRingBStages, ph = (itB / kRingBStages) & 1u;
-                        if (mbar_test(smem_u32(&bars->fullB[st]), ph)) {
+                        const uint32_t st = op.ring_a ? itA % kRingAStages : itB % kRingBStages;
+                        const uint32_t ph = op.ring_a ? (itA / kRingAStages) & 1u : (itB / kRingBStages) & 1u;
+                        if (mbar_test(smem_u32(op.ring_a ? &bars->fullA[st] : &bars->fullB[st]), ph)) {
                             tc_fence_after();
-                            const uint32_t b_base = smem_u32(ringB + st * kRingBStageBytes);
+                            const uint32_t b_base = op.ring_a ? smem_u32(ringA + st * kStageBytes + kStageABytes)
+                                                              : smem_u32(ringB + st * kRingBStageBytes);
                             const uint32_t idesc = make_idesc<kBf16>(kTileRows, op.n);
                             const int n_st = op.seg ? segs.n_seg : 1;
                             if (op.seg) {
@@ -556,8 +571,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                                     umma_kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u, idesc,
                                                 op.accumulate || kb > 0);
                             }
-                            umma_commit(smem_u32(&bars->emptyB[st]));
-                            ++itB;
+                            umma_commit(smem_u32(op.ring_a ? &bars->emptyA[st] : &bars->emptyB[st]));
+                            if (op.ring_a) ++itA;
+                            else ++itB;
                             tl_mark(a, 200 + d_idx);
                             if (++d_seg == n_st) {
                                 if (op.commit != 255) umma_commit(smem_u32(&bars->d_ready[op.commit]));
@@ -604,10 +620,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
 
         // ---- residual stream -> TMEM
         {
-            const float4* src = reinterpret_cast<const float4*>(a.h + (size_t)g * kD + c0);
+            const float4* src = reinterpret_cast<const float4*>(a.h + blk_index(g, c0, kD));      // chunk stride 512 floats
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 f = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 f = valid ? src[i * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
             }
             tmem_st32(trow + kColH + c0, v);
@@ -690,9 +706,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
         tmem_wait_ld();
         if (a.do_main) add_bias32(v, prm + kPrmStFf + kStBo + c0);
         if (valid) {
-            float4* dst = reinterpret_cast<float4*>(a.h + (size_t)g * kD + c0);
+            float4* dst = reinterpret_cast<float4*>(a.h + blk_index(g, c0, kD));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) dst[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
 
         if (a.do_sa1) {
@@ -711,38 +727,41 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             add_bias32(v, prm_sa + kPrmSaBq + c0);
             softmax16(v);
             softmax16(v + 16);
-            if (valid) {
-                uint8_t* qi = a.q_img + (size_t)blockIdx.x * kAworkBytes + (c0 >> 6) * kABlockBytes;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t p[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(v[8 * ch + 2 * i], v[8 * ch + 2 * i + 1]);
-                    *reinterpret_cast<uint4*>(qi + sw128_offset(r, ((c0 & 63) >> 3) + ch)) = make_uint4(p[0], p[1], p[2], p[3]);
-                }
+            // staged in the (now idle) operand buffer in exactly the image format, then one bulk store per tile
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+            fence_async_smem();
+            named_bar_sync(5, kRowThreads);
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.q_img + (size_t)blockIdx.x * kAworkBytes),
+                             "r"(awork), "r"((uint32_t)kAworkBytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             // k (masked frames get -1e6 before the time softmax), v (masked frames zeroed): reference :107,:114
             tmem_ld32(trow + kColS + 128 + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm_sa + kPrmSaBk + c0);
             if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.kv + (size_t)g * 256 + c0);
+                float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, c0, 256));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     if (!keep) o.x += -1000000.f, o.y += -1000000.f, o.z += -1000000.f, o.w += -1000000.f;
-                    dst[i] = o;
+                    dst[i * 128] = o;
                 }
             }
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             add_bias32(v, prm_sa + kPrmSaBv + c0);
             if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.kv + (size_t)g * 256 + kD + c0);
+                float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, kD + c0, 256));
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    dst[i] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[i * 128] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            // the q image must have left shared memory before the CTA exits
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
     if (threadIdx.x == 0) tl_mark(a, 2);
