@@ -105,6 +105,7 @@ struct dc_handle {
 
     // graphs
     bool use_graphs = true;
+    bool use_pdl = true;
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t gexec = nullptr;
     GraphKey gkey;
@@ -269,6 +270,23 @@ int init_kernel_attrs(dc_handle* h) {
     return 0;
 }
 
+// Launch with the programmatic-dependent-launch attribute: the kernel may be scheduled while its predecessor
+// in the stream drains; every kernel of the step calls griddepcontrol.wait before touching activations.
+template <class... KArgs, class... Args>
+cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <bool kBf16>
 int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream_t st) {
     gemm_rows_kernel<kBf16><<<tiles, kTileThreads, kGemmSmemBytes, st>>>(ga);
@@ -277,7 +295,7 @@ int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream
 
 template <bool kBf16>
 int launch_layer(dc_handle* h, const LayerArgs& la, int tiles, cudaStream_t st) {
-    layer_kernel<kBf16><<<tiles, kTileThreads, kLayerSmemBytes, st>>>(la);
+    DC_CUDA(h, launch_k(h->use_pdl, layer_kernel<kBf16>, dim3(tiles), dim3(kTileThreads), kLayerSmemBytes, st, la));
     return 0;
 }
 
@@ -345,12 +363,10 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         h->prof_cls.push_back(cls);
     };
     mark(-1);
-    if (h->bf16)
-        step_begin_kernel<true><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
-                                                         h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
-    else
-        step_begin_kernel<false><<<blocks8, 128, 0, st>>>(x_in, h->xp, te, te_from_ctr ? h->step_ctr : nullptr, te_stride, h->WjT,
-                                                          h->bj, h->pos, M, h->T, h->aemb, h->hbuf);
+    const int* ctr = te_from_ctr ? h->step_ctr : nullptr;
+    DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_begin_kernel<true> : step_begin_kernel<false>, dim3(blocks8), dim3(128), 0, st, x_in,
+                        (const float*)h->xp, te, ctr, te_stride, (const float*)h->WjT, (const float*)h->bj, (const float*)h->pos, M, h->T,
+                        h->aemb, h->hbuf));
     h->launches++;
     mark(0);
     for (int l = -1; l < L; ++l) {
@@ -360,13 +376,14 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         h->launches++;
         mark(1);
         if (l + 1 < L) {
-            if (h->bf16) kv_reduce_kernel<true><<<h->B * kH, 256, 0, st>>>(h->kv, h->T, h->bd_sa, (size_t)kAworkBytes);
-            else kv_reduce_kernel<false><<<h->B * kH, 256, 0, st>>>(h->kv, h->T, h->bd_sa, (size_t)kAworkBytes);
+            DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? kv_reduce_kernel<true> : kv_reduce_kernel<false>, dim3(h->B * kH), dim3(256), 0, st,
+                                (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes));
             h->launches++;
             mark(2);
         }
     }
-    out_update_kernel<<<blocks8, 256, 0, st>>>(h->hbuf, h->WoT, h->bo, M, mode, h->coef, h->step_ctr, noise, x_upd, x0_out);
+    DC_CUDA(h, launch_k(h->use_pdl, out_update_kernel, dim3(blocks8), dim3(256), 0, st, (const float*)h->hbuf, (const float*)h->WoT,
+                        (const float*)h->bo, M, mode, (const float*)h->coef, (const int*)h->step_ctr, noise, x_upd, x0_out));
     h->launches++;
     mark(3);
     (void)noise_stride, (void)trace_stride, (void)trace_x;
@@ -408,6 +425,8 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
     const char* mi = getenv("DC_MASK_INVERT");
     if (mi && mi[0] == '1') h->mask_invert = 1;
+    const char* np = getenv("DC_NO_PDL");
+    if (np && np[0] == '1') h->use_pdl = false;
     const char* ng = getenv("DC_NO_GRAPH");
     if (ng && ng[0] == '1') h->use_graphs = false;
     *out = h;
@@ -732,7 +751,7 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
             int rc = 0;
             for (int i = 0; i < key.steps && !rc; ++i) {
                 rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, 0, 0, nullptr, h->cap_stream);
-                set_step_kernel<<<1, 1, 0, h->cap_stream>>>(h->step_ctr, 0, -1);
+                launch_k(h->use_pdl, set_step_kernel, dim3(1), dim3(1), 0, h->cap_stream, h->step_ctr, 0, -1);
             }
             h->launches = before;
             cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);

@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
     __shared__ float xs[TOK][kP + 2];
     const int j = threadIdx.x;
     const long g0 = (long)blockIdx.x * TOK;
+    pdl_trigger();
+    pdl_wait();
     const float* te0 = te + (step_ctr ? (size_t)(*step_ctr) * kE : 0);
     for (int i = j; i < TOK * kP; i += 128) {
         const int tk = i / kP, c = i % kP;
@@ -274,6 +276,8 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
     const int q = tid >> 6, tt = tid & 63;
     const long g0 = (long)b * T;
     const int kcol = hh * kHd + 4 * q;
+    pdl_trigger();
+    pdl_wait();
     // pass 1: column max over the clip
     float4 m4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int t0 = 0; t0 < T; t0 += 256) {
@@ -372,6 +376,8 @@ __global__ void __launch_bounds__(256) out_update_kernel(const float* __restrict
     constexpr int TOK = 8;
     __shared__ float hs[TOK][kD];
     const long g0 = (long)blockIdx.x * TOK;
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < TOK * kD; i += 256) {
         const long g = g0 + i / kD;
         hs[i / kD][i % kD] = g < M ? h[blk_index(g, i % kD, kD)] : 0.f;
@@ -403,6 +409,10 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0, size_t n, in
     x[i] = (mode & 0xF) == 1 ? ddim_rule(x[i], x0[i], cf, nz) : ddpm_rule(x[i], x0[i], cf, nz);
 }
 
-__global__ void set_step_kernel(int* ctr, int value, int delta) { *ctr = delta ? *ctr + delta : value; }
+__global__ void set_step_kernel(int* ctr, int value, int delta) {
+    pdl_trigger();
+    pdl_wait();
+    *ctr = delta ? *ctr + delta : value;
+}
 
 }  // namespace dc

@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
     uint8_t* ring = smem;
     TileBarriers* bars = reinterpret_cast<TileBarriers*>(smem + kStages * kStageBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     tile_setup(bars, warp, lane);
+    pdl_wait();
     const uint32_t tmem_base = bars->tmem_base;
 
     __shared__ TileOp op;
@@ -231,14 +233,14 @@ constexpr int kStBe = 0, kStG = 256, kStB = 384, kStBo = 512;
 //            per-clip block-diagonal attention matrices.
 // The issuer polls both (dependent work first), so a short dependent GEMM never queues behind a long
 // FiLM projection.
-constexpr int kRingAStages = 2;
+constexpr int kRingAStages = 3;
 constexpr int kRingBStages = 2;
-constexpr int kRingBStageBytes = 32 * 1024;
+constexpr int kRingBStageBytes = 16 * 1024;     // one k-block (64) of a dependent GEMM's B operand
 constexpr int kSopStages = 8;
 
 struct DOp {
     uint32_t w_off;        // byte offset in the packed weight buffer (seg == 0)
-    uint32_t w_bytes;      // bytes of the ring-B stage
+    uint32_t w_bytes;      // bytes of the whole B operand (kb ring-B stages of w_bytes / kb each)
     uint16_t n;            // UMMA N
     uint16_t d_col;        // accumulator column
     uint8_t kb;            // k-blocks of 64
@@ -326,8 +328,7 @@ __device__ __forceinline__ void softmax16(float* q) {
 }
 
 // Row statistics over 128 features held as 4 x 32 registers by the 4 warps that share a row:
-// local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.  `flip` alternates
-// between two exchange buffers so consecutive calls need no second barrier.
+// local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.
 struct RowStats {
     float2* xchg;      // [2][4][128]
     uint32_t bar_id;   // 1 + lq
@@ -347,11 +348,11 @@ __device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float&
         const float d = v[i] - lm;
         m2 = fmaf(d, d, m2);
     }
-    float2* buf = rs.xchg + rs.flip * 512;
-    rs.flip ^= 1u;
+    float2* buf = rs.xchg;
     buf[rs.cq * 128 + rs.r] = make_float2(lm, m2);
     named_bar_sync(rs.bar_id, 128);
     const float2 p0 = buf[rs.r], p1 = buf[128 + rs.r], p2 = buf[256 + rs.r], p3 = buf[384 + rs.r];
+    named_bar_sync(rs.bar_id, 128);       // single exchange buffer: everyone has read before the next call writes
     mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
     const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
     const float M2 = (p0.y + p1.y) + (p2.y + p3.y) + 32.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
@@ -446,10 +447,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     uint8_t* awork_p = ringB + kRingBStages * kRingBStageBytes;
     float* prm = reinterpret_cast<float*>(awork_p + kAworkBytes);          // [kPrmFloats]
     float* prm_sa = prm + kPrmFloats;                                      // [384] SA biases of layer l+1
-    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);                // [2][4][128]
-    LayerBarriers* bars = reinterpret_cast<LayerBarriers*>(xchg + 1024);
+    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);                // [4][128]
+    LayerBarriers* bars = reinterpret_cast<LayerBarriers*>(xchg + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    pdl_trigger();
+    // prologue that touches only weights / on-chip state overlaps the previous kernel's tail
     if (a.do_main)
         for (int i = threadIdx.x; i < kPrmFloats; i += kTileThreads) prm[i] = a.prm[i];
     if (a.do_sa1)
@@ -470,6 +473,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
     if (threadIdx.x == 0) tl_mark(a, 1);
 
     if (warp == kProducerWarp) {
@@ -515,15 +519,18 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 const DOp op = a.dops[o];
                 if (op.ring_a) continue;
                 const int n_st = op.seg ? segs.n_seg : 1;
-                for (int s = 0; s < n_st; ++s, ++it) {
-                    const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
-                    mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
-                    const uint32_t full = smem_u32(&bars->fullB[st]);
+                const uint32_t kb_bytes = op.w_bytes / op.kb;
+                for (int s = 0; s < n_st; ++s) {
                     const uint8_t* src = op.seg == 0   ? a.wbuf + op.w_off
                                          : op.seg == 1 ? a.bd_sa + (size_t)(segs.first_clip + s) * kAworkBytes
                                                        : a.bd_ca + (size_t)(segs.first_clip + s) * a.bd_ca_stride;
-                    mbar_arrive_expect_tx(full, op.w_bytes);
-                    bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src, op.w_bytes, full);
+                    for (int kb = 0; kb < op.kb; ++kb, ++it) {
+                        const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
+                        mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
+                        const uint32_t full = smem_u32(&bars->fullB[st]);
+                        mbar_arrive_expect_tx(full, kb_bytes);
+                        bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src + (size_t)kb * kb_bytes, kb_bytes, full);
+                    }
                 }
             }
         }
@@ -535,7 +542,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
             const uint32_t awork = smem_u32(awork_p);
             uint32_t itA = 0, itB = 0, a_phase = 0;
-            int d_idx = 0, d_seg = 0, s_idx = 0, s_stage = 0, s_allowed = 1;
+            int d_idx = 0, d_seg = 0, d_kb = 0, s_idx = 0, s_stage = 0, s_allowed = 1;
             bool d_waited = false;
             while (d_idx < a.n_d || s_idx < a.n_s) {
                 bool progressed = false;
@@ -556,26 +563,35 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         const uint32_t ph = op.ring_a ? (itA / kRingAStages) & 1u : (itB / kRingBStages) & 1u;
                         if (mbar_test(smem_u32(op.ring_a ? &bars->fullA[st] : &bars->fullB[st]), ph)) {
                             tc_fence_after();
-                            const uint32_t b_base = op.ring_a ? smem_u32(ringA + st * kStageBytes + kStageABytes)
-                                                              : smem_u32(ringB + st * kRingBStageBytes);
                             const uint32_t idesc = make_idesc<kBf16>(kTileRows, op.n);
                             const int n_st = op.seg ? segs.n_seg : 1;
-                            if (op.seg) {
-                                uint32_t m[4];
-                                segs.mask(d_seg, m, a.mask_invert != 0);
-                                for (int kb = 0; kb < op.kb; ++kb)
-                                    umma_kblock_masked(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u,
-                                                       idesc, kb > 0, m);
-                            } else {
+                            bool op_done = false;
+                            if (op.ring_a) {            // whole operand in one ring-A stage
+                                const uint32_t b_base = smem_u32(ringA + st * kStageBytes + kStageABytes);
                                 for (int kb = 0; kb < op.kb; ++kb)
                                     umma_kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u, idesc,
                                                 op.accumulate || kb > 0);
+                                umma_commit(smem_u32(&bars->emptyA[st]));
+                                ++itA;
+                                op_done = true;
+                            } else {                    // one k-block per ring-B stage
+                                const uint32_t b_base = smem_u32(ringB + st * kRingBStageBytes);
+                                if (op.seg) {
+                                    uint32_t m[4];
+                                    segs.mask(d_seg, m, a.mask_invert != 0);
+                                    umma_kblock_masked(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, d_kb > 0, m);
+                                } else {
+                                    umma_kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, op.accumulate || d_kb > 0);
+                                }
+                                umma_commit(smem_u32(&bars->emptyB[st]));
+                                ++itB;
+                                if (++d_kb == op.kb) {
+                                    d_kb = 0;
+                                    if (++d_seg == n_st) op_done = true;
+                                }
                             }
-                            umma_commit(smem_u32(op.ring_a ? &bars->emptyA[st] : &bars->emptyB[st]));
-                            if (op.ring_a) ++itA;
-                            else ++itB;
-                            tl_mark(a, 200 + d_idx);
-                            if (++d_seg == n_st) {
+                            if (op_done) {
+                                tl_mark(a, 200 + d_idx);
                                 if (op.commit != 255) umma_commit(smem_u32(&bars->d_ready[op.commit]));
                                 ++d_idx, d_seg = 0, d_waited = false;
                             }
@@ -775,6 +791,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
 
 constexpr int kGemmSmemBytes = kStages * kStageBytes + sizeof(TileBarriers) + 1024;
 constexpr int kLayerSmemBytes = kRingAStages * kStageBytes + kRingBStages * kRingBStageBytes + kAworkBytes +
-                                (kPrmFloats + 384) * 4 + 1024 * 8 + sizeof(LayerBarriers) + 1024;
+                                (kPrmFloats + 384) * 4 + 512 * 8 + sizeof(LayerBarriers) + 1024;
+static_assert(kLayerSmemBytes <= 232448, "layer kernel exceeds the 227 KB shared-memory limit");
 
 }  // namespace dc
