@@ -105,7 +105,7 @@ struct dc_handle {
 
     // graphs
     bool use_graphs = true;
-    bool use_pdl = true;
+    bool use_pdl = false;          // measured slightly slower on C2 (r01): kernels cannot co-reside with the 213 KB layer CTA
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t gexec = nullptr;
     GraphKey gkey;
@@ -425,8 +425,9 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
     const char* mi = getenv("DC_MASK_INVERT");
     if (mi && mi[0] == '1') h->mask_invert = 1;
-    const char* np = getenv("DC_NO_PDL");
-    if (np && np[0] == '1') h->use_pdl = false;
+    if (mi && mi[0] == '2') h->mask_invert = 2;
+    const char* np = getenv("DC_PDL");
+    if (np && np[0] == '1') h->use_pdl = true;
     const char* ng = getenv("DC_NO_GRAPH");
     if (ng && ng[0] == '1') h->use_graphs = false;
     *out = h;
