@@ -92,6 +92,9 @@ struct dc_handle {
     uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
     uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
     int mask_invert = 0;
+    float* kv_part = nullptr;     // [tiles][2][kKvPartFloats] partial time-axis reductions
+    int* clip_cnt = nullptr;      // [B]
+    bool fuse_kv = false;
     unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
     bool timeline_on = false;
     long long* length = nullptr;
@@ -212,6 +215,9 @@ DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bo
 }
 
 void free_workspace(dc_handle* h) {
+    if (h->kv_part) cudaFree(h->kv_part);
+    if (h->clip_cnt) cudaFree(h->clip_cnt);
+    h->kv_part = nullptr, h->clip_cnt = nullptr;
     void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q_img, h->kv, h->bd_sa, h->bd_ca, h->length,
                     h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
     for (void* p : ptrs)
@@ -245,6 +251,9 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->bd_sa, (size_t)B * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->bd_ca, (size_t)B * L * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
+    DC_CUDA(h, cudaMalloc((void**)&h->kv_part, tiles * 2 * (size_t)kKvPartFloats * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->clip_cnt, (size_t)B * 4));
+    DC_CUDA(h, cudaMemset(h->clip_cnt, 0, (size_t)B * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->te_b, (size_t)B * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->xwork, Mpad * kP * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->x0work, Mpad * kP * 4));
@@ -343,6 +352,10 @@ LayerArgs layer_args(dc_handle* h, int l) {
     a.bd_ca = h->bd_ca + (size_t)(l >= 0 ? l : 0) * kAworkBytes;
     a.bd_ca_stride = (size_t)L * kAworkBytes;
     a.length = h->has_length ? h->length : nullptr;
+    a.fuse_kv = h->fuse_kv;
+    a.kv_part = h->kv_part;
+    a.clip_cnt = h->clip_cnt;
+    a.bd_sa_out = h->bd_sa;
     a.timeline = h->timeline_on ? h->timeline + (size_t)(l + 1) * 512 : nullptr;
     return a;
 }
@@ -375,7 +388,7 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         if (rc) return rc;
         h->launches++;
         mark(1);
-        if (l + 1 < L) {
+        if (l + 1 < L && !h->fuse_kv) {
             DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? kv_reduce_kernel<true> : kv_reduce_kernel<false>, dim3(h->B * kH), dim3(256), 0, st,
                                 (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes));
             h->launches++;
@@ -645,6 +658,13 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
     if (int rc = ensure_workspace(h, B, T)) return rc;
     if (h->B != B || h->T != T) drop_graph(h);
     h->B = B, h->T = T, h->M = B * T, h->tiles = (h->M + kTileRows - 1) / kTileRows;
+    {
+        const char* nf = getenv("DC_NO_FUSE_KV");
+        const bool fuse = T >= kTileRows && !(nf && nf[0] == '1');
+        if (fuse != h->fuse_kv) drop_graph(h);
+        h->fuse_kv = fuse;
+        DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)B * 4, st));
+    }
     bool masked = false;
     if (length) {
         for (int i = 0; i < B; ++i) {
@@ -739,7 +759,7 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
     DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
     set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
     h->launches++;
-    const int64_t per_step = 2 * (int64_t)h->cfg.num_layers + 4;
+    const int64_t per_step = (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
     if (h->use_graphs && !traced) {
         GraphKey key;
         key.sampler = sampler;

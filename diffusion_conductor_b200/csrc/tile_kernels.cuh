@@ -255,6 +255,7 @@ struct DOp {
 };
 
 constexpr int kMaxDOps = 12;
+constexpr int kKvPartFloats = 128 + 128 + kH * 256;
 constexpr int kMaxSOps = 3;
 
 struct LayerBarriers {
@@ -286,6 +287,10 @@ struct LayerArgs {
     const uint8_t* bd_ca;   // cross-attention counterpart of layer l; clip stride bd_ca_stride bytes
     size_t bd_ca_stride;
     const long long* length;  // [B] or null (all frames valid)
+    int fuse_kv;            // 1 (T >= 128): time-axis softmax + K^T V fused into this kernel's epilogue
+    float* kv_part;         // [tiles][2][kKvPartFloats] per (tile, clip segment): max[128] | sum[128] | K^T V [8][16][16]
+    int* clip_cnt;          // [B] arrival counters (zero between launches)
+    uint8_t* bd_sa_out;     // == bd_sa; written for the NEXT layer by the CTA that completes a clip
     unsigned long long* timeline;   // debug: [0] = event count, then (clock64, id) pairs of CTA 0; null = off
 };
 
@@ -760,26 +765,166 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             // k (masked frames get -1e6 before the time softmax), v (masked frames zeroed): reference :107,:114
-            tmem_ld32(trow + kColS + 128 + c0, v);
-            tmem_wait_ld();
-            add_bias32(v, prm_sa + kPrmSaBk + c0);
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, c0, 256));
+            if (!a.fuse_kv) {
+                // general path (T < 128: a tile may span many clips): k|v to global, reduced by kv_reduce_kernel
+                tmem_ld32(trow + kColS + 128 + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm_sa + kPrmSaBk + c0);
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, c0, 256));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (!keep) o.x += -1000000.f, o.y += -1000000.f, o.z += -1000000.f, o.w += -1000000.f;
+                        dst[i * 128] = o;
+                    }
+                }
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm_sa + kPrmSaBv + c0);
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, kD + c0, 256));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i * 128] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                // Fused time-axis softmax + K^T V (reference :111,:117).  With T >= 128 a tile touches at most two
+                // clips.  Per (tile, clip segment): column max, exp, column sums and the per-head 16x16 outer products
+                // over the segment's tokens, from shared memory (the operand rings are idle now); the partial
+                // (max, sum, K^T V) goes to global memory and the CTA that completes a clip merges its partials
+                // (online-softmax style) into that clip's block-diagonal B-operand image for the next layer.
+                constexpr int LDS = 132;                               // padded row stride (floats)
+                float* kS = reinterpret_cast<float*>(ringA);           // [128][132]
+                float* vS = kS + kTileRows * LDS;                      // [128][132]
+                float* pm = reinterpret_cast<float*>(ringB);           // [4][2][128] partial maxima, then [2][128] maxima
+                float* msm = pm + 1024;
+                int* flags = reinterpret_cast<int*>(msm + 256);
+                const int row0 = blockIdx.x * kTileRows;
+                const int first_clip = row0 / a.T;
+                const int nvalid = min(kTileRows, a.M - row0);
+                const int e = min(nvalid, (first_clip + 1) * a.T - row0);   // rows [0,e): first clip, [e,nvalid): next clip
+                const int n_seg = nvalid > e ? 2 : 1;
+                tmem_ld32(trow + kColS + 128 + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm_sa + kPrmSaBk + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     if (!keep) o.x += -1000000.f, o.y += -1000000.f, o.z += -1000000.f, o.w += -1000000.f;
-                    dst[i * 128] = o;
+                    if (!valid) o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    *reinterpret_cast<float4*>(kS + r * LDS + c0 + 4 * i) = o;
                 }
-            }
-            tmem_ld32(trow + kColW + c0, v);
-            tmem_wait_ld();
-            add_bias32(v, prm_sa + kPrmSaBv + c0);
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.kv + blk_index(g, kD + c0, 256));
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm_sa + kPrmSaBv + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    dst[i * 128] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(vS + r * LDS + c0 + 4 * i) =
+                        keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                named_bar_sync(5, kRowThreads);
+                const int tx = threadIdx.x, col = tx & 127, qr = tx >> 7;
+                {   // column maxima per segment
+                    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = 32 * qr + rr;
+                        const float x = kS[row * LDS + col];
+                        if (row < e) m0 = fmaxf(m0, x);
+                        else m1 = fmaxf(m1, x);
+                    }
+                    pm[(qr * 2 + 0) * 128 + col] = m0;
+                    pm[(qr * 2 + 1) * 128 + col] = m1;
+                }
+                named_bar_sync(5, kRowThreads);
+                if (tx < 256) {
+                    const int sg = tx >> 7;
+                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
+                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
+                }
+                named_bar_sync(5, kRowThreads);
+                {   // exp in place (padded rows hold -inf -> 0)
+                    const float mm0 = msm[col], mm1 = msm[128 + col];
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = 32 * qr + rr;
+                        const float x = kS[row * LDS + col];
+                        kS[row * LDS + col] = row < nvalid ? expf(x - (row < e ? mm0 : mm1)) : 0.f;
+                    }
+                }
+                named_bar_sync(5, kRowThreads);
+                const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    const int lo = sg ? e : 0, hi = sg ? nvalid : e;
+                    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+                    for (int tok = lo; tok < hi; ++tok) {
+                        const float2 ee = *reinterpret_cast<const float2*>(kS + tok * LDS + 16 * hh + d0);
+                        const float2 vv2 = *reinterpret_cast<const float2*>(vS + tok * LDS + 16 * hh + l0);
+                        a00 = fmaf(ee.x, vv2.x, a00), a01 = fmaf(ee.x, vv2.y, a01);
+                        a10 = fmaf(ee.y, vv2.x, a10), a11 = fmaf(ee.y, vv2.y, a11);
+                        s0 += ee.x, s1 += ee.y;
+                    }
+                    float* P = a.kv_part + ((size_t)blockIdx.x * 2 + sg) * kKvPartFloats;
+                    float* Pa = P + 256 + hh * 256;
+                    *reinterpret_cast<float2*>(Pa + d0 * 16 + l0) = make_float2(a00, a01);
+                    *reinterpret_cast<float2*>(Pa + (d0 + 1) * 16 + l0) = make_float2(a10, a11);
+                    if (l0 == 0) P[128 + 16 * hh + d0] = s0, P[128 + 16 * hh + d0 + 1] = s1;
+                    if (tx < 128) P[tx] = msm[sg * 128 + tx];
+                }
+                __threadfence();
+                named_bar_sync(5, kRowThreads);
+                if (tx == 0) {
+                    for (int sg = 0; sg < 2; ++sg) {
+                        flags[sg] = 0;
+                        if (sg < n_seg) {
+                            const int clip = first_clip + sg;
+                            const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
+                            const int old = atomicAdd(a.clip_cnt + clip, 1);
+                            if (old + 1 == ntiles) {
+                                flags[sg] = 1;
+                                a.clip_cnt[clip] = 0;          // ready for the next launch
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(5, kRowThreads);
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    if (!flags[sg]) continue;
+                    __threadfence();
+                    const int clip = first_clip + sg;
+                    const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
+                    float M0 = -INFINITY, M1 = -INFINITY;
+                    for (int ti = t_first; ti <= t_last; ++ti) {
+                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                        M0 = fmaxf(M0, __ldcg(P + 16 * hh + d0));
+                        M1 = fmaxf(M1, __ldcg(P + 16 * hh + d0 + 1));
+                    }
+                    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
+                    for (int ti = t_first; ti <= t_last; ++ti) {
+                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                        const float w0 = expf(__ldcg(P + 16 * hh + d0) - M0), w1 = expf(__ldcg(P + 16 * hh + d0 + 1) - M1);
+                        s0 = fmaf(__ldcg(P + 128 + 16 * hh + d0), w0, s0);
+                        s1 = fmaf(__ldcg(P + 128 + 16 * hh + d0 + 1), w1, s1);
+                        const float* Pa = P + 256 + hh * 256;
+                        const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
+                        const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
+                        a00 = fmaf(r0.x, w0, a00), a01 = fmaf(r0.y, w0, a01);
+                        a10 = fmaf(r1.x, w1, a10), a11 = fmaf(r1.y, w1, a11);
+                    }
+                    uint8_t* img = a.bd_sa_out + (size_t)clip * kAworkBytes;
+                    const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};
+#pragma unroll
+                    for (int dd = 0; dd < 2; ++dd) {
+                        const int ki = 16 * hh + d0 + dd;
+                        uint8_t* base = img + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
+#pragma unroll
+                        for (int ll = 0; ll < 2; ++ll) {
+                            const int nj = 16 * hh + l0 + ll;
+                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
+                        }
+                    }
+                }
             }
             // the q image must have left shared memory before the CTA exits
             if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
