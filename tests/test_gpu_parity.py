@@ -238,11 +238,12 @@ def test_full_size_properties_c2():
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
     kwp = dict(xf_proj=xf_proj[perm].cuda(), xf_out=xf_out[perm].cuda(), length=[T] * B)
     p = d.ddim_sample_loop(m, noise.shape, noise=noise[perm].cuda(), clip_denoised=False, model_kwargs=kwp)
-    assert torch.equal(p, a[perm.cuda()])
+    close(p, a[perm.cuda()], "bf16", "permutation equivariance")
     sub = [3, 17, 40]
     kws = dict(xf_proj=xf_proj[sub].cuda(), xf_out=xf_out[sub].cuda(), length=[T] * 3)
     s = d.ddim_sample_loop(m, (3, T, 26), noise=noise[sub].cuda(), clip_denoised=False, model_kwargs=kws)
-    assert torch.equal(s, a[sub])
+    # a clip's tokens are reduced in a tile-dependent order, so this holds to operand-rounding level, not bit-exactly
+    close(s, a[sub], "bf16", "clip independence")
     # oracle on the 3-clip sub-batch, first 2 steps
     _, x0s, _ = O.sample_loop(sd, O.Tables(O.linear_betas(S)), noise[sub], [T] * 3, xf_proj[sub], xf_out[sub], max_steps=2)
     gen = d.ddim_sample_loop_progressive(m, (3, T, 26), noise=noise[sub].cuda(), clip_denoised=False, model_kwargs=kws)
