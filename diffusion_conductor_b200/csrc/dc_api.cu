@@ -108,6 +108,7 @@ struct dc_handle {
 
     // graphs
     bool use_graphs = true;
+    bool use_pair = true;          // cta_group::2 CTA pairs in the layer kernel
     bool use_pdl = false;          // measured slightly slower on C2 (r01): kernels cannot co-reside with the 213 KB layer CTA
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -236,7 +237,7 @@ void drop_graph(dc_handle* h) {
 
 int ensure_workspace(dc_handle* h, int B, int T) {
     const size_t M = (size_t)B * T;
-    const size_t tiles = (M + kTileRows - 1) / kTileRows;
+    const size_t tiles = (((M + kTileRows - 1) / kTileRows) + 1) & ~size_t(1);     // even: CTA pairs may add a padding tile
     if (M <= h->cap_tokens && B <= h->cap_B) return 0;
     drop_graph(h);
     free_workspace(h);
@@ -274,26 +275,43 @@ int ensure_workspace(dc_handle* h, int B, int T) {
 int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(gemm_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(gemm_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     return 0;
 }
 
 // Launch with the programmatic-dependent-launch attribute: the kernel may be scheduled while its predecessor
 // in the stream drains; every kernel of the step calls griddepcontrol.wait before touching activations.
 template <class... KArgs, class... Args>
-cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+cudaError_t launch_kc(bool pdl, int cluster, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_kc(pdl, 1, kern, grid, block, smem, st, args...);
 }
 
 template <bool kBf16>
@@ -304,7 +322,10 @@ int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream
 
 template <bool kBf16>
 int launch_layer(dc_handle* h, const LayerArgs& la, int tiles, cudaStream_t st) {
-    DC_CUDA(h, launch_k(h->use_pdl, layer_kernel<kBf16>, dim3(tiles), dim3(kTileThreads), kLayerSmemBytes, st, la));
+    if (h->use_pair)      // CTA pairs (cta_group::2): grid padded to an even number of tiles
+        DC_CUDA(h, launch_kc(h->use_pdl, 2, layer_kernel<kBf16, true>, dim3((tiles + 1) & ~1), dim3(kTileThreads), kLayerSmemBytes, st, la));
+    else
+        DC_CUDA(h, launch_k(h->use_pdl, layer_kernel<kBf16, false>, dim3(tiles), dim3(kTileThreads), kLayerSmemBytes, st, la));
     return 0;
 }
 
@@ -438,7 +459,9 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
     const char* mi = getenv("DC_MASK_INVERT");
     if (mi && mi[0] == '1') h->mask_invert = 1;
-    if (mi && mi[0] == '2') h->mask_invert = 2;
+    if (mi && mi[0] == '3') h->mask_invert = 3;
+    const char* pr = getenv("DC_PAIR");
+    if (pr && pr[0] == '0') h->use_pair = false;
     const char* np = getenv("DC_PDL");
     if (np && np[0] == '1') h->use_pdl = true;
     const char* ng = getenv("DC_NO_GRAPH");

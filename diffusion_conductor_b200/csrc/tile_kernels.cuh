@@ -9,6 +9,8 @@
 //                LayerNorm partial statistics through shared memory + a 128-thread named barrier.
 //   warp 16    : producer -- streams packed operand blocks global/L2 -> smem ring with cp.async.bulk
 //   warp 17    : MMA issuer (one elected lane) + TMEM allocator
+//   warps 18,19: second producer (dependent-GEMM operands) and, in the follower CTA of a pair, the relay that
+//                forwards "stage landed" events to the leader
 // Synchronisation in the main loop is mbarrier-only between roles: full/empty per ring stage,
 // a_ready (row threads -> MMA), d_ready per accumulator (tcgen05.commit -> row threads).
 #pragma once
@@ -23,8 +25,8 @@ constexpr int kStageBytes = kStageABytes + kStageWBytes;
 constexpr int kAworkBytes = 2 * kABlockBytes;     // [128 x 128] A operand written by the row threads
 constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;       // 512
-constexpr int kProducerWarp = 16, kMmaWarp = 17, kProducerBWarp = 18;
-constexpr int kTileThreads = kRowThreads + 96;    // 608
+constexpr int kProducerWarp = 16, kMmaWarp = 17, kProducerBWarp = 18, kRelayWarp = 19;
+constexpr int kTileThreads = kRowThreads + 128;   // 640
 
 // TMEM column map (512 columns x 128 lanes x fp32)
 constexpr uint32_t kColH = 0;      // residual stream h            [128]
@@ -407,11 +409,12 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias) {
     }
 }
 
-// row threads signal "A operand (and any TMEM writes) ready"
-__device__ __forceinline__ void rows_publish(LayerBarriers* bars) {
+// row threads signal "A operand (and any TMEM writes) ready": one elected arrive per warp on the leader CTA's barrier
+__device__ __forceinline__ void rows_publish(uint32_t a_ready_cluster_addr, int lane) {
     fence_async_smem();
     tc_fence_before();
-    mbar_arrive(smem_u32(&bars->a_ready));
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(a_ready_cluster_addr);
 }
 __device__ __forceinline__ void rows_wait(LayerBarriers* bars, int which, uint32_t& phase) {
     mbar_wait(smem_u32(&bars->d_ready[which]), phase & 1u);
@@ -419,22 +422,24 @@ __device__ __forceinline__ void rows_wait(LayerBarriers* bars, int which, uint32
     tc_fence_after();
 }
 
-// clip segments of a 128-row tile: rows [lo, hi) of the tile belong to clip first_clip + s
-struct TileSegs {
-    int first_clip, n_seg, tile_row0, T;
-    __device__ __forceinline__ void init(int tile, int M, int T_) {
+// Clip segments of the rows one MMA covers (128 rows of a tile, or 256 rows of a CTA pair): rows [lo, hi)
+// belong to clip first_clip + s.
+struct RowSegs {
+    int first_clip, n_seg, row0, T, rows;
+    __device__ __forceinline__ void init(int first_tile, int rows_, int M, int T_) {
         T = T_;
-        tile_row0 = tile * kTileRows;
-        first_clip = tile_row0 / T;
-        const int last_row = min(tile_row0 + kTileRows - 1, M - 1);
+        rows = rows_;
+        row0 = first_tile * kTileRows;
+        first_clip = row0 / T;
+        const int last_row = min(row0 + rows - 1, M - 1);
         n_seg = last_row / T - first_clip + 1;
     }
-    // bit r set <=> row r is NOT in segment s (the tcgen05 "disable output lane" convention)
+    // bit r set <=> row r is NOT in segment s (the tcgen05 "disable output lane" convention); 8 words = 256 rows
     __device__ __forceinline__ void mask(int s, uint32_t* m, bool invert) const {
-        const int lo = max(0, (first_clip + s) * T - tile_row0);
-        const int hi = (s == n_seg - 1) ? kTileRows : min(kTileRows, (first_clip + s + 1) * T - tile_row0);
+        const int lo = max(0, (first_clip + s) * T - row0);
+        const int hi = (s == n_seg - 1) ? rows : min(rows, (first_clip + s + 1) * T - row0);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < 8; ++w) {
             uint32_t in = 0;
             const int a = max(lo, 32 * w), b = min(hi, 32 * w + 32);
             if (b > a) in = ((b - a) == 32 ? 0xFFFFFFFFu : ((1u << (b - a)) - 1u)) << (a - 32 * w);
@@ -443,7 +448,11 @@ struct TileSegs {
     }
 };
 
-template <bool kBf16>
+// kPair: two CTAs of a cluster (same TPC) run one tile each and share every MMA (cta_group::2, M = 256): each CTA
+// supplies its own 128 A rows and HALF of the B operand (N/2 rows), which halves the shared-memory operand
+// bandwidth and the weight bytes each SM pulls from L2.  The leader CTA (rank 0) issues all MMAs; completion is
+// multicast to both CTAs' barriers; the follower relays its "stage landed" events to the leader.
+template <bool kBf16, bool kPair>
 __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -455,6 +464,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);                // [4][128]
     LayerBarriers* bars = reinterpret_cast<LayerBarriers*>(xchg + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    constexpr uint32_t kHalf = kPair ? 2u : 1u;     // each CTA holds 1/kHalf of every B operand
+    const uint32_t brank = (a.mask_invert == 3) ? (rank ^ 1u) : rank;   // which half of B this CTA holds (debug: swapped)
 
     pdl_trigger();
     // prologue that touches only weights / on-chip state overlaps the previous kernel's tail
@@ -463,44 +476,52 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     if (a.do_sa1)
         for (int i = threadIdx.x; i < 384; i += kTileThreads) prm_sa[i] = a.prm_next[i];
     if (warp == kProducerWarp && lane == 0) {
-        for (int i = 0; i < kRingAStages; ++i) mbar_init(smem_u32(&bars->fullA[i]), 1), mbar_init(smem_u32(&bars->emptyA[i]), 1);
-        for (int i = 0; i < kRingBStages; ++i) mbar_init(smem_u32(&bars->fullB[i]), 1), mbar_init(smem_u32(&bars->emptyB[i]), 1);
-        mbar_init(smem_u32(&bars->a_ready), kRowThreads);
-        mbar_init(smem_u32(&bars->q_full), 1);
+        // "full" barriers of the leader also collect the follower's relay arrival
+        const uint32_t nfull = (kPair && leader) ? 2u : 1u;
+        for (int i = 0; i < kRingAStages; ++i) mbar_init(smem_u32(&bars->fullA[i]), nfull), mbar_init(smem_u32(&bars->emptyA[i]), 1);
+        for (int i = 0; i < kRingBStages; ++i) mbar_init(smem_u32(&bars->fullB[i]), nfull), mbar_init(smem_u32(&bars->emptyB[i]), 1);
+        mbar_init(smem_u32(&bars->a_ready), kRowWarps * kHalf);
+        mbar_init(smem_u32(&bars->q_full), nfull);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) {
-        tmem_alloc(smem_u32(&bars->tmem_base), 512);
-        tmem_relinquish();
+        if constexpr (kPair) {
+            tmem_alloc2(smem_u32(&bars->tmem_base), 512);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(smem_u32(&bars->tmem_base), 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();
     if (threadIdx.x == 0) tl_mark(a, 1);
 
+    // segments of the rows covered by one MMA
+    RowSegs segs;
+    segs.init(kPair ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x, kPair ? 2 * kTileRows : kTileRows, a.M, a.T);
+
     if (warp == kProducerWarp) {
-        // ---------------- ring A: A_emb k-blocks + FiLM projection weights
+        // ---------------- ring A: A_emb k-blocks + this CTA's share of the FiLM projection weights
         if (lane == 0) {
             const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
+            constexpr uint32_t kWShare = kStageWBytes / kHalf;
             uint32_t it = 0;
             for (int o = 0; o < a.n_s; ++o) {
-                const uint8_t* w = a.wbuf + a.sop_w_off[o];
+                const uint8_t* w = a.wbuf + a.sop_w_off[o] + brank * kWShare;
                 for (int s = 0; s < kSopStages; ++s, ++it) {
                     const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
                     mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bars->fullA[st]);
                     uint8_t* stage = ringA + st * kStageBytes;
-                    if (a.mask_invert == 2) {          // experiment: weight half only (wrong results, timing probe)
-                        mbar_arrive_expect_tx(full, kStageWBytes);
-                        bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kStageWBytes, full);
-                        continue;
-                    }
-                    mbar_arrive_expect_tx(full, kStageBytes);
+                    mbar_arrive_expect_tx(full, kStageABytes + kWShare);
                     bulk_g2s(smem_u32(stage), a_img + (size_t)s * kStageABytes, kStageABytes, full);
-                    bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kStageWBytes, full);
+                    bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kWShare, full);
                 }
             }
             for (int o = 0; o < a.n_d; ++o) {
@@ -510,15 +531,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 ++it;
                 mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bars->fullA[st]);
-                mbar_arrive_expect_tx(full, op.w_bytes);
-                bulk_g2s(smem_u32(ringA + st * kStageBytes + kStageABytes), a.wbuf + op.w_off, op.w_bytes, full);
+                const uint32_t kb_bytes = op.w_bytes / op.kb, share = kb_bytes / kHalf;
+                mbar_arrive_expect_tx(full, share * op.kb);
+                for (int kb = 0; kb < op.kb; ++kb)
+                    bulk_g2s(smem_u32(ringA + st * kStageBytes + kStageABytes + kb * share),
+                             a.wbuf + op.w_off + (size_t)kb * kb_bytes + brank * share, share, full);
             }
         }
     } else if (warp == kProducerBWarp) {
         // ---------------- ring B: dependent-GEMM weights, per-clip attention matrices, the q image
         if (lane == 0) {
-            TileSegs segs;
-            segs.init(blockIdx.x, a.M, a.T);
             if (a.do_main) {
                 const uint32_t qf = smem_u32(&bars->q_full);
                 mbar_arrive_expect_tx(qf, kAworkBytes);
@@ -529,7 +551,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 const DOp op = a.dops[o];
                 if (op.ring_a) continue;
                 const int n_st = op.seg ? segs.n_seg : 1;
-                const uint32_t kb_bytes = op.w_bytes / op.kb;
+                const uint32_t kb_bytes = op.w_bytes / op.kb, share = kb_bytes / kHalf;
                 for (int s = 0; s < n_st; ++s) {
                     const uint8_t* src = op.seg == 0   ? a.wbuf + op.w_off
                                          : op.seg == 1 ? a.bd_sa + (size_t)(segs.first_clip + s) * kAworkBytes
@@ -538,19 +560,56 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
                         mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
                         const uint32_t full = smem_u32(&bars->fullB[st]);
-                        mbar_arrive_expect_tx(full, kb_bytes);
-                        bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src + (size_t)kb * kb_bytes, kb_bytes, full);
+                        mbar_arrive_expect_tx(full, share);
+                        bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src + (size_t)kb * kb_bytes + brank * share, share, full);
                     }
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ---------------- MMA issuer: dependent GEMMs first, FiLM projection stages in the gaps
+    } else if (warp == kRelayWarp) {
+        // ---------------- follower only: forward ring-B / q-image arrivals to the leader's barriers
+        if (kPair && !leader && lane == 0) {
+            if (a.do_main) {
+                mbar_wait(smem_u32(&bars->q_full), 0);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->q_full), 0));
+            }
+            uint32_t total = 0;
+            for (int o = 0; o < a.n_d; ++o)
+                if (!a.dops[o].ring_a) total += (a.dops[o].seg ? segs.n_seg : 1) * a.dops[o].kb;
+            for (uint32_t it = 0; it < total; ++it) {
+                const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
+                mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fullB[st]), 0));
+            }
+        }
+    } else if (warp == kMmaWarp && !leader) {
+        // ---------------- follower only: forward ring-A arrivals to the leader
         if (lane == 0) {
-            TileSegs segs;
-            segs.init(blockIdx.x, a.M, a.T);
-            const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
+            uint32_t total = (uint32_t)a.n_s * kSopStages;
+            for (int o = 0; o < a.n_d; ++o) total += a.dops[o].ring_a ? 1u : 0u;
+            for (uint32_t it = 0; it < total; ++it) {
+                const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                mbar_wait(smem_u32(&bars->fullA[st]), ph);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fullA[st]), 0));
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ---------------- MMA issuer (leader): dependent GEMMs first, FiLM projection stages in the gaps
+        if (lane == 0) {
+            constexpr int kM = kPair ? 2 * kTileRows : kTileRows;
+            const uint32_t idesc_s = make_idesc<kBf16>(kM, 256);
             const uint32_t awork = smem_u32(awork_p);
+            uint32_t zero_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            auto test = [](uint32_t bar, uint32_t parity) { return kPair ? mbar_test_cluster(bar, parity) : mbar_test(bar, parity); };
+            auto commit = [](uint32_t bar) {
+                if constexpr (kPair) umma_commit_2cta(bar);
+                else umma_commit(bar);
+            };
+            auto kblock = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool acc, const uint32_t* m, bool masked) {
+                if constexpr (kPair) umma_kblock_2cta(d, a_addr, b_addr, idesc, acc, m);
+                else if (masked) umma_kblock_masked(d, a_addr, b_addr, idesc, acc, m);
+                else umma_kblock(d, a_addr, b_addr, idesc, acc);
+            };
             uint32_t itA = 0, itB = 0, a_phase = 0;
             int d_idx = 0, d_seg = 0, d_kb = 0, s_idx = 0, s_stage = 0, s_allowed = 1;
             bool d_waited = false;
@@ -561,8 +620,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                     if (!d_waited) {
                         if (op.wait == 0) d_waited = true;
                         else if (op.wait == 1) {
-                            if (mbar_test(smem_u32(&bars->a_ready), a_phase & 1u)) ++a_phase, d_waited = true;
-                        } else if (mbar_test(smem_u32(&bars->q_full), 0)) d_waited = true;
+                            if (test(smem_u32(&bars->a_ready), a_phase & 1u)) ++a_phase, d_waited = true;
+                        } else if (test(smem_u32(&bars->q_full), 0)) d_waited = true;
                         if (d_waited) {
                             tc_fence_after();
                             if (op.releases_s) ++s_allowed;
@@ -571,29 +630,31 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                     if (d_waited) {
                         const uint32_t st = op.ring_a ? itA % kRingAStages : itB % kRingBStages;
                         const uint32_t ph = op.ring_a ? (itA / kRingAStages) & 1u : (itB / kRingBStages) & 1u;
-                        if (mbar_test(smem_u32(op.ring_a ? &bars->fullA[st] : &bars->fullB[st]), ph)) {
+                        if (test(smem_u32(op.ring_a ? &bars->fullA[st] : &bars->fullB[st]), ph)) {
                             tc_fence_after();
-                            const uint32_t idesc = make_idesc<kBf16>(kTileRows, op.n);
+                            const uint32_t idesc = make_idesc<kBf16>(kM, op.n);
+                            const uint32_t kb_stride = (uint32_t)op.n * 128u / kHalf;     // bytes of one k-block of this CTA's B share
                             const int n_st = op.seg ? segs.n_seg : 1;
                             bool op_done = false;
                             if (op.ring_a) {            // whole operand in one ring-A stage
                                 const uint32_t b_base = smem_u32(ringA + st * kStageBytes + kStageABytes);
                                 for (int kb = 0; kb < op.kb; ++kb)
-                                    umma_kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * (uint32_t)op.n * 128u, idesc,
-                                                op.accumulate || kb > 0);
-                                umma_commit(smem_u32(&bars->emptyA[st]));
+                                    kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * kb_stride, idesc,
+                                           op.accumulate || kb > 0, zero_mask, false);
+                                commit(smem_u32(&bars->emptyA[st]));
                                 ++itA;
                                 op_done = true;
                             } else {                    // one k-block per ring-B stage
                                 const uint32_t b_base = smem_u32(ringB + st * kRingBStageBytes);
                                 if (op.seg) {
-                                    uint32_t m[4];
-                                    segs.mask(d_seg, m, a.mask_invert != 0);
-                                    umma_kblock_masked(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, d_kb > 0, m);
+                                    uint32_t m[8];
+                                    segs.mask(d_seg, m, a.mask_invert == 1);
+                                    kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, d_kb > 0, m, true);
                                 } else {
-                                    umma_kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, op.accumulate || d_kb > 0);
+                                    kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, op.accumulate || d_kb > 0,
+                                           zero_mask, false);
                                 }
-                                umma_commit(smem_u32(&bars->emptyB[st]));
+                                commit(smem_u32(&bars->emptyB[st]));
                                 ++itB;
                                 if (++d_kb == op.kb) {
                                     d_kb = 0;
@@ -602,7 +663,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                             }
                             if (op_done) {
                                 tl_mark(a, 200 + d_idx);
-                                if (op.commit != 255) umma_commit(smem_u32(&bars->d_ready[op.commit]));
+                                if (op.commit != 255) commit(smem_u32(&bars->d_ready[op.commit]));
                                 ++d_idx, d_seg = 0, d_waited = false;
                             }
                             progressed = true;
@@ -611,25 +672,24 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 }
                 if (!progressed && s_idx < a.n_s && s_idx < s_allowed) {
                     const uint32_t st = itA % kRingAStages, ph = (itA / kRingAStages) & 1u;
-                    if (mbar_test(smem_u32(&bars->fullA[st]), ph)) {
+                    if (test(smem_u32(&bars->fullA[st]), ph)) {
                         tc_fence_after();
                         const uint32_t stage = smem_u32(ringA + st * kStageBytes);
-                        umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, s_stage > 0);
-                        umma_commit(smem_u32(&bars->emptyA[st]));
+                        kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, s_stage > 0, zero_mask, false);
+                        commit(smem_u32(&bars->emptyA[st]));
                         ++itA;
                         if (s_stage == 0) tl_mark(a, 300 + s_idx);
                         if (++s_stage == kSopStages) {
                             tl_mark(a, 310 + s_idx);
-                            umma_commit(smem_u32(&bars->d_ready[0]));
+                            commit(smem_u32(&bars->d_ready[0]));
                             ++s_idx, s_stage = 0;
                         }
-                        progressed = true;
                     }
                 }
-                (void)progressed;      // tight poll: this is the only thread of its warp doing work, and __nanosleep costs ~1e3 cycles
             }
         }
     } else {
+        const uint32_t a_ready_addr = kPair ? mapa_u32(smem_u32(&bars->a_ready), 0) : smem_u32(&bars->a_ready);
         const uint32_t lq = warp & 3, cq = warp >> 2;
         const uint32_t r = lq * 32 + lane;            // row of the tile == TMEM lane
         const uint32_t c0 = cq * 32;                  // first of this thread's 32 features (heads 2cq, 2cq+1)
@@ -664,7 +724,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 102);                                   // S = A_emb . We_sa
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
 
             // ================= cross-attention
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
@@ -678,7 +738,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
@@ -687,14 +747,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             softmax16(v + 16);
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 106);                                   // S = A_emb . We_ca
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
 
             // ================= FFN (no pre-norm, reference transformer.py:170-173)
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
@@ -705,7 +765,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
             {
                 float u[16];                                             // hidden 64 = 4 quarters of 16
@@ -715,7 +775,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
                 store_a16<kBf16>(awork, r, 16 * cq, u);
             }
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
@@ -723,7 +783,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
         }
 
@@ -744,7 +804,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq/Wk/Wv
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(bars); if (threadIdx.x == 0) tl_mark(a, 158);
+            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 112);
             const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
             // q: softmax over head-dim, written as this tile's packed A-operand image for the next launch
@@ -802,9 +862,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 int* flags = reinterpret_cast<int*>(msm + 256);
                 const int row0 = blockIdx.x * kTileRows;
                 const int first_clip = row0 / a.T;
-                const int nvalid = min(kTileRows, a.M - row0);
+                const int nvalid = max(0, min(kTileRows, a.M - row0));     // 0 for the padding tile of an odd pair
                 const int e = min(nvalid, (first_clip + 1) * a.T - row0);   // rows [0,e): first clip, [e,nvalid): next clip
-                const int n_seg = nvalid > e ? 2 : 1;
+                const int n_seg = nvalid == 0 ? 0 : (nvalid > e ? 2 : 1);
                 tmem_ld32(trow + kColS + 128 + c0, v);
                 tmem_wait_ld();
                 add_bias32(v, prm_sa + kPrmSaBk + c0);
@@ -932,10 +992,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     }
     if (threadIdx.x == 0) tl_mark(a, 2);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();      // the peer may still be reading this CTA's shared memory / barriers
+    else __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (kPair) tmem_dealloc2(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
