@@ -108,7 +108,8 @@ struct dc_handle {
 
     // graphs
     bool use_graphs = true;
-    bool use_pair = true;          // cta_group::2 CTA pairs in the layer kernel
+    bool use_pair = false;         // cta_group::2 CTA pairs in the layer kernel (DC_PAIR=1); measured r01: 7 % slower on
+                                   // C2/C3 -- the kernel is bound by the dependent chain, and pairing adds signalling latency
     bool use_pdl = false;          // measured slightly slower on C2 (r01): kernels cannot co-reside with the 213 KB layer CTA
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -461,7 +462,7 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     if (mi && mi[0] == '1') h->mask_invert = 1;
     if (mi && mi[0] == '3') h->mask_invert = 3;
     const char* pr = getenv("DC_PAIR");
-    if (pr && pr[0] == '0') h->use_pair = false;
+    if (pr) h->use_pair = pr[0] == '1';
     const char* np = getenv("DC_PDL");
     if (np && np[0] == '1') h->use_pdl = true;
     const char* ng = getenv("DC_NO_GRAPH");

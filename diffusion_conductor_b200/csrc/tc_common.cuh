@@ -78,6 +78,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  : "memory");
 }
 
+// same copy issued as independent pieces of kBulkChunk bytes (experiment knob: the TMA unit serves several
+// outstanding bulk requests concurrently, one big request is served sequentially)
+#ifndef DC_BULK_CHUNK
+#define DC_BULK_CHUNK 4096
+#endif
+__device__ __forceinline__ void bulk_g2s_chunked(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    const uint8_t* p = static_cast<const uint8_t*>(src);
+    for (uint32_t off = 0; off < bytes; off += DC_BULK_CHUNK)
+        bulk_g2s(dst_smem + off, p + off, min((uint32_t)DC_BULK_CHUNK, bytes - off), bar);
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -236,17 +247,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
-}
+// The barriers the MMA issuer waits on are local to the leader CTA; the peer arrives on them with
+// release.cluster after fencing its own shared-memory writes for the async proxy.  Those writes are read by the
+// peer SM's own tensor-core datapath, so the ordinary CTA-scope probe is what is needed here (cluster-scope
+// acquires / fences measured 1.5-2x slower for the whole kernel: they invalidate L1).
+__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) { return mbar_test(bar, parity); }
 __device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }

@@ -235,10 +235,16 @@ constexpr int kStBe = 0, kStG = 256, kStB = 384, kStBo = 512;
 //            per-clip block-diagonal attention matrices.
 // The issuer polls both (dependent work first), so a short dependent GEMM never queues behind a long
 // FiLM projection.
-constexpr int kRingAStages = 3;
+constexpr int kRingAStages = 3;                 // single-CTA mode: 3 x (16 KB A_emb + 32 KB weights)
 constexpr int kRingBStages = 2;
 constexpr int kRingBStageBytes = 16 * 1024;     // one k-block (64) of a dependent GEMM's B operand
 constexpr int kSopStages = 8;
+// pair mode: each CTA holds half of every B operand, so the same shared memory gives deeper rings, which the
+// longer leader<->follower signalling round trip needs
+constexpr int kPairRingAStages = 4;             // 4 x (16 KB A_emb + 16 KB weights)
+constexpr int kPairStageBytes = kStageABytes + kStageWBytes / 2;
+constexpr int kPairRingBStages = 4;             // 4 x 8 KB
+constexpr int kPairRingBStageBytes = 8 * 1024;
 
 struct DOp {
     uint32_t w_off;        // byte offset in the packed weight buffer (seg == 0)
@@ -261,9 +267,10 @@ constexpr int kKvPartFloats = 128 + 128 + kH * 256;
 constexpr int kMaxSOps = 3;
 
 struct LayerBarriers {
-    uint64_t fullA[kRingAStages], emptyA[kRingAStages];
-    uint64_t fullB[kRingBStages], emptyB[kRingBStages];
+    uint64_t fullA[4], emptyA[4];
+    uint64_t fullB[4], emptyB[4];
     uint64_t a_ready;
+    uint64_t s_free;       // row threads -> FiLM-projection issuer: the S accumulator has been consumed
     uint64_t q_full;
     uint64_t d_ready[3];   // 0: S, 1: H, 2: W
     uint32_t tmem_base;
@@ -456,8 +463,12 @@ template <bool kBf16, bool kPair>
 __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kNA = kPair ? kPairRingAStages : kRingAStages, kSA = kPair ? kPairStageBytes : kStageBytes;
+    constexpr int kNB = kPair ? kPairRingBStages : kRingBStages, kSB = kPair ? kPairRingBStageBytes : kRingBStageBytes;
+    static_assert(kNA * kSA <= kRingAStages * kStageBytes && kNB * kSB <= kRingBStages * kRingBStageBytes,
+                  "pair-mode rings must fit the single-CTA ring footprint");
     uint8_t* ringA = smem;
-    uint8_t* ringB = ringA + kRingAStages * kStageBytes;
+    uint8_t* ringB = smem + kRingAStages * kStageBytes;          // same carve-up in both modes (fused-kv scratch relies on it)
     uint8_t* awork_p = ringB + kRingBStages * kRingBStageBytes;
     float* prm = reinterpret_cast<float*>(awork_p + kAworkBytes);          // [kPrmFloats]
     float* prm_sa = prm + kPrmFloats;                                      // [384] SA biases of layer l+1
@@ -478,9 +489,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
     if (warp == kProducerWarp && lane == 0) {
         // "full" barriers of the leader also collect the follower's relay arrival
         const uint32_t nfull = (kPair && leader) ? 2u : 1u;
-        for (int i = 0; i < kRingAStages; ++i) mbar_init(smem_u32(&bars->fullA[i]), nfull), mbar_init(smem_u32(&bars->emptyA[i]), 1);
-        for (int i = 0; i < kRingBStages; ++i) mbar_init(smem_u32(&bars->fullB[i]), nfull), mbar_init(smem_u32(&bars->emptyB[i]), 1);
+        for (int i = 0; i < kNA; ++i) mbar_init(smem_u32(&bars->fullA[i]), nfull), mbar_init(smem_u32(&bars->emptyA[i]), 1);
+        for (int i = 0; i < kNB; ++i) mbar_init(smem_u32(&bars->fullB[i]), nfull), mbar_init(smem_u32(&bars->emptyB[i]), 1);
         mbar_init(smem_u32(&bars->a_ready), kRowWarps * kHalf);
+        mbar_init(smem_u32(&bars->s_free), kRowWarps * kHalf);
         mbar_init(smem_u32(&bars->q_full), nfull);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
         mbar_fence_init();
@@ -515,26 +527,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             for (int o = 0; o < a.n_s; ++o) {
                 const uint8_t* w = a.wbuf + a.sop_w_off[o] + brank * kWShare;
                 for (int s = 0; s < kSopStages; ++s, ++it) {
-                    const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                    const uint32_t st = it % kNA, ph = (it / kNA) & 1u;
                     mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bars->fullA[st]);
-                    uint8_t* stage = ringA + st * kStageBytes;
+                    uint8_t* stage = ringA + st * kSA;
                     mbar_arrive_expect_tx(full, kStageABytes + kWShare);
-                    bulk_g2s(smem_u32(stage), a_img + (size_t)s * kStageABytes, kStageABytes, full);
-                    bulk_g2s(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kWShare, full);
+                    bulk_g2s_chunked(smem_u32(stage), a_img + (size_t)s * kStageABytes, kStageABytes, full);
+                    bulk_g2s_chunked(smem_u32(stage + kStageABytes), w + (size_t)s * kStageWBytes, kWShare, full);
                 }
             }
             for (int o = 0; o < a.n_d; ++o) {
                 const DOp op = a.dops[o];
                 if (!op.ring_a) continue;
-                const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                const uint32_t st = it % kNA, ph = (it / kNA) & 1u;
                 ++it;
                 mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bars->fullA[st]);
                 const uint32_t kb_bytes = op.w_bytes / op.kb, share = kb_bytes / kHalf;
                 mbar_arrive_expect_tx(full, share * op.kb);
                 for (int kb = 0; kb < op.kb; ++kb)
-                    bulk_g2s(smem_u32(ringA + st * kStageBytes + kStageABytes + kb * share),
+                    bulk_g2s_chunked(smem_u32(ringA + st * kSA + kStageABytes + kb * share),
                              a.wbuf + op.w_off + (size_t)kb * kb_bytes + brank * share, share, full);
             }
         }
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             if (a.do_main) {
                 const uint32_t qf = smem_u32(&bars->q_full);
                 mbar_arrive_expect_tx(qf, kAworkBytes);
-                bulk_g2s(smem_u32(awork_p), a.q_img + (size_t)blockIdx.x * kAworkBytes, kAworkBytes, qf);
+                bulk_g2s_chunked(smem_u32(awork_p), a.q_img + (size_t)blockIdx.x * kAworkBytes, kAworkBytes, qf);
             }
             uint32_t it = 0;
             for (int o = 0; o < a.n_d; ++o) {
@@ -557,29 +569,62 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                                          : op.seg == 1 ? a.bd_sa + (size_t)(segs.first_clip + s) * kAworkBytes
                                                        : a.bd_ca + (size_t)(segs.first_clip + s) * a.bd_ca_stride;
                     for (int kb = 0; kb < op.kb; ++kb, ++it) {
-                        const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
+                        const uint32_t st = it % kNB, ph = (it / kNB) & 1u;
                         mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
                         const uint32_t full = smem_u32(&bars->fullB[st]);
                         mbar_arrive_expect_tx(full, share);
-                        bulk_g2s(smem_u32(ringB + st * kRingBStageBytes), src + (size_t)kb * kb_bytes + brank * share, share, full);
+                        bulk_g2s_chunked(smem_u32(ringB + st * kSB), src + (size_t)kb * kb_bytes + brank * share, share, full);
                     }
                 }
             }
         }
     } else if (warp == kRelayWarp) {
-        // ---------------- follower only: forward ring-B / q-image arrivals to the leader's barriers
-        if (kPair && !leader && lane == 0) {
-            if (a.do_main) {
-                mbar_wait(smem_u32(&bars->q_full), 0);
-                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->q_full), 0));
+        if (kPair && !leader) {
+            // ---------------- follower: forward ring-B / q-image arrivals to the leader's barriers
+            if (lane == 0) {
+                if (a.do_main) {
+                    mbar_wait(smem_u32(&bars->q_full), 0);
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&bars->q_full), 0));
+                }
+                uint32_t total = 0;
+                for (int o = 0; o < a.n_d; ++o)
+                    if (!a.dops[o].ring_a) total += (a.dops[o].seg ? segs.n_seg : 1) * a.dops[o].kb;
+                for (uint32_t it = 0; it < total; ++it) {
+                    const uint32_t st = it % kNB, ph = (it / kNB) & 1u;
+                    mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fullB[st]), 0));
+                }
             }
-            uint32_t total = 0;
-            for (int o = 0; o < a.n_d; ++o)
-                if (!a.dops[o].ring_a) total += (a.dops[o].seg ? segs.n_seg : 1) * a.dops[o].kb;
-            for (uint32_t it = 0; it < total; ++it) {
-                const uint32_t st = it % kRingBStages, ph = (it / kRingBStages) & 1u;
-                mbar_wait(smem_u32(&bars->fullB[st]), ph);
-                mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fullB[st]), 0));
+        } else if (lane == 0) {
+            // ---------------- leader: issuer of the FiLM projections S = A_emb . We (ring A).  They depend only on
+            // the S accumulator being free (s_free: the row threads are done reading the previous projection), so
+            // this lane runs ahead of the dependent chain and the tensor pipe fills its gaps with these MMAs.
+            constexpr int kM = kPair ? 2 * kTileRows : kTileRows;
+            const uint32_t idesc_s = make_idesc<kBf16>(kM, 256);
+            uint32_t zero_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t it = 0;
+            for (int o = 0; o < a.n_s; ++o) {
+                if (o > 0) {
+                    mbar_wait(smem_u32(&bars->s_free), (uint32_t)(o - 1) & 1u);
+                    tc_fence_after();
+                }
+                for (int sgi = 0; sgi < kSopStages; ++sgi, ++it) {
+                    const uint32_t st = it % kNA, ph = (it / kNA) & 1u;
+                    mbar_wait(smem_u32(&bars->fullA[st]), ph);
+                    tc_fence_after();
+                    const uint32_t stage = smem_u32(ringA + st * kSA);
+                    if constexpr (kPair) {
+                        umma_kblock_2cta(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, sgi > 0, zero_mask);
+                        umma_commit_2cta(smem_u32(&bars->emptyA[st]));
+                    } else {
+                        umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, sgi > 0);
+                        umma_commit(smem_u32(&bars->emptyA[st]));
+                    }
+                    if (sgi == 0) tl_mark(a, 300 + o);
+                }
+                tl_mark(a, 310 + o);
+                if constexpr (kPair) umma_commit_2cta(smem_u32(&bars->d_ready[0]));
+                else umma_commit(smem_u32(&bars->d_ready[0]));
             }
         }
     } else if (warp == kMmaWarp && !leader) {
@@ -588,19 +633,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             uint32_t total = (uint32_t)a.n_s * kSopStages;
             for (int o = 0; o < a.n_d; ++o) total += a.dops[o].ring_a ? 1u : 0u;
             for (uint32_t it = 0; it < total; ++it) {
-                const uint32_t st = it % kRingAStages, ph = (it / kRingAStages) & 1u;
+                const uint32_t st = it % kNA, ph = (it / kNA) & 1u;
                 mbar_wait(smem_u32(&bars->fullA[st]), ph);
                 mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fullA[st]), 0));
             }
         }
     } else if (warp == kMmaWarp) {
-        // ---------------- MMA issuer (leader): dependent GEMMs first, FiLM projection stages in the gaps
+        // ---------------- leader: issuer of the dependent GEMMs, strictly in chain order with blocking waits
         if (lane == 0) {
             constexpr int kM = kPair ? 2 * kTileRows : kTileRows;
-            const uint32_t idesc_s = make_idesc<kBf16>(kM, 256);
             const uint32_t awork = smem_u32(awork_p);
             uint32_t zero_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            auto test = [](uint32_t bar, uint32_t parity) { return kPair ? mbar_test_cluster(bar, parity) : mbar_test(bar, parity); };
             auto commit = [](uint32_t bar) {
                 if constexpr (kPair) umma_commit_2cta(bar);
                 else umma_commit(bar);
@@ -610,86 +653,51 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 else if (masked) umma_kblock_masked(d, a_addr, b_addr, idesc, acc, m);
                 else umma_kblock(d, a_addr, b_addr, idesc, acc);
             };
-            uint32_t itA = 0, itB = 0, a_phase = 0;
-            int d_idx = 0, d_seg = 0, d_kb = 0, s_idx = 0, s_stage = 0, s_allowed = 1;
-            bool d_waited = false;
-            while (d_idx < a.n_d || s_idx < a.n_s) {
-                bool progressed = false;
-                if (d_idx < a.n_d) {
-                    const DOp op = a.dops[d_idx];
-                    if (!d_waited) {
-                        if (op.wait == 0) d_waited = true;
-                        else if (op.wait == 1) {
-                            if (test(smem_u32(&bars->a_ready), a_phase & 1u)) ++a_phase, d_waited = true;
-                        } else if (test(smem_u32(&bars->q_full), 0)) d_waited = true;
-                        if (d_waited) {
+            uint32_t itA = (uint32_t)a.n_s * kSopStages, itB = 0, a_phase = 0;     // ring A: behind the FiLM projections
+            for (int d_idx = 0; d_idx < a.n_d; ++d_idx) {
+                const DOp op = a.dops[d_idx];
+                if (op.wait == 1) {
+                    mbar_wait(smem_u32(&bars->a_ready), a_phase & 1u);
+                    ++a_phase;
+                } else if (op.wait == 2) {
+                    mbar_wait(smem_u32(&bars->q_full), 0);
+                }
+                tc_fence_after();
+                const uint32_t idesc = make_idesc<kBf16>(kM, op.n);
+                const uint32_t kb_stride = (uint32_t)op.n * 128u / kHalf;     // bytes of one k-block of this CTA's B share
+                if (op.ring_a) {            // whole operand in one ring-A stage
+                    const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
+                    mbar_wait(smem_u32(&bars->fullA[st]), ph);
+                    tc_fence_after();
+                    const uint32_t b_base = smem_u32(ringA + st * kSA + kStageABytes);
+                    for (int kb = 0; kb < op.kb; ++kb)
+                        kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * kb_stride, idesc, op.accumulate || kb > 0,
+                               zero_mask, false);
+                    commit(smem_u32(&bars->emptyA[st]));
+                    ++itA;
+                } else {                    // one k-block per ring-B stage
+                    const int n_st = op.seg ? segs.n_seg : 1;
+                    for (int sg = 0; sg < n_st; ++sg) {
+                        uint32_t m[8];
+                        if (op.seg) segs.mask(sg, m, a.mask_invert == 1);
+                        for (int kb = 0; kb < op.kb; ++kb, ++itB) {
+                            const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
+                            mbar_wait(smem_u32(&bars->fullB[st]), ph);
                             tc_fence_after();
-                            if (op.releases_s) ++s_allowed;
-                        }
-                    }
-                    if (d_waited) {
-                        const uint32_t st = op.ring_a ? itA % kRingAStages : itB % kRingBStages;
-                        const uint32_t ph = op.ring_a ? (itA / kRingAStages) & 1u : (itB / kRingBStages) & 1u;
-                        if (test(smem_u32(op.ring_a ? &bars->fullA[st] : &bars->fullB[st]), ph)) {
-                            tc_fence_after();
-                            const uint32_t idesc = make_idesc<kBf16>(kM, op.n);
-                            const uint32_t kb_stride = (uint32_t)op.n * 128u / kHalf;     // bytes of one k-block of this CTA's B share
-                            const int n_st = op.seg ? segs.n_seg : 1;
-                            bool op_done = false;
-                            if (op.ring_a) {            // whole operand in one ring-A stage
-                                const uint32_t b_base = smem_u32(ringA + st * kStageBytes + kStageABytes);
-                                for (int kb = 0; kb < op.kb; ++kb)
-                                    kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base + kb * kb_stride, idesc,
-                                           op.accumulate || kb > 0, zero_mask, false);
-                                commit(smem_u32(&bars->emptyA[st]));
-                                ++itA;
-                                op_done = true;
-                            } else {                    // one k-block per ring-B stage
-                                const uint32_t b_base = smem_u32(ringB + st * kRingBStageBytes);
-                                if (op.seg) {
-                                    uint32_t m[8];
-                                    segs.mask(d_seg, m, a.mask_invert == 1);
-                                    kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, d_kb > 0, m, true);
-                                } else {
-                                    kblock(tmem_base + op.d_col, awork + d_kb * kABlockBytes, b_base, idesc, op.accumulate || d_kb > 0,
-                                           zero_mask, false);
-                                }
-                                commit(smem_u32(&bars->emptyB[st]));
-                                ++itB;
-                                if (++d_kb == op.kb) {
-                                    d_kb = 0;
-                                    if (++d_seg == n_st) op_done = true;
-                                }
-                            }
-                            if (op_done) {
-                                tl_mark(a, 200 + d_idx);
-                                if (op.commit != 255) commit(smem_u32(&bars->d_ready[op.commit]));
-                                ++d_idx, d_seg = 0, d_waited = false;
-                            }
-                            progressed = true;
+                            const uint32_t b_base = smem_u32(ringB + st * kSB);
+                            if (op.seg) kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base, idesc, kb > 0, m, true);
+                            else kblock(tmem_base + op.d_col, awork + kb * kABlockBytes, b_base, idesc, op.accumulate || kb > 0, zero_mask, false);
+                            commit(smem_u32(&bars->emptyB[st]));
                         }
                     }
                 }
-                if (!progressed && s_idx < a.n_s && s_idx < s_allowed) {
-                    const uint32_t st = itA % kRingAStages, ph = (itA / kRingAStages) & 1u;
-                    if (test(smem_u32(&bars->fullA[st]), ph)) {
-                        tc_fence_after();
-                        const uint32_t stage = smem_u32(ringA + st * kStageBytes);
-                        kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, s_stage > 0, zero_mask, false);
-                        commit(smem_u32(&bars->emptyA[st]));
-                        ++itA;
-                        if (s_stage == 0) tl_mark(a, 300 + s_idx);
-                        if (++s_stage == kSopStages) {
-                            tl_mark(a, 310 + s_idx);
-                            commit(smem_u32(&bars->d_ready[0]));
-                            ++s_idx, s_stage = 0;
-                        }
-                    }
-                }
+                tl_mark(a, 200 + d_idx);
+                if (op.commit != 255) commit(smem_u32(&bars->d_ready[op.commit]));
             }
         }
     } else {
         const uint32_t a_ready_addr = kPair ? mapa_u32(smem_u32(&bars->a_ready), 0) : smem_u32(&bars->a_ready);
+        const uint32_t s_free_addr = kPair ? mapa_u32(smem_u32(&bars->s_free), 0) : smem_u32(&bars->s_free);
         const uint32_t lq = warp & 3, cq = warp >> 2;
         const uint32_t r = lq * 32 + lane;            // row of the tile == TMEM lane
         const uint32_t c0 = cq * 32;                  // first of this thread's 32 features (heads 2cq, 2cq+1)
@@ -724,6 +732,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 102);                                   // S = A_emb . We_sa
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
+            tc_fence_before();                                           // S consumed: the next FiLM projection may start
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(s_free_addr);
             rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
 
             // ================= cross-attention
@@ -754,6 +765,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 106);                                   // S = A_emb . We_ca
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
+            tc_fence_before();                                           // S consumed: the next FiLM projection may start
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(s_free_addr);
             rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
 
             // ================= FFN (no pre-norm, reference transformer.py:170-173)
@@ -783,6 +797,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             row_stats32(rs, v, mean, rstd);
             rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
+            tc_fence_before();                                           // S consumed: the next FiLM projection may start
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(s_free_addr);
             rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
         }
