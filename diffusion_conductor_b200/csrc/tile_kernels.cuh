@@ -330,21 +330,30 @@ __device__ __forceinline__ void softmax16(float* q) {
     float mx = q[0];
 #pragma unroll
     for (int i = 1; i < 16; ++i) mx = fmaxf(mx, q[i]);
-    float s = 0.f;
+    // exp(x - mx) = 2^(x*log2e - mx*log2e): one packed FMA per pair, then MUFU.EX2
+    const uint64_t l2 = pk2(1.4426950408889634f, 1.4426950408889634f);
+    const uint64_t nm = pk2(-mx * 1.4426950408889634f, -mx * 1.4426950408889634f);
+    uint64_t acc = pk2(0.f, 0.f);
+    uint64_t e2[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        q[i] = __expf(q[i] - mx);
-        s += q[i];
+    for (int i = 0; i < 8; ++i) {
+        float a0, a1;
+        upk2(ffma2(pk2(q[2 * i], q[2 * i + 1]), l2, nm), a0, a1);
+        e2[i] = pk2(exp2f(a0), exp2f(a1));
+        acc = fadd2(acc, e2[i]);
     }
-    const float inv = __fdividef(1.f, s);
+    float s0, s1;
+    upk2(acc, s0, s1);
+    const float inv = __fdividef(1.f, s0 + s1);
+    const uint64_t inv2 = pk2(inv, inv);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] *= inv;
+    for (int i = 0; i < 8; ++i) upk2(fmul2(e2[i], inv2), q[2 * i], q[2 * i + 1]);
 }
 
 // Row statistics over 128 features held as 4 x 32 registers by the 4 warps that share a row:
 // local (mean, M2) -> shared memory -> 128-thread named barrier -> Chan combine.
 struct RowStats {
-    float2* xchg;      // [2][4][128]
+    float2* xchg;      // [4][128]
     uint32_t bar_id;   // 1 + lq
     uint32_t r;        // row within the tile
     uint32_t cq;
@@ -352,16 +361,26 @@ struct RowStats {
 };
 
 __device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float& mean, float& rstd) {
-    float s = 0.f;
+    uint64_t s2a = pk2(0.f, 0.f), s2b = s2a;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s += v[i];
-    const float lm = s * (1.f / 32.f);
-    float m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float d = v[i] - lm;
-        m2 = fmaf(d, d, m2);
+    for (int i = 0; i < 8; ++i) {
+        s2a = fadd2(s2a, pk2(v[4 * i], v[4 * i + 1]));
+        s2b = fadd2(s2b, pk2(v[4 * i + 2], v[4 * i + 3]));
     }
+    float sa, sb;
+    upk2(fadd2(s2a, s2b), sa, sb);
+    const float lm = (sa + sb) * (1.f / 32.f);
+    const uint64_t nlm = pk2(-lm, -lm);
+    uint64_t qa = pk2(0.f, 0.f), qb = qa;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint64_t d0 = fadd2(pk2(v[4 * i], v[4 * i + 1]), nlm), d1 = fadd2(pk2(v[4 * i + 2], v[4 * i + 3]), nlm);
+        qa = ffma2(d0, d0, qa);
+        qb = ffma2(d1, d1, qb);
+    }
+    float m2a, m2b;
+    upk2(fadd2(qa, qb), m2a, m2b);
+    const float m2 = m2a + m2b;
     float2* buf = rs.xchg;
     buf[rs.cq * 128 + rs.r] = make_float2(lm, m2);
     named_bar_sync(rs.bar_id, 128);
@@ -373,6 +392,13 @@ __device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float&
     rstd = rsqrtf(M2 * (1.f / kD) + kLnEps);
 }
 
+// v <- (v - mean) * rstd for 32 values (LayerNorm without affine)
+__device__ __forceinline__ void normalize32(float* v, float mean, float rstd) {
+    const uint64_t r2 = pk2(rstd, rstd), nm = pk2(-mean * rstd, -mean * rstd);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) upk2(ffma2(pk2(v[2 * i], v[2 * i + 1]), r2, nm), v[2 * i], v[2 * i + 1]);
+}
+
 // A operand <- SiLU( LN(y) * (1 + scale) + shift ) for this thread's 32 features [c0, c0+32)
 // (reference transformer.py:77-80).  The scale|shift accumulator in TMEM columns kColS is laid out
 //   [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]; st = stylization params in smem.
@@ -381,6 +407,7 @@ __device__ __forceinline__ void film_to_a(uint32_t trow, const float* y, float m
                                           uint32_t r, uint32_t c0) {
     const uint32_t sbase = trow + kColS + (c0 >> 6) * 128 + (c0 & 63);     // scale column of feature c0
     const float* be = st + kStBe + (c0 >> 6) * 128 + (c0 & 63);
+    const uint64_t r2 = pk2(rstd, rstd), nm = pk2(-mean * rstd, -mean * rstd), half2 = pk2(0.5f, 0.5f);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         float sc[16], sh[16], o[16];
@@ -393,14 +420,27 @@ __device__ __forceinline__ void film_to_a(uint32_t trow, const float* y, float m
             const float4 b4 = *reinterpret_cast<const float4*>(st + kStB + c0 + 16 * hf + 4 * i4);
             const float4 es = *reinterpret_cast<const float4*>(be + 16 * hf + 4 * i4);
             const float4 eh = *reinterpret_cast<const float4*>(be + 64 + 16 * hf + 4 * i4);
-            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            const float ss[4] = {es.x, es.y, es.z, es.w}, hh[4] = {eh.x, eh.y, eh.z, eh.w};
+            const uint64_t gg[2] = {pk2(g4.x, g4.y), pk2(g4.z, g4.w)}, bb[2] = {pk2(b4.x, b4.y), pk2(b4.z, b4.w)};
+            const uint64_t ss[2] = {pk2(es.x, es.y), pk2(es.z, es.w)}, hh[2] = {pk2(eh.x, eh.y), pk2(eh.z, eh.w)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = 4 * i4 + k;
-                const float n = fmaf((y[16 * hf + i] - mean) * rstd, gg[k], bb[k]);
-                const float v = fmaf(n, sc[i] + ss[k], sh[i] + hh[k]);
-                o[i] = silu_f<kBf16>(v);
+            for (int k = 0; k < 2; ++k) {
+                const int i = 4 * i4 + 2 * k;
+                const uint64_t z = ffma2(pk2(y[16 * hf + i], y[16 * hf + i + 1]), r2, nm);          // (y - mean) * rstd
+                const uint64_t n = ffma2(z, gg[k], bb[k]);                                          // LN affine
+                const uint64_t sca = fadd2(pk2(sc[i], sc[i + 1]), ss[k]), shf = fadd2(pk2(sh[i], sh[i + 1]), hh[k]);
+                const uint64_t u = ffma2(n, sca, shf);                                              // FiLM
+                float u0, u1;
+                if constexpr (kBf16) {        // SiLU(u) = u * (0.5 + 0.5 tanh(u / 2)): one MUFU per element
+                    upk2(fmul2(u, half2), u0, u1);
+                    float t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+                    upk2(fmul2(u, ffma2(pk2(t0, t1), half2, half2)), o[i], o[i + 1]);
+                } else {
+                    upk2(u, u0, u1);
+                    o[i] = __fdividef(u0, 1.f + __expf(-u0));
+                    o[i + 1] = __fdividef(u1, 1.f + __expf(-u1));
+                }
             }
         }
         store_a16<kBf16>(awork, r, c0 + 16 * hf, o);
@@ -412,7 +452,8 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias) {
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * i4);
-        v[4 * i4] += b4.x, v[4 * i4 + 1] += b4.y, v[4 * i4 + 2] += b4.z, v[4 * i4 + 3] += b4.w;
+        upk2(fadd2(pk2(v[4 * i4], v[4 * i4 + 1]), pk2(b4.x, b4.y)), v[4 * i4], v[4 * i4 + 1]);
+        upk2(fadd2(pk2(v[4 * i4 + 2], v[4 * i4 + 3]), pk2(b4.z, b4.w)), v[4 * i4 + 2], v[4 * i4 + 3]);
     }
 }
 
@@ -744,8 +785,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             add_bias32(v, prm + kPrmStSa + kStBo + c0);                  // deferred bias of Wo_sa
             tmem_st32(trow + kColH + c0, v);
             row_stats32(rs, v, mean, rstd);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq_ca
+            normalize32(v, mean, rstd);                                  // LN affine folded into Wq_ca
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
@@ -817,8 +857,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
         if (a.do_sa1) {
             // ================= next layer's self-attention head: LN -> q | k | v
             row_stats32(rs, v, mean, rstd);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;    // LN affine folded into Wq/Wk/Wv
+            normalize32(v, mean, rstd);                                  // LN affine folded into Wq/Wk/Wv
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
