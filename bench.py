@@ -263,8 +263,12 @@ def main():
     flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * B * T / max(cnt["layer"], 1)
     achieved = flop_per_launch / (layer_ms * 1e-3) / 1e12
     step_ms = sum(agg.values())
+    traffic = None        # dram__bytes_read + write per launch of the layer kernel, from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "dc::layer_kernel", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": traffic,
                 "peak_source": pk["source"], "launch_ms": round(layer_ms, 4), "launches_per_denoise_step": cnt["layer"],
                 "share_of_denoise_step": round(agg["layer"] / step_ms, 3),
                 "denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()},

@@ -272,3 +272,70 @@ def test_full_size_properties_c3_long_sequence():
     y1 = m(noise.cuda(), t, **kw)
     y2 = m(x2.cuda(), t, **kw)
     assert torch.equal(y1[2, :1000], y2[2, :1000]) and torch.equal(y1[[0, 1, 3]], y2[[0, 1, 3]])
+
+
+def test_pair_mode_cta_group_2(golden_dir, monkeypatch):
+    """The opt-in CTA-pair build of the layer kernel (tcgen05 cta_group::2, DC_PAIR=1) computes the same thing."""
+    monkeypatch.setenv("DC_PAIR", "1")
+    g = np.load(os.path.join(golden_dir, "small_masked.npz"))
+    m, sd = make_model(2, 7, "bf16")                      # a fresh handle reads DC_PAIR at creation
+    B, T = 3, 40
+    xf_proj, xf_out = synth_features(B, T, seed=11)
+    _, x = synth_inputs(B, T, seed=11)
+    length = [int(v) for v in g["length"]]
+    y = m(x.cuda(), torch.from_numpy(g["t"]).cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    close(y, g["forward"], "bf16", "pair-mode forward vs reference golden")
+    m8, sd8 = make_model(8, 0, "bf16")
+    xf_proj, xf_out = synth_features(5, 300, seed=3)       # odd tile count -> padding tile in the last pair; fused reduction off/on
+    _, x = synth_inputs(5, 300, seed=3)
+    t = torch.tensor([3, 0, 24, 7, 11])
+    y = m8(x.cuda(), t.cuda(), length=[300, 300, 17, 300, 299], xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    with torch.no_grad():
+        ref = O.motion_transformer_forward(sd8, x, t, [300, 300, 17, 300, 299], xf_proj, xf_out)
+    close(y, ref, "bf16", "pair-mode forward B=5 T=300")
+
+
+def test_fused_time_axis_reduction_both_ways(monkeypatch):
+    """The time-axis softmax + K^T V reduction fused into the layer kernel (default for T >= 512) and the stand-alone
+    kv_reduce kernel agree with the oracle on the same inputs (T = 300: 2-3 tiles per clip, clips straddling tiles)."""
+    B, T = 4, 300
+    xf_proj, xf_out = synth_features(B, T, seed=9)
+    _, x = synth_inputs(B, T, seed=9)
+    t = torch.tensor([24, 1, 13, 0])
+    length = [300, 120, 300, 299]
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("DC_FUSE_KV", flag)
+        m, sd = make_model(3, 5, "fp16")
+        y = m(x.cuda(), t.cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+        with torch.no_grad():
+            ref = O.motion_transformer_forward(sd, x, t, length, xf_proj, xf_out)
+        close(y, ref, "fp16", f"forward, DC_FUSE_KV={flag}")
+        outs.append(y)
+    close(outs[0], outs[1], "fp16", "fused vs stand-alone reduction")
+
+
+def test_ddpm_1000_steps_small():
+    """BASELINE.json configs[4] sampler (1000-step DDPM) at a small shape: the whole stochastic trajectory with a fixed
+    noise stream against the oracle."""
+    m, sd = make_model(2, 13, "fp16")
+    B, T, S = 2, 24, 1000
+    xf_proj, xf_out = synth_features(B, T, seed=4)
+    _, x = synth_inputs(B, T, seed=4)
+    d = diffusion(S)
+    gen = torch.Generator().manual_seed(99)
+    step_noise = torch.randn(S, B, T, 26, generator=gen)
+    eng = d._bind(m, x.cuda(), dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B))
+    xs = x.cuda().clone()
+    eng.sample_loop(_lib.DC_SAMPLER_DDPM, xs, step_noise=step_noise.cuda())
+    ref, _, _ = O.sample_loop(sd, O.Tables(O.linear_betas(S)), x, [T] * B, xf_proj, xf_out, kind="ddpm", step_noise=step_noise)
+    assert torch.isfinite(xs).all()
+    close(xs, ref, "bf16", "1000-step DDPM final sample (fp16 operands, bf16-level bound over 1000 stochastic steps)")
+    # the public API draws the same per-step noise from torch's generator as the reference does
+    torch.manual_seed(5)
+    a = d.p_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False,
+                        model_kwargs=dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B))
+    torch.manual_seed(5)
+    b = d.p_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False,
+                        model_kwargs=dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B))
+    assert torch.equal(a, b) and not torch.equal(a, xs)
