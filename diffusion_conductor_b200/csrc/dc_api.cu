@@ -358,6 +358,7 @@ LayerArgs layer_args(dc_handle* h, int l) {
         a.dops[n++] = make_dop(base + kOffWq, 32768, 2, 128, kColS, false, 1, 255);
         a.dops[n++] = make_dop(base + kOffWk, 32768, 2, 128, kColS + 128, false, 0, 255, 0, false, true);
         a.dops[n++] = make_dop(base + kOffWv, 32768, 2, 128, kColW, false, 0, 2, 0, false, true);
+        if (h->fuse_kv && !h->use_pair) a.dops[n++] = make_dop(0, 0, 1, 128, kColW, false, 1, 255, 3);   // K^T V partial (tensor cores)
     }
     a.n_d = n;
     a.M = h->M;

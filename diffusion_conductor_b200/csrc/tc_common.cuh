@@ -178,6 +178,32 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major (transposed) operand, SWIZZLE_128B: the image is the same [rows x 64]-block image, read with the
+// block's 128-byte rows as the K index (8 rows = one K atom, 1024 B apart -> SBO) and the 64 elements of a row
+// as the M/N index (blocks of 64 are kABlockBytes apart -> LBO).  Used for K^T V, where the contraction runs
+// over tokens.  One MMA consumes K = 16 = two K atoms; advance the start address by 2048 B per step.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(kABlockBytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+template <bool kBf16>
+__device__ __forceinline__ constexpr uint32_t make_idesc_mn(int M, int N) {   // both operands MN-major
+    return (1u << 4) | ((kBf16 ? 1u : 0u) << 7) | ((kBf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// order-preserving float <-> int key (for redux.sync max on floats)
+__device__ __forceinline__ int f2key(float x) {
+    const int i = __float_as_int(x);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 //   [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt (0=f16, 1=bf16) | [17,23) N>>3 | [24,29) M>>4
 template <bool kBf16>

@@ -262,7 +262,7 @@ struct DOp {
     uint8_t pad;
 };
 
-constexpr int kMaxDOps = 12;
+constexpr int kMaxDOps = 13;
 constexpr int kKvPartFloats = 128 + 128 + kH * 256;
 constexpr int kMaxSOps = 3;
 
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             uint32_t it = 0;
             for (int o = 0; o < a.n_d; ++o) {
                 const DOp op = a.dops[o];
-                if (op.ring_a) continue;
+                if (op.ring_a || op.seg == 3) continue;       // seg 3: operands come from the row threads, not from memory
                 const int n_st = op.seg ? segs.n_seg : 1;
                 const uint32_t kb_bytes = op.w_bytes / op.kb, share = kb_bytes / kHalf;
                 for (int s = 0; s < n_st; ++s) {
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 }
                 uint32_t total = 0;
                 for (int o = 0; o < a.n_d; ++o)
-                    if (!a.dops[o].ring_a) total += (a.dops[o].seg ? segs.n_seg : 1) * a.dops[o].kb;
+                    if (!a.dops[o].ring_a && a.dops[o].seg != 3) total += (a.dops[o].seg ? segs.n_seg : 1) * a.dops[o].kb;
                 for (uint32_t it = 0; it < total; ++it) {
                     const uint32_t st = it % kNB, ph = (it / kNB) & 1u;
                     mbar_wait(smem_u32(&bars->fullB[st]), ph);
@@ -706,6 +706,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t idesc = make_idesc<kBf16>(kM, op.n);
                 const uint32_t kb_stride = (uint32_t)op.n * 128u / kHalf;     // bytes of one k-block of this CTA's B share
+                if (op.seg == 3) {
+                    // K^T V partial of this tile: E^T . V over the 128 tokens, both operands MN-major images written by
+                    // the row threads (E at ring A, V behind it); one pass per clip segment of the tile.
+                    if constexpr (!kPair) {
+                        const int nvalid = max(0, min(kTileRows, a.M - (int)blockIdx.x * kTileRows));
+                        const int e_rows = min(nvalid, ((int)blockIdx.x * kTileRows / a.T + 1) * a.T - (int)blockIdx.x * kTileRows);
+                        const int passes = nvalid > e_rows ? 2 : 1;
+                        const uint32_t idmn = make_idesc_mn<kBf16>(kTileRows, kTileRows);
+                        const uint32_t eimg = smem_u32(ringA), vimg = eimg + kAworkBytes;
+                        for (int ps = 0; ps < passes; ++ps) {
+                            if (ps > 0) {
+                                mbar_wait(smem_u32(&bars->a_ready), a_phase & 1u);
+                                ++a_phase;
+                                tc_fence_after();
+                            }
+                            for (int ks = 0; ks < 8; ++ks)
+                                umma_f16(tmem_base + kColW, make_desc_mnmajor_sw128(eimg + ks * 2048), make_desc_mnmajor_sw128(vimg + ks * 2048),
+                                         idmn, ks > 0);
+                            umma_commit(smem_u32(&bars->d_ready[2]));
+                        }
+                    }
+                    tl_mark(a, 200 + d_idx);
+                    continue;
+                }
                 if (op.ring_a) {            // whole operand in one ring-A stage
                     const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
                     mbar_wait(smem_u32(&bars->fullA[st]), ph);
@@ -903,6 +927,178 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         dst[i * 128] = keep ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else if (!kPair) {
+                // Fused time-axis softmax + K^T V (reference :111,:117) on the tensor cores.  With T >= 128 a tile touches
+                // at most two clips.  Per clip segment of the tile: column maxima (redux.sync over the warp's 32 rows +
+                // a 4-way combine through shared memory), E = exp(k - max) and V written as 16-bit MN-major operand
+                // images, P = E^T V as 8 MMAs (contraction over the tile's tokens), column sums by integer redux.  The
+                // partial (max, sum, diagonal 16x16 blocks of P) goes to global memory; the CTA that completes a clip
+                // merges its partials into the clip's block-diagonal B-operand image for the next layer.
+                float* pm = reinterpret_cast<float*>(ringB);           // [4 lq][2 seg][128] exchange (max, then sums)
+                float* msm = pm + 1024;                                // [2][128] maxima
+                float* ssm = msm + 256;                                // [2][128] sums
+                int* flags = reinterpret_cast<int*>(ssm + 256);
+                const uint32_t eimg = smem_u32(ringA), vimg = eimg + kAworkBytes;
+                const int row0 = blockIdx.x * kTileRows;
+                const int first_clip = row0 / a.T;
+                const int nvalid = max(0, min(kTileRows, a.M - row0));
+                const int e = min(nvalid, (first_clip + 1) * a.T - row0);   // rows [0,e): first clip, [e,nvalid): next clip
+                const int n_seg = nvalid == 0 ? 0 : (nvalid > e ? 2 : 1);
+                const int tx = threadIdx.x;
+                const bool in_tile = (int)r < nvalid;
+                const int myseg = (int)r >= e ? 1 : 0;
+                const bool warp_lo = (int)(lq * 32) < e, warp_hi = (int)(lq * 32 + 31) >= e;      // segments present in this warp
+                float kx[32];
+                tmem_ld32(trow + kColS + 128 + c0, kx);
+                tmem_wait_ld();
+                add_bias32(kx, prm_sa + kPrmSaBk + c0);
+                {   // column maxima of this warp's 32 rows, per segment; lane i keeps column c0 + i
+                    int k0 = f2key(-INFINITY), k1 = k0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float x = kx[i];
+                        if (!keep) x += -1000000.f;
+                        if (!in_tile) x = -INFINITY;
+                        kx[i] = x;
+                        const int key = f2key(x);
+                        if (warp_lo) {
+                            const int m = __reduce_max_sync(0xffffffffu, myseg == 0 ? key : f2key(-INFINITY));
+                            if ((int)lane == i) k0 = m;
+                        }
+                        if (warp_hi) {
+                            const int m = __reduce_max_sync(0xffffffffu, myseg == 1 ? key : f2key(-INFINITY));
+                            if ((int)lane == i) k1 = m;
+                        }
+                    }
+                    pm[(lq * 2 + 0) * 128 + c0 + lane] = key2f(k0);
+                    pm[(lq * 2 + 1) * 128 + c0 + lane] = key2f(k1);
+                }
+                named_bar_sync(5, kRowThreads);
+                if (tx < 256) {
+                    const int sg = tx >> 7, col = tx & 127;
+                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
+                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
+                }
+                named_bar_sync(5, kRowThreads);
+                {   // E = exp(k - max) (0 for padding rows), image + fixed-point column sums
+                    const float* mrow = msm + myseg * 128 + c0;
+                    unsigned s0 = 0, s1 = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float ev = in_tile ? exp2f((kx[i] - mrow[i]) * 1.4426950408889634f) : 0.f;
+                        kx[i] = ev;
+                        const unsigned q20 = __float2uint_rn(ev * 1048576.f);
+                        if (warp_lo) {
+                            const unsigned t0 = __reduce_add_sync(0xffffffffu, myseg == 0 ? q20 : 0u);
+                            if ((int)lane == i) s0 = t0;
+                        }
+                        if (warp_hi) {
+                            const unsigned t1 = __reduce_add_sync(0xffffffffu, myseg == 1 ? q20 : 0u);
+                            if ((int)lane == i) s1 = t1;
+                        }
+                    }
+                    store_a16<kBf16>(eimg, r, c0, kx);
+                    store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
+                    pm[(lq * 2 + 0) * 128 + c0 + lane] = (float)s0 * (1.f / 1048576.f);
+                    pm[(lq * 2 + 1) * 128 + c0 + lane] = (float)s1 * (1.f / 1048576.f);
+                }
+                float vx[32];
+                tmem_ld32(trow + kColW + c0, vx);
+                tmem_wait_ld();
+                add_bias32(vx, prm_sa + kPrmSaBv + c0);
+                if (!keep) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) vx[i] = 0.f;
+                }
+                for (int ps = 0; ps < max(n_seg, 1); ++ps) {
+                    {   // V image of this pass: rows of the other segment (and padding rows) are zero
+                        float z[32];
+                        const bool mine = in_tile && myseg == ps;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[i] = mine ? vx[i] : 0.f;
+                        store_a16<kBf16>(vimg, r, c0, z);
+                        store_a16<kBf16>(vimg, r, c0 + 16, z + 16);
+                    }
+                    rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
+                    if (ps == 0) {
+                        named_bar_sync(5, kRowThreads);
+                        if (tx < 256) {
+                            const int sg = tx >> 7, col = tx & 127;
+                            ssm[tx] = (pm[(0 + sg) * 128 + col] + pm[(2 + sg) * 128 + col]) + (pm[(4 + sg) * 128 + col] + pm[(6 + sg) * 128 + col]);
+                        }
+                    }
+                    rows_wait(bars, 2, ph[2]);
+                    if (ps < n_seg) {
+                        float* P = a.kv_part + ((size_t)blockIdx.x * 2 + ps) * kKvPartFloats;
+                        if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
+                            float pr[32];
+                            tmem_ld32(trow + kColW + 32 * lq, pr);
+                            tmem_wait_ld();
+                            float4* dst = reinterpret_cast<float4*>(P + 256 + (r >> 4) * 256 + (r & 15) * 16);
+                            const int o = (lane & 16);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
+                                           : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
+                        }
+                        named_bar_sync(5, kRowThreads);                    // ssm written (pass 0) / everyone done reading W
+                        if (tx < 128) P[tx] = msm[ps * 128 + tx], P[128 + tx] = ssm[ps * 128 + tx];
+                    }
+                }
+                __threadfence();
+                named_bar_sync(5, kRowThreads);
+                if (tx == 0) {
+                    for (int sg = 0; sg < 2; ++sg) {
+                        flags[sg] = 0;
+                        if (sg < n_seg) {
+                            const int clip = first_clip + sg;
+                            const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
+                            const int old = atomicAdd(a.clip_cnt + clip, 1);
+                            if (old + 1 == ntiles) {
+                                flags[sg] = 1;
+                                a.clip_cnt[clip] = 0;          // ready for the next launch
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(5, kRowThreads);
+                const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    if (!flags[sg]) continue;
+                    __threadfence();
+                    const int clip = first_clip + sg;
+                    const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
+                    float M0 = -INFINITY, M1 = -INFINITY;
+                    for (int ti = t_first; ti <= t_last; ++ti) {
+                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                        M0 = fmaxf(M0, __ldcg(P + 16 * hh + d0));
+                        M1 = fmaxf(M1, __ldcg(P + 16 * hh + d0 + 1));
+                    }
+                    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
+                    for (int ti = t_first; ti <= t_last; ++ti) {
+                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                        const float w0 = expf(__ldcg(P + 16 * hh + d0) - M0), w1 = expf(__ldcg(P + 16 * hh + d0 + 1) - M1);
+                        s0 = fmaf(__ldcg(P + 128 + 16 * hh + d0), w0, s0);
+                        s1 = fmaf(__ldcg(P + 128 + 16 * hh + d0 + 1), w1, s1);
+                        const float* Pa = P + 256 + hh * 256;
+                        const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
+                        const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
+                        a00 = fmaf(r0.x, w0, a00), a01 = fmaf(r0.y, w0, a01);
+                        a10 = fmaf(r1.x, w1, a10), a11 = fmaf(r1.y, w1, a11);
+                    }
+                    uint8_t* img = a.bd_sa_out + (size_t)clip * kAworkBytes;
+                    const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};
+#pragma unroll
+                    for (int dd = 0; dd < 2; ++dd) {
+                        const int ki = 16 * hh + d0 + dd;
+                        uint8_t* base = img + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
+#pragma unroll
+                        for (int ll = 0; ll < 2; ++ll) {
+                            const int nj = 16 * hh + l0 + ll;
+                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
+                        }
+                    }
                 }
             } else {
                 // Fused time-axis softmax + K^T V (reference :111,:117).  With T >= 128 a tile touches at most two
