@@ -930,15 +930,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 }
             } else if (!kPair) {
                 // Fused time-axis softmax + K^T V (reference :111,:117) on the tensor cores.  With T >= 128 a tile touches
-                // at most two clips.  Per clip segment of the tile: column maxima (redux.sync over the warp's 32 rows +
-                // a 4-way combine through shared memory), E = exp(k - max) and V written as 16-bit MN-major operand
-                // images, P = E^T V as 8 MMAs (contraction over the tile's tokens), column sums by integer redux.  The
-                // partial (max, sum, diagonal 16x16 blocks of P) goes to global memory; the CTA that completes a clip
-                // merges its partials into the clip's block-diagonal B-operand image for the next layer.
-                float* pm = reinterpret_cast<float*>(ringB);           // [4 lq][2 seg][128] exchange (max, then sums)
+                // at most two clips.  Two 32 KB operand-image buffers X, Y are all the scratch it needs:
+                //   k (16-bit) -> X ; per-segment column maxima by a column scan of X ; E = exp(k - max) -> X ;
+                //   V -> Y (rows of the other segment zeroed) ; P = E^T V as 8 MN-major MMAs over the tile's tokens ;
+                //   per-segment column sums by a column scan of the E image (same rounded values as the MMA sees).
+                // The partial (max, sum, diagonal 16x16 blocks of P) goes to global memory; the CTA that completes a clip
+                // merges its partials (online-softmax rescaling) into the clip's block-diagonal B-operand image.
+                float* pm = reinterpret_cast<float*>(ringB);           // [4 qr][2 seg][128] exchange (max, then sums)
                 float* msm = pm + 1024;                                // [2][128] maxima
                 float* ssm = msm + 256;                                // [2][128] sums
                 int* flags = reinterpret_cast<int*>(ssm + 256);
+                uint8_t* Xp = ringA;
                 const uint32_t eimg = smem_u32(ringA), vimg = eimg + kAworkBytes;
                 const int row0 = blockIdx.x * kTileRows;
                 const int first_clip = row0 / a.T;
@@ -948,69 +950,63 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 const int tx = threadIdx.x;
                 const bool in_tile = (int)r < nvalid;
                 const int myseg = (int)r >= e ? 1 : 0;
-                const bool warp_lo = (int)(lq * 32) < e, warp_hi = (int)(lq * 32 + 31) >= e;      // segments present in this warp
+                const int col = tx & 127, qr = tx >> 7;
+                // element (row, col) of a [128 x 128] 16-bit operand image
+                auto img_at = [&](int row) -> const uint16_t* {
+                    return reinterpret_cast<const uint16_t*>(Xp + (col >> 6) * kABlockBytes + sw128_offset(row, (col & 63) >> 3) + (col & 7) * 2);
+                };
+                auto to_f = [](uint16_t u) -> float {
+                    if constexpr (kBf16) return __uint_as_float((uint32_t)u << 16);
+                    else return __half2float(__ushort_as_half(u));
+                };
                 float kx[32];
                 tmem_ld32(trow + kColS + 128 + c0, kx);
                 tmem_wait_ld();
                 add_bias32(kx, prm_sa + kPrmSaBk + c0);
-                {   // column maxima of this warp's 32 rows, per segment; lane i keeps column c0 + i
-                    int k0 = f2key(-INFINITY), k1 = k0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = kx[i];
-                        if (!keep) x += -1000000.f;
-                        if (!in_tile) x = -INFINITY;
-                        kx[i] = x;
-                        const int key = f2key(x);
-                        if (warp_lo) {
-                            const int m = __reduce_max_sync(0xffffffffu, myseg == 0 ? key : f2key(-INFINITY));
-                            if ((int)lane == i) k0 = m;
-                        }
-                        if (warp_hi) {
-                            const int m = __reduce_max_sync(0xffffffffu, myseg == 1 ? key : f2key(-INFINITY));
-                            if ((int)lane == i) k1 = m;
-                        }
-                    }
-                    pm[(lq * 2 + 0) * 128 + c0 + lane] = key2f(k0);
-                    pm[(lq * 2 + 1) * 128 + c0 + lane] = key2f(k1);
+                for (int i = 0; i < 32; ++i) {
+                    if (!keep) kx[i] += -1000000.f;
+                    if (!in_tile) kx[i] = -INFINITY;
+                    if constexpr (!kBf16) kx[i] = fmaxf(kx[i], -60000.f);      // fp16 image of k: keep the mask finite
                 }
-                named_bar_sync(5, kRowThreads);
-                if (tx < 256) {
-                    const int sg = tx >> 7, col = tx & 127;
-                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
-                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
-                }
-                named_bar_sync(5, kRowThreads);
-                {   // E = exp(k - max) (0 for padding rows), image + fixed-point column sums
-                    const float* mrow = msm + myseg * 128 + c0;
-                    unsigned s0 = 0, s1 = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float ev = in_tile ? exp2f((kx[i] - mrow[i]) * 1.4426950408889634f) : 0.f;
-                        kx[i] = ev;
-                        const unsigned q20 = __float2uint_rn(ev * 1048576.f);
-                        if (warp_lo) {
-                            const unsigned t0 = __reduce_add_sync(0xffffffffu, myseg == 0 ? q20 : 0u);
-                            if ((int)lane == i) s0 = t0;
-                        }
-                        if (warp_hi) {
-                            const unsigned t1 = __reduce_add_sync(0xffffffffu, myseg == 1 ? q20 : 0u);
-                            if ((int)lane == i) s1 = t1;
-                        }
-                    }
-                    store_a16<kBf16>(eimg, r, c0, kx);
-                    store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
-                    pm[(lq * 2 + 0) * 128 + c0 + lane] = (float)s0 * (1.f / 1048576.f);
-                    pm[(lq * 2 + 1) * 128 + c0 + lane] = (float)s1 * (1.f / 1048576.f);
-                }
+                store_a16<kBf16>(eimg, r, c0, kx);
+                store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
                 float vx[32];
                 tmem_ld32(trow + kColW + c0, vx);
                 tmem_wait_ld();
                 add_bias32(vx, prm_sa + kPrmSaBv + c0);
+                named_bar_sync(5, kRowThreads);
+                {   // column maxima per segment: this thread scans rows [32 qr, 32 qr + 32) of column `col`
+                    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = 32 * qr + rr;
+                        const float x = to_f(*img_at(row));
+                        if (row < e) m0 = fmaxf(m0, x);
+                        else m1 = fmaxf(m1, x);
+                    }
+                    pm[(qr * 2 + 0) * 128 + col] = m0;
+                    pm[(qr * 2 + 1) * 128 + col] = m1;
+                }
+                named_bar_sync(5, kRowThreads);
+                if (tx < 256) {
+                    const int sg = tx >> 7;
+                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
+                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
+                }
+                named_bar_sync(5, kRowThreads);
+                {   // E = exp(k - max) (0 for padding rows) -> X ; V of the first segment -> Y
+                    const float* mrow = msm + myseg * 128 + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) kx[i] = in_tile ? exp2f((kx[i] - mrow[i]) * 1.4426950408889634f) : 0.f;
+                    store_a16<kBf16>(eimg, r, c0, kx);
+                    store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
+                }
                 if (!keep) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) vx[i] = 0.f;
                 }
+                if (tx == 0) tl_mark(a, 120);
                 for (int ps = 0; ps < max(n_seg, 1); ++ps) {
                     {   // V image of this pass: rows of the other segment (and padding rows) are zero
                         float z[32];
@@ -1021,14 +1017,27 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         store_a16<kBf16>(vimg, r, c0 + 16, z + 16);
                     }
                     rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
+                    if (tx == 0) tl_mark(a, 122);
                     if (ps == 0) {
+                        named_bar_sync(5, kRowThreads);                    // E image complete
+                        float s0 = 0.f, s1 = 0.f;                          // column sums per segment from the rounded E
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int row = 32 * qr + rr;
+                            const float x = to_f(*img_at(row));
+                            if (row < e) s0 += x;
+                            else s1 += x;
+                        }
+                        pm[(qr * 2 + 0) * 128 + col] = s0;
+                        pm[(qr * 2 + 1) * 128 + col] = s1;
                         named_bar_sync(5, kRowThreads);
                         if (tx < 256) {
-                            const int sg = tx >> 7, col = tx & 127;
+                            const int sg = tx >> 7;
                             ssm[tx] = (pm[(0 + sg) * 128 + col] + pm[(2 + sg) * 128 + col]) + (pm[(4 + sg) * 128 + col] + pm[(6 + sg) * 128 + col]);
                         }
                     }
                     rows_wait(bars, 2, ph[2]);
+                    if (tx == 0) tl_mark(a, 123);
                     if (ps < n_seg) {
                         float* P = a.kv_part + ((size_t)blockIdx.x * 2 + ps) * kKvPartFloats;
                         if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
@@ -1046,46 +1055,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         if (tx < 128) P[tx] = msm[ps * 128 + tx], P[128 + tx] = ssm[ps * 128 + tx];
                     }
                 }
+                if (tx == 0) tl_mark(a, 124);
                 __threadfence();
                 named_bar_sync(5, kRowThreads);
-                if (tx == 0) {
-                    for (int sg = 0; sg < 2; ++sg) {
-                        flags[sg] = 0;
-                        if (sg < n_seg) {
-                            const int clip = first_clip + sg;
-                            const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
-                            const int old = atomicAdd(a.clip_cnt + clip, 1);
-                            if (old + 1 == ntiles) {
-                                flags[sg] = 1;
-                                a.clip_cnt[clip] = 0;          // ready for the next launch
-                            }
+                if (tx == 0 || tx == 32) {          // one arrival counter per clip; both segments in parallel
+                    const int sg = tx >> 5;
+                    int f = 0;
+                    if (sg < n_seg) {
+                        const int clip = first_clip + sg;
+                        const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
+                        const int old = atomicAdd(a.clip_cnt + clip, 1);
+                        if (old + 1 == ntiles) {
+                            f = 1;
+                            a.clip_cnt[clip] = 0;          // ready for the next launch
                         }
                     }
+                    flags[sg] = f;
                 }
                 named_bar_sync(5, kRowThreads);
+                if (tx == 0) tl_mark(a, 125);
                 const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
                 for (int sg = 0; sg < n_seg; ++sg) {
                     if (!flags[sg]) continue;
                     __threadfence();
                     const int clip = first_clip + sg;
                     const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
-                    float M0 = -INFINITY, M1 = -INFINITY;
+                    // one pass with online rescaling
+                    float M0 = -INFINITY, M1 = -INFINITY, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
                     for (int ti = t_first; ti <= t_last; ++ti) {
                         const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
-                        M0 = fmaxf(M0, __ldcg(P + 16 * hh + d0));
-                        M1 = fmaxf(M1, __ldcg(P + 16 * hh + d0 + 1));
-                    }
-                    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
-                    for (int ti = t_first; ti <= t_last; ++ti) {
-                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
-                        const float w0 = expf(__ldcg(P + 16 * hh + d0) - M0), w1 = expf(__ldcg(P + 16 * hh + d0 + 1) - M1);
-                        s0 = fmaf(__ldcg(P + 128 + 16 * hh + d0), w0, s0);
-                        s1 = fmaf(__ldcg(P + 128 + 16 * hh + d0 + 1), w1, s1);
+                        const float mi0 = __ldcg(P + 16 * hh + d0), mi1 = __ldcg(P + 16 * hh + d0 + 1);
+                        const float si0 = __ldcg(P + 128 + 16 * hh + d0), si1 = __ldcg(P + 128 + 16 * hh + d0 + 1);
                         const float* Pa = P + 256 + hh * 256;
                         const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
                         const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
-                        a00 = fmaf(r0.x, w0, a00), a01 = fmaf(r0.y, w0, a01);
-                        a10 = fmaf(r1.x, w1, a10), a11 = fmaf(r1.y, w1, a11);
+                        const float n0 = fmaxf(M0, mi0), n1 = fmaxf(M1, mi1);
+                        const float c0s = __expf(M0 - n0), c1s = __expf(M1 - n1), w0 = __expf(mi0 - n0), w1 = __expf(mi1 - n1);
+                        M0 = n0, M1 = n1;
+                        s0 = fmaf(s0, c0s, si0 * w0), s1 = fmaf(s1, c1s, si1 * w1);
+                        a00 = fmaf(a00, c0s, r0.x * w0), a01 = fmaf(a01, c0s, r0.y * w0);
+                        a10 = fmaf(a10, c1s, r1.x * w1), a11 = fmaf(a11, c1s, r1.y * w1);
                     }
                     uint8_t* img = a.bd_sa_out + (size_t)clip * kAworkBytes;
                     const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};

@@ -12,9 +12,9 @@ from diffusion_conductor_b200.gaussian_diffusion import LossType, ModelMeanType,
 from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict  # noqa: E402
 
 NAMES = {1: "start", 2: "rows_done"}
-ROWW = ["qA_sa", "S_sa", "Wo_sa(H)", "Wq_ca", "qA_ca", "S_ca", "Wo_ca(H)", "W1", "W2", "S_ff", "Wo_ff(H)", "QKV"]
-ROWP = ["film_sa", "ln_ca", "softmax_ca", "film_ca", "h_bf16", "gelu", "film_ff", "ln_sa"]
-DOPS = ["qA_sa", "Wo_sa", "Wq_ca", "qA_ca", "Wo_ca", "W1", "W2", "Wo_ff", "Wq", "Wk", "Wv"]
+ROWW = ["qA_sa", "S_sa", "Wo_sa(H)", "Wq_ca", "qA_ca", "S_ca", "Wo_ca(H)", "W1", "W2", "S_ff", "Wo_ff(H)", "QKV", "KtV pass", "KtV pass2", "?"]
+ROWP = ["film_sa", "ln_ca", "softmax_ca", "film_ca", "h_bf16", "gelu", "film_ff", "ln_sa", "E,V images", "V image 2", "?"]
+DOPS = ["qA_sa", "Wo_sa", "Wq_ca", "qA_ca", "Wo_ca", "W1", "W2", "Wo_ff", "Wq", "Wk", "Wv", "KtV", "?", "?"]
 B, T, S = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (64, 180, 50)))
 m = MotionTransformer(26, num_frames=1800, num_layers=8, latent_dim=128, device="cuda", music_model_path=None)
 m.load_state_dict(synth_state_dict(0), strict=True)
@@ -41,6 +41,8 @@ for launch in (1, 4):
     for t, i in ev:
         if i in NAMES:
             nm = NAMES[i]
+        elif 120 <= i < 130:
+            nm = "rows epi: " + ["col max done", "E image + sums done", "published V", "got KtV", "partials written", "counters done"][i - 120]
         elif 100 < i < 150:
             nm = "rows: got " + ROWW[i - 101] if launch > 0 else f"rows wait {i}"
         elif 150 < i < 200:
