@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/dc_b200.h"
-#include "tile_kernels.cuh"
+#include "step_kernel.cuh"
 
 using namespace dc;
 
@@ -94,7 +94,10 @@ struct dc_handle {
     int mask_invert = 0;
     float* kv_part = nullptr;     // [tiles][2][kKvPartFloats] partial time-axis reductions
     int* clip_cnt = nullptr;      // [B]
+    int* clip_done = nullptr;     // [B] merges completed in the current step (persistent kernel)
     bool fuse_kv = false;
+    bool persist = false;         // whole step in one persistent kernel (tiles <= SMs, T >= 128)
+    int num_sms = 0;
     unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
     bool timeline_on = false;
     long long* length = nullptr;
@@ -219,7 +222,8 @@ DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bo
 void free_workspace(dc_handle* h) {
     if (h->kv_part) cudaFree(h->kv_part);
     if (h->clip_cnt) cudaFree(h->clip_cnt);
-    h->kv_part = nullptr, h->clip_cnt = nullptr;
+    if (h->clip_done) cudaFree(h->clip_done);
+    h->kv_part = nullptr, h->clip_cnt = nullptr, h->clip_done = nullptr;
     void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q_img, h->kv, h->bd_sa, h->bd_ca, h->length,
                     h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
     for (void* p : ptrs)
@@ -256,6 +260,8 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->kv_part, tiles * 2 * (size_t)kKvPartFloats * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->clip_cnt, (size_t)B * 4));
     DC_CUDA(h, cudaMemset(h->clip_cnt, 0, (size_t)B * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->clip_done, (size_t)B * 4));
+    DC_CUDA(h, cudaMemset(h->clip_done, 0, (size_t)B * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->te_b, (size_t)B * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->xwork, Mpad * kP * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->x0work, Mpad * kP * 4));
@@ -280,6 +286,8 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
     return 0;
 }
 
@@ -405,6 +413,21 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
                         h->aemb, h->hbuf));
     h->launches++;
     mark(0);
+    if (h->persist) {
+        StepArgs sa{};
+        sa.L = L, sa.M = M, sa.T = h->T;
+        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.prm = h->prm, sa.h = h->hbuf;
+        sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
+        sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
+        sa.length = h->has_length ? h->length : nullptr;
+        const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
+        for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
+        sa.timeline = h->timeline_on ? h->timeline : nullptr;
+        DC_CUDA(h, cudaMemsetAsync(h->clip_done, 0, (size_t)h->B * 4, st));
+        DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
+        h->launches++;
+        mark(1);
+    } else
     for (int l = -1; l < L; ++l) {
         const LayerArgs la = layer_args(h, l);
         const int rc = h->bf16 ? launch_layer<true>(h, la, h->tiles, st) : launch_layer<false>(h, la, h->tiles, st);
@@ -454,6 +477,7 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     dc_handle* h = new dc_handle();
     h->cfg = *cfg;
     h->bf16 = cfg->operand != DC_OPERAND_FP16;
+    h->num_sms = prop.multiProcessorCount;
     DC_CUDA(h, cudaSetDevice(cfg->device));
     if (int rc = init_kernel_attrs(h)) return rc;
     DC_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
@@ -688,8 +712,13 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         // T = 1800 -> 1.34x faster loop; T = 180 -> 7 % slower than the stand-alone kv_reduce kernel).
         const char* nf = getenv("DC_FUSE_KV");      // "0" / "1" force the choice
         const bool fuse = T >= kTileRows && (nf ? nf[0] == '1' : T >= 4 * kTileRows);
-        if (fuse != h->fuse_kv) drop_graph(h);
+        // One persistent kernel per step when every tile's CTA can be resident at once (in-kernel per-clip
+        // dependency) and a tile touches at most two clips.
+        const char* pe = getenv("DC_PERSIST");
+        const bool persist = T >= kTileRows && h->tiles <= h->num_sms && !h->use_pair && !(pe && pe[0] == '0');
+        if (fuse != h->fuse_kv || persist != h->persist) drop_graph(h);
         h->fuse_kv = fuse;
+        h->persist = persist;
         DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)B * 4, st));
     }
     bool masked = false;
@@ -786,7 +815,7 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
     DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
     set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
     h->launches++;
-    const int64_t per_step = (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
+    const int64_t per_step = h->persist ? 4 : (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
     if (h->use_graphs && !traced) {
         GraphKey key;
         key.sampler = sampler;

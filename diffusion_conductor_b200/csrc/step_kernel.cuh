@@ -1,0 +1,605 @@
+// Persistent whole-step kernel: one CTA per 128-token tile runs ALL decoder layers of a denoise step without
+// leaving the SM.  The residual stream stays in TMEM for the whole step, q stays in shared memory, the FiLM
+// projection of the next layer streams in while the current layer's tail is still being computed, and the one
+// cross-tile dependency of the model -- the time-axis softmax of the self-attention keys, a per-clip reduction --
+// is resolved in-kernel: every tile publishes a (max, sum, K^T V) partial per clip segment, the CTA that completes
+// a clip merges them into the clip's block-diagonal B-operand image and releases a per-clip counter that the
+// consumers' producer lane acquires before loading the image.  Requires every CTA to be co-resident (tiles <= SMs)
+// and T >= 128 (a tile touches at most two clips); otherwise the host falls back to one launch per layer.
+#pragma once
+#include "tile_kernels.cuh"
+
+namespace dc {
+
+constexpr int kPRingAStages = 2;        // persistent kernel: 2 x 48 KB (the FiLM projection is shared-memory-bandwidth bound)
+constexpr int kRedFloats = 1024 + 256 + 256 + 8;
+
+struct StepArgs {
+    int L, M, T;
+    const uint8_t* wbuf;        // packed weights [L][1 MiB]
+    const uint8_t* aemb;        // A_emb image [tiles][8][16 KB]
+    const float* prm;           // [L][kPrmFloats]
+    float* h;                   // blocked [Mpad][128] residual stream (in: h0 from step_begin, out: after the last layer)
+    const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
+    size_t bd_ca_stride;
+    uint8_t* bd_sa_out;         // [B][32 KB] self-attention images (written by the merging CTA, read by the clip's tiles)
+    float* kv_part;             // [tiles][2][kKvPartFloats]
+    int* clip_cnt;              // [B] arrival counters (zero between uses)
+    int* clip_done;             // [B] number of completed merges in this step (zeroed by step_begin)
+    const long long* length;    // [B] or null
+    uint32_t off[12];           // byte offsets of the packed matrices inside a layer slab (see dc_api.cu)
+    unsigned long long* timeline;
+};
+enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, kOWq, kOWk, kOWv };
+
+__device__ __forceinline__ void tl_mark(const StepArgs& a, unsigned long long id) {
+    if (a.timeline != nullptr && blockIdx.x == 0) {
+        const unsigned long long slot = atomicAdd(a.timeline, 1ull);
+        if (slot < 2040) {
+            a.timeline[1 + 2 * slot] = (unsigned long long)clock64();
+            a.timeline[2 + 2 * slot] = id;
+        }
+    }
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_constant__ StepArgs a) {
+    constexpr bool kPair = false;
+    constexpr int kNA = kPRingAStages, kSA = kStageBytes, kNB = kRingBStages, kSB = kRingBStageBytes;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ringA = smem;
+    uint8_t* ringB = ringA + kNA * kSA;                               // also the V image of the fused reduction
+    uint8_t* awork_p = ringB + kNB * kSB;
+    uint8_t* xbuf = awork_p + kAworkBytes;                            // k / E image of the fused reduction
+    float* prm = reinterpret_cast<float*>(xbuf + kAworkBytes);        // [kPrmFloats] layer `it`
+    float* prm_sa = prm + kPrmFloats;                                 // [384] SA biases of layer it + 1
+    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);           // [4][128]
+    float* red = reinterpret_cast<float*>(xchg + 512);                // kRedFloats
+    LayerBarriers* bars = reinterpret_cast<LayerBarriers*>(red + kRedFloats);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = a.L;
+
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 384; i += kTileThreads) prm_sa[i] = a.prm[i];         // SA biases of layer 0
+    if (warp == kProducerWarp && lane == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->fullA[i]), 1), mbar_init(smem_u32(&bars->emptyA[i]), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->fullB[i]), 1), mbar_init(smem_u32(&bars->emptyB[i]), 1);
+        mbar_init(smem_u32(&bars->a_ready), kRowWarps);
+        mbar_init(smem_u32(&bars->s_free), kRowWarps);
+        mbar_init(smem_u32(&bars->q_full), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
+    if (threadIdx.x == 0) tl_mark(a, 1);
+
+    RowSegs segs;
+    segs.init((int)blockIdx.x, kTileRows, a.M, a.T);
+
+    if (warp == kProducerWarp) {
+        // ---------------- ring A: per layer 3 FiLM projections (8 stages each), then Wk, Wv of the next layer
+        if (lane == 0) {
+            const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
+            uint32_t it_ = 0;
+            auto stage_in = [&](const uint8_t* a_src, const uint8_t* w_src, uint32_t w_bytes) {
+                const uint32_t st = it_ % kNA, ph = (it_ / kNA) & 1u;
+                ++it_;
+                mbar_wait(smem_u32(&bars->emptyA[st]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bars->fullA[st]);
+                uint8_t* stage = ringA + st * kSA;
+                mbar_arrive_expect_tx(full, w_bytes + (a_src ? kStageABytes : 0));
+                if (a_src) bulk_g2s(smem_u32(stage), a_src, kStageABytes, full);
+                bulk_g2s(smem_u32(stage + kStageABytes), w_src, w_bytes, full);
+            };
+            for (int it = -1; it < L; ++it) {
+                if (it >= 0) {
+                    const uint8_t* slab = a.wbuf + ((size_t)it << 20);
+                    const uint32_t so[3] = {a.off[kOWeSa], a.off[kOWeCa], a.off[kOWeFf]};
+                    for (int o = 0; o < 3; ++o)
+                        for (int s = 0; s < kSopStages; ++s) stage_in(a_img + (size_t)s * kStageABytes, slab + so[o] + (size_t)s * kStageWBytes, kStageWBytes);
+                }
+                if (it + 1 < L) {
+                    const uint8_t* slab = a.wbuf + ((size_t)(it + 1) << 20);
+                    stage_in(nullptr, slab + a.off[kOWk], 32768);
+                    stage_in(nullptr, slab + a.off[kOWv], 32768);
+                }
+            }
+        }
+    } else if (warp == kProducerBWarp) {
+        // ---------------- ring B (one k-block per stage): dependent-GEMM weights and per-clip attention images
+        if (lane == 0) {
+            uint32_t it_ = 0;
+            auto load = [&](const uint8_t* src, int kb, uint32_t kb_bytes) {
+                for (int k = 0; k < kb; ++k, ++it_) {
+                    const uint32_t st = it_ % kNB, ph = (it_ / kNB) & 1u;
+                    mbar_wait(smem_u32(&bars->emptyB[st]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bars->fullB[st]);
+                    mbar_arrive_expect_tx(full, kb_bytes);
+                    bulk_g2s(smem_u32(ringB + st * kSB), src + (size_t)k * kb_bytes, kb_bytes, full);
+                }
+            };
+            for (int it = -1; it < L; ++it) {
+                if (it >= 0) {
+                    const uint8_t* slab = a.wbuf + ((size_t)it << 20);
+                    for (int s = 0; s < segs.n_seg; ++s) {           // y = q . blockdiag(A_sa): wait for the clip's merge
+                        const int clip = segs.first_clip + s;
+                        int done;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.clip_done + clip) : "memory");
+                        } while (done < it + 1);
+                        asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the merger -> bulk (async proxy) read
+                        load(a.bd_sa_out + (size_t)clip * kAworkBytes, 2, 16384);
+                    }
+                    load(slab + a.off[kOWoSa], 2, 16384);
+                    load(slab + a.off[kOWqCa], 2, 16384);
+                    for (int s = 0; s < segs.n_seg; ++s)
+                        load(a.bd_ca + (size_t)(segs.first_clip + s) * a.bd_ca_stride + (size_t)it * kAworkBytes, 2, 16384);
+                    load(slab + a.off[kOWoCa], 2, 16384);
+                    load(slab + a.off[kOW1], 2, 8192);
+                    load(slab + a.off[kOW2], 1, 16384);
+                    load(slab + a.off[kOWoFf], 2, 16384);
+                }
+                if (it + 1 < L) load(a.wbuf + ((size_t)(it + 1) << 20) + a.off[kOWq], 2, 16384);
+            }
+        }
+    } else if (warp == kRelayWarp) {
+        // ---------------- issuer of the FiLM projections S = A_emb . We (ring A), gated only by s_free
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
+            uint32_t sj = 0;
+            for (int it = 0; it < L; ++it) {
+                const uint32_t base_it = (uint32_t)it * 26 + 2;        // ring-A items before this layer: 2 (Wk,Wv of layer 0) + 26 per layer
+                for (int o = 0; o < 3; ++o, ++sj) {
+                    mbar_wait(smem_u32(&bars->s_free), sj & 1u);
+                    tc_fence_after();
+                    for (int sgi = 0; sgi < kSopStages; ++sgi) {
+                        const uint32_t itA = base_it + o * kSopStages + sgi;
+                        const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
+                        mbar_wait(smem_u32(&bars->fullA[st]), ph);
+                        tc_fence_after();
+                        const uint32_t stage = smem_u32(ringA + st * kSA);
+                        umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, sgi > 0);
+                        umma_commit(smem_u32(&bars->emptyA[st]));
+                    }
+                    umma_commit(smem_u32(&bars->d_ready[0]));
+                    tl_mark(a, 310 + o);
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ---------------- issuer of the dependent GEMMs, strictly in chain order with blocking waits
+        if (lane == 0) {
+            const uint32_t awork = smem_u32(awork_p);
+            uint32_t itB = 0, a_phase = 0;
+            auto wait_a = [&]() {
+                mbar_wait(smem_u32(&bars->a_ready), a_phase & 1u);
+                ++a_phase;
+                tc_fence_after();
+            };
+            // B operand through ring B, one k-block per stage; optional lane mask (clip segment)
+            auto gemm_b = [&](int kb, int n, uint32_t d_col, bool acc, const uint32_t* mask) {
+                const uint32_t idesc = make_idesc<kBf16>(kTileRows, n);
+                for (int k = 0; k < kb; ++k, ++itB) {
+                    const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
+                    mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                    tc_fence_after();
+                    const uint32_t b_base = smem_u32(ringB + st * kSB);
+                    if (mask) umma_kblock_masked(tmem_base + d_col, awork + k * kABlockBytes, b_base, idesc, k > 0, mask);
+                    else umma_kblock(tmem_base + d_col, awork + k * kABlockBytes, b_base, idesc, acc || k > 0);
+                    umma_commit(smem_u32(&bars->emptyB[st]));
+                }
+            };
+            auto seg_gemm = [&]() {
+                for (int s = 0; s < segs.n_seg; ++s) {
+                    uint32_t m[8];
+                    segs.mask(s, m, false);
+                    gemm_b(2, 128, kColW, false, m);
+                }
+            };
+            auto done = [&](int which) { umma_commit(smem_u32(&bars->d_ready[which])); };
+            const int nvalid = max(0, min(kTileRows, a.M - (int)blockIdx.x * kTileRows));
+            const int e_rows = min(nvalid, ((int)blockIdx.x * kTileRows / a.T + 1) * a.T - (int)blockIdx.x * kTileRows);
+            const int passes = nvalid > e_rows ? 2 : 1;
+            const uint32_t idmn = make_idesc_mn<kBf16>(kTileRows, kTileRows);
+            const uint32_t idesc128 = make_idesc<kBf16>(kTileRows, 128);
+            for (int it = -1; it < L; ++it) {
+                if (it >= 0) {
+                    seg_gemm(), done(2), tl_mark(a, 200);                          // y = q . blockdiag(A_sa)   (q published with the K^T V operands)
+                    wait_a(), gemm_b(2, 128, kColH, true, nullptr), done(1), tl_mark(a, 201);   // h += . Wo_sa
+                    wait_a(), gemm_b(2, 128, kColW, false, nullptr), done(2), tl_mark(a, 202);  // q_ca
+                    wait_a(), seg_gemm(), done(2), tl_mark(a, 203);                // y = softmax(q) . blockdiag(A_ca)
+                    wait_a(), gemm_b(2, 128, kColH, true, nullptr), done(1), tl_mark(a, 204);   // h += . Wo_ca
+                    wait_a(), gemm_b(2, 64, kColW, false, nullptr), done(2), tl_mark(a, 205);   // FFN up
+                    wait_a(), gemm_b(1, 128, kColW, false, nullptr), done(2), tl_mark(a, 206);  // FFN down
+                    wait_a(), gemm_b(2, 128, kColH, true, nullptr), done(1), tl_mark(a, 207);   // h += . Wo_ffn
+                }
+                if (it + 1 < L) {
+                    wait_a();
+                    gemm_b(2, 128, kColS, false, nullptr);                         // q -> S[0:128]
+                    const uint32_t itA0 = (uint32_t)(it + 1) * 26;                 // Wk, Wv of layer it+1 in ring A
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t itA = itA0 + j;
+                        const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
+                        mbar_wait(smem_u32(&bars->fullA[st]), ph);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(ringA + st * kSA + kStageABytes);
+                        for (int k = 0; k < 2; ++k)
+                            umma_kblock(tmem_base + (j == 0 ? kColS + 128 : kColW), awork + k * kABlockBytes, b_base + k * 16384, idesc128, k > 0);
+                        umma_commit(smem_u32(&bars->emptyA[st]));
+                    }
+                    done(2), tl_mark(a, 208);
+                    for (int ps = 0; ps < passes; ++ps) {                          // K^T V partial(s): E^T . V, MN-major images
+                        wait_a();
+                        const uint32_t eimg = smem_u32(xbuf), vimg = smem_u32(ringB);
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_f16(tmem_base + kColW, make_desc_mnmajor_sw128(eimg + ks * 2048), make_desc_mnmajor_sw128(vimg + ks * 2048), idmn, ks > 0);
+                        done(2), tl_mark(a, 209);
+                    }
+                }
+            }
+        }
+    } else {
+        const uint32_t a_ready_addr = smem_u32(&bars->a_ready);
+        const uint32_t s_free_addr = smem_u32(&bars->s_free);
+        const uint32_t lq = warp & 3, cq = warp >> 2;
+        const uint32_t r = lq * 32 + lane;            // row of the tile == TMEM lane
+        const uint32_t c0 = cq * 32;                  // first of this thread's 32 features (heads 2cq, 2cq+1)
+        const uint32_t trow = tmem_base + ((lq * 32) << 16);
+        const uint32_t awork = smem_u32(awork_p);
+        const long g = (long)blockIdx.x * kTileRows + r;
+        const bool valid = g < a.M;
+        const int b = valid ? (int)(g / a.T) : 0;
+        const int t = valid ? (int)(g - (long)b * a.T) : 0;
+        const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
+        uint32_t ph[3] = {0, 0, 0};
+        RowStats rs{xchg, 1 + lq, r, cq, 0};
+        float mean, rstd;
+        float v[32];
+
+        // ---- residual stream -> TMEM (stays there for the whole step)
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.h + blk_index(g, c0, kD));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 f = valid ? src[i * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
+            }
+            tmem_st32(trow + kColH + c0, v);
+            tmem_wait_st();
+        }
+
+        for (int it = -1; it < L; ++it) {
+            if (it >= 0) {
+            // ================= self-attention tail: y = q . blockdiag(A_sa) (tensor cores) ; h += Styl(y)
+                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 101);
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                row_stats32(rs, v, mean, rstd);
+                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 102);                                   // S = A_emb . We_sa
+                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
+                tc_fence_before();                                           // S consumed: the next FiLM projection may start
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(s_free_addr);
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
+    
+                // ================= cross-attention
+                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
+                tmem_ld32(trow + kColH + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm + kPrmStSa + kStBo + c0);                  // deferred bias of Wo_sa
+                tmem_st32(trow + kColH + c0, v);
+                row_stats32(rs, v, mean, rstd);
+                normalize32(v, mean, rstd);                                  // LN affine folded into Wq_ca
+                store_a16<kBf16>(awork, r, c0, v);
+                store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+                tmem_wait_st();
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
+                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm + kPrmCaBq + c0);
+                softmax16(v);
+                softmax16(v + 16);
+                store_a16<kBf16>(awork, r, c0, v);
+                store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                row_stats32(rs, v, mean, rstd);
+                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 106);                                   // S = A_emb . We_ca
+                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
+                tc_fence_before();                                           // S consumed: the next FiLM projection may start
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(s_free_addr);
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
+    
+                // ================= FFN (no pre-norm, reference transformer.py:170-173)
+                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
+                tmem_ld32(trow + kColH + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm + kPrmStCa + kStBo + c0);                  // deferred bias of Wo_ca
+                tmem_st32(trow + kColH + c0, v);
+                store_a16<kBf16>(awork, r, c0, v);
+                store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+                tmem_wait_st();
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
+                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
+                {
+                    float u[16];                                             // hidden 64 = 4 quarters of 16
+                    tmem_ld16(trow + kColW + 16 * cq, u);
+                    tmem_wait_ld();
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
+                    store_a16<kBf16>(awork, r, 16 * cq, u);
+                }
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
+                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
+                tmem_ld32(trow + kColW + c0, v);
+                tmem_wait_ld();
+                add_bias32(v, prm + kPrmFfB2 + c0);
+                row_stats32(rs, v, mean, rstd);
+                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
+                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
+                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
+                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
+            }
+
+            // ---- residual stream after layer `it` (deferred bias of the last FFN block)
+            tmem_ld32(trow + kColH + c0, v);
+            tmem_wait_ld();
+            if (it >= 0) {
+                add_bias32(v, prm + kPrmStFf + kStBo + c0);
+                if (it + 1 < L) tmem_st32(trow + kColH + c0, v);        // h keeps living in TMEM
+            }
+            if (it + 1 == L) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(a.h + blk_index(g, c0, kD));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                break;
+            }
+
+            // ================= self-attention head of layer it+1: LN -> q | k | v, then the time-axis reduction
+            row_stats32(rs, v, mean, rstd);
+            normalize32(v, mean, rstd);                                  // LN affine folded into Wq/Wk/Wv
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+            tmem_wait_st();
+            rows_publish(a_ready_addr, lane);
+            rows_wait(bars, 2, ph[2]);
+            if (threadIdx.x == 0) tl_mark(a, 112);
+            // q: softmax over head-dim -> operand buffer (A operand of the next layer's q . blockdiag(A_sa))
+            tmem_ld32(trow + kColS + c0, v);
+            tmem_wait_ld();
+            add_bias32(v, prm_sa + kPrmSaBq + c0);
+            softmax16(v);
+            softmax16(v + 16);
+            store_a16<kBf16>(awork, r, c0, v);
+            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+            {
+                // Fused time-axis softmax + K^T V (reference :111,:117) on the tensor cores.  With T >= 128 a tile touches
+                // at most two clips.  Two 32 KB operand-image buffers X, Y are all the scratch it needs:
+                //   k (16-bit) -> X ; per-segment column maxima by a column scan of X ; E = exp(k - max) -> X ;
+                //   V -> Y (rows of the other segment zeroed) ; P = E^T V as 8 MN-major MMAs over the tile's tokens ;
+                //   per-segment column sums by a column scan of the E image (same rounded values as the MMA sees).
+                // The partial (max, sum, diagonal 16x16 blocks of P) goes to global memory; the CTA that completes a clip
+                // merges its partials (online-softmax rescaling) into the clip's block-diagonal B-operand image.
+                float* pm = red;                                       // [4 qr][2 seg][128] exchange (max, then sums)
+                float* msm = pm + 1024;                                // [2][128] maxima
+                float* ssm = msm + 256;                                // [2][128] sums
+                int* flags = reinterpret_cast<int*>(ssm + 256);
+                uint8_t* Xp = xbuf;
+                const uint32_t eimg = smem_u32(xbuf), vimg = smem_u32(ringB);
+                const int row0 = blockIdx.x * kTileRows;
+                const int first_clip = row0 / a.T;
+                const int nvalid = max(0, min(kTileRows, a.M - row0));
+                const int e = min(nvalid, (first_clip + 1) * a.T - row0);   // rows [0,e): first clip, [e,nvalid): next clip
+                const int n_seg = nvalid == 0 ? 0 : (nvalid > e ? 2 : 1);
+                const int tx = threadIdx.x;
+                const bool in_tile = (int)r < nvalid;
+                const int myseg = (int)r >= e ? 1 : 0;
+                const int col = tx & 127, qr = tx >> 7;
+                // element (row, col) of a [128 x 128] 16-bit operand image
+                auto img_at = [&](int row) -> const uint16_t* {
+                    return reinterpret_cast<const uint16_t*>(Xp + (col >> 6) * kABlockBytes + sw128_offset(row, (col & 63) >> 3) + (col & 7) * 2);
+                };
+                auto to_f = [](uint16_t u) -> float {
+                    if constexpr (kBf16) return __uint_as_float((uint32_t)u << 16);
+                    else return __half2float(__ushort_as_half(u));
+                };
+                float kx[32];
+                tmem_ld32(trow + kColS + 128 + c0, kx);
+                tmem_wait_ld();
+                tc_fence_before();                                       // q and k consumed: the next layer's FiLM projection may overwrite S
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(s_free_addr);
+                add_bias32(kx, prm_sa + kPrmSaBk + c0);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (!keep) kx[i] += -1000000.f;
+                    if (!in_tile) kx[i] = -INFINITY;
+                    if constexpr (!kBf16) kx[i] = fmaxf(kx[i], -60000.f);      // fp16 image of k: keep the mask finite
+                }
+                store_a16<kBf16>(eimg, r, c0, kx);
+                store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
+                float vx[32];
+                tmem_ld32(trow + kColW + c0, vx);
+                tmem_wait_ld();
+                add_bias32(vx, prm_sa + kPrmSaBv + c0);
+                named_bar_sync(5, kRowThreads);
+                {   // column maxima per segment: this thread scans rows [32 qr, 32 qr + 32) of column `col`
+                    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = 32 * qr + rr;
+                        const float x = to_f(*img_at(row));
+                        if (row < e) m0 = fmaxf(m0, x);
+                        else m1 = fmaxf(m1, x);
+                    }
+                    pm[(qr * 2 + 0) * 128 + col] = m0;
+                    pm[(qr * 2 + 1) * 128 + col] = m1;
+                }
+                named_bar_sync(5, kRowThreads);
+                if (tx < 256) {
+                    const int sg = tx >> 7;
+                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
+                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
+                }
+                named_bar_sync(5, kRowThreads);
+                {   // E = exp(k - max) (0 for padding rows) -> X ; V of the first segment -> Y
+                    const float* mrow = msm + myseg * 128 + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) kx[i] = in_tile ? exp2f((kx[i] - mrow[i]) * 1.4426950408889634f) : 0.f;
+                    store_a16<kBf16>(eimg, r, c0, kx);
+                    store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
+                }
+                if (!keep) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) vx[i] = 0.f;
+                }
+                if (tx == 0) tl_mark(a, 120);
+                for (int ps = 0; ps < max(n_seg, 1); ++ps) {
+                    {   // V image of this pass: rows of the other segment (and padding rows) are zero
+                        float z[32];
+                        const bool mine = in_tile && myseg == ps;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[i] = mine ? vx[i] : 0.f;
+                        store_a16<kBf16>(vimg, r, c0, z);
+                        store_a16<kBf16>(vimg, r, c0 + 16, z + 16);
+                    }
+                    rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
+                    if (tx == 0) tl_mark(a, 122);
+                    if (ps == 0) {
+                        named_bar_sync(5, kRowThreads);                    // E image complete
+                        float s0 = 0.f, s1 = 0.f;                          // column sums per segment from the rounded E
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int row = 32 * qr + rr;
+                            const float x = to_f(*img_at(row));
+                            if (row < e) s0 += x;
+                            else s1 += x;
+                        }
+                        pm[(qr * 2 + 0) * 128 + col] = s0;
+                        pm[(qr * 2 + 1) * 128 + col] = s1;
+                        named_bar_sync(5, kRowThreads);
+                        if (tx < 256) {
+                            const int sg = tx >> 7;
+                            ssm[tx] = (pm[(0 + sg) * 128 + col] + pm[(2 + sg) * 128 + col]) + (pm[(4 + sg) * 128 + col] + pm[(6 + sg) * 128 + col]);
+                        }
+                    }
+                    rows_wait(bars, 2, ph[2]);
+                    if (tx == 0) tl_mark(a, 123);
+                    if (ps < n_seg) {
+                        float* P = a.kv_part + ((size_t)blockIdx.x * 2 + ps) * kKvPartFloats;
+                        if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
+                            float pr[32];
+                            tmem_ld32(trow + kColW + 32 * lq, pr);
+                            tmem_wait_ld();
+                            float4* dst = reinterpret_cast<float4*>(P + 256 + (r >> 4) * 256 + (r & 15) * 16);
+                            const int o = (lane & 16);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
+                                           : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
+                        }
+                        named_bar_sync(5, kRowThreads);                    // ssm written (pass 0) / everyone done reading W
+                        if (tx < 128) P[tx] = msm[ps * 128 + tx], P[128 + tx] = ssm[ps * 128 + tx];
+                    }
+                }
+                if (tx == 0) tl_mark(a, 124);
+                __threadfence();
+                named_bar_sync(5, kRowThreads);
+                if (tx == 0 || tx == 32) {          // one arrival counter per clip; both segments in parallel
+                    const int sg = tx >> 5;
+                    int f = 0;
+                    if (sg < n_seg) {
+                        const int clip = first_clip + sg;
+                        const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
+                        const int old = atomicAdd(a.clip_cnt + clip, 1);
+                        if (old + 1 == ntiles) {
+                            f = 1;
+                            a.clip_cnt[clip] = 0;          // ready for the next launch
+                        }
+                    }
+                    flags[sg] = f;
+                }
+                named_bar_sync(5, kRowThreads);
+                if (tx == 0) tl_mark(a, 125);
+                const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
+                for (int sg = 0; sg < n_seg; ++sg) {
+                    if (!flags[sg]) continue;
+                    __threadfence();
+                    const int clip = first_clip + sg;
+                    const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
+                    // one pass with online rescaling
+                    float M0 = -INFINITY, M1 = -INFINITY, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
+                    for (int ti = t_first; ti <= t_last; ++ti) {
+                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                        const float mi0 = __ldcg(P + 16 * hh + d0), mi1 = __ldcg(P + 16 * hh + d0 + 1);
+                        const float si0 = __ldcg(P + 128 + 16 * hh + d0), si1 = __ldcg(P + 128 + 16 * hh + d0 + 1);
+                        const float* Pa = P + 256 + hh * 256;
+                        const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
+                        const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
+                        const float n0 = fmaxf(M0, mi0), n1 = fmaxf(M1, mi1);
+                        const float c0s = __expf(M0 - n0), c1s = __expf(M1 - n1), w0 = __expf(mi0 - n0), w1 = __expf(mi1 - n1);
+                        M0 = n0, M1 = n1;
+                        s0 = fmaf(s0, c0s, si0 * w0), s1 = fmaf(s1, c1s, si1 * w1);
+                        a00 = fmaf(a00, c0s, r0.x * w0), a01 = fmaf(a01, c0s, r0.y * w0);
+                        a10 = fmaf(a10, c1s, r1.x * w1), a11 = fmaf(a11, c1s, r1.y * w1);
+                    }
+                    uint8_t* img = a.bd_sa_out + (size_t)clip * kAworkBytes;
+                    const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};
+#pragma unroll
+                    for (int dd = 0; dd < 2; ++dd) {
+                        const int ki = 16 * hh + d0 + dd;
+                        uint8_t* base = img + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
+#pragma unroll
+                        for (int ll = 0; ll < 2; ++ll) {
+                            const int nj = 16 * hh + l0 + ll;
+                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
+                        }
+                    }
+                    __threadfence();
+                    named_bar_sync(5, kRowThreads);
+                    if (tx == 0) {                     // release: the clip's attention image of layer it+1 is complete
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.clip_done + clip), "r"(it + 2) : "memory");
+                    }
+                }
+
+            }
+            // ---- parameters of the next layer (all row threads are past their last use of the current ones)
+            named_bar_sync(5, kRowThreads);
+            {
+                const float* pn = a.prm + (size_t)(it + 1) * kPrmFloats;
+                for (int i = threadIdx.x; i < kPrmFloats; i += kRowThreads) prm[i] = pn[i];
+                if (it + 2 < L)
+                    for (int i = threadIdx.x; i < 384; i += kRowThreads) prm_sa[i] = pn[kPrmFloats + i];
+            }
+            named_bar_sync(5, kRowThreads);
+        }
+    }
+    if (threadIdx.x == 0) tl_mark(a, 2);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+constexpr int kStepSmemBytes = kPRingAStages * kStageBytes + kRingBStages * kRingBStageBytes + 2 * kAworkBytes +
+                               (kPrmFloats + 384) * 4 + 512 * 8 + kRedFloats * 4 + sizeof(LayerBarriers) + 1024;
+static_assert(kStepSmemBytes <= 232448, "step kernel exceeds the 227 KB shared-memory limit");
+
+}  // namespace dc
