@@ -423,7 +423,7 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
         for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
         sa.timeline = h->timeline_on ? h->timeline : nullptr;
-        DC_CUDA(h, cudaMemsetAsync(h->clip_done, 0, (size_t)h->B * 4, st));
+        DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));
         DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
         h->launches++;
         mark(1);

@@ -130,15 +130,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
-                    for (int s = 0; s < segs.n_seg; ++s) {           // y = q . blockdiag(A_sa): wait for the clip's merge
-                        const int clip = segs.first_clip + s;
-                        int done;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.clip_done + clip) : "memory");
-                        } while (done < it + 1);
-                        asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes of the merger -> bulk (async proxy) read
-                        load(a.bd_sa_out + (size_t)clip * kAworkBytes, 2, 16384);
-                    }
+                    // ring B doubles as the segment-1 attention image until q . blockdiag(A_sa) of this layer has completed
+                    mbar_wait(smem_u32(&bars->q_full), (uint32_t)it & 1u);
                     load(slab + a.off[kOWoSa], 2, 16384);
                     load(slab + a.off[kOWqCa], 2, 16384);
                     for (int s = 0; s < segs.n_seg; ++s)
@@ -213,7 +206,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             const uint32_t idesc128 = make_idesc<kBf16>(kTileRows, 128);
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
-                    seg_gemm(), done(2), tl_mark(a, 200);                          // y = q . blockdiag(A_sa)   (q published with the K^T V operands)
+                    wait_a();                                                      // merged attention images written by the row threads
+                    for (int sgi = 0; sgi < segs.n_seg; ++sgi) {                   // y = q . blockdiag(A_sa): one lane-masked GEMM per clip segment
+                        uint32_t m[8];
+                        segs.mask(sgi, m, false);
+                        const uint32_t bimg = sgi == 0 ? smem_u32(xbuf) : smem_u32(ringB);
+                        for (int k = 0; k < 2; ++k)
+                            umma_kblock_masked(tmem_base + kColW, awork + k * kABlockBytes, bimg + k * kABlockBytes, idesc128, k > 0, m);
+                    }
+                    done(2), tl_mark(a, 200);
+                    umma_commit(smem_u32(&bars->q_full));                          // ring B (segment-1 image) may be refilled now
                     wait_a(), gemm_b(2, 128, kColH, true, nullptr), done(1), tl_mark(a, 201);   // h += . Wo_sa
                     wait_a(), gemm_b(2, 128, kColW, false, nullptr), done(2), tl_mark(a, 202);  // q_ca
                     wait_a(), seg_gemm(), done(2), tl_mark(a, 203);                // y = softmax(q) . blockdiag(A_ca)
@@ -518,31 +520,40 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     }
                 }
                 if (tx == 0) tl_mark(a, 124);
+                // ---- publish: one arrival per (tile, clip); the counters only grow within a step (zeroed by the host)
                 __threadfence();
                 named_bar_sync(5, kRowThreads);
-                if (tx == 0 || tx == 32) {          // one arrival counter per clip; both segments in parallel
-                    const int sg = tx >> 5;
-                    int f = 0;
-                    if (sg < n_seg) {
-                        const int clip = first_clip + sg;
-                        const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
-                        const int old = atomicAdd(a.clip_cnt + clip, 1);
-                        if (old + 1 == ntiles) {
-                            f = 1;
-                            a.clip_cnt[clip] = 0;          // ready for the next launch
-                        }
+                if ((tx == 0 || tx == 32) && (tx >> 5) < n_seg) atomicAdd(a.clip_cnt + first_clip + (tx >> 5), 1);
+                // ---- meanwhile: clear the two image buffers (E / V are dead: the last K^T V pass has completed) and
+                //      fetch the next layer's parameters
+                {
+                    const uint4 z4 = make_uint4(0, 0, 0, 0);
+                    for (int i = tx; i < kAworkBytes / 16; i += kRowThreads) {
+                        reinterpret_cast<uint4*>(xbuf)[i] = z4;
+                        reinterpret_cast<uint4*>(ringB)[i] = z4;
                     }
-                    flags[sg] = f;
+                    const float* pn = a.prm + (size_t)(it + 1) * kPrmFloats;
+                    for (int i = tx; i < kPrmFloats; i += kRowThreads) prm[i] = pn[i];
+                    if (it + 2 < L)
+                        for (int i = tx; i < 384; i += kRowThreads) prm_sa[i] = pn[kPrmFloats + i];
+                }
+                // ---- wait until every tile of this tile's clip(s) has published, then merge the partials (online-softmax
+                //      rescaling) straight into block-diagonal B-operand images in shared memory: segment 0 -> xbuf,
+                //      segment 1 -> ring B.  Every tile does this for itself: no second global round trip.
+                if ((tx == 0 || tx == 32) && (tx >> 5) < n_seg) {
+                    const int clip = first_clip + (tx >> 5);
+                    const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
+                    int cnt;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cnt) : "l"(a.clip_cnt + clip) : "memory");
+                    } while (cnt < ntiles * (it + 2));
                 }
                 named_bar_sync(5, kRowThreads);
                 if (tx == 0) tl_mark(a, 125);
                 const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
                 for (int sg = 0; sg < n_seg; ++sg) {
-                    if (!flags[sg]) continue;
-                    __threadfence();
                     const int clip = first_clip + sg;
                     const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
-                    // one pass with online rescaling
                     float M0 = -INFINITY, M1 = -INFINITY, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
                     for (int ti = t_first; ti <= t_last; ++ti) {
                         const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
@@ -558,7 +569,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         a00 = fmaf(a00, c0s, r0.x * w0), a01 = fmaf(a01, c0s, r0.y * w0);
                         a10 = fmaf(a10, c1s, r1.x * w1), a11 = fmaf(a11, c1s, r1.y * w1);
                     }
-                    uint8_t* img = a.bd_sa_out + (size_t)clip * kAworkBytes;
+                    uint8_t* img = sg == 0 ? xbuf : ringB;
                     const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};
 #pragma unroll
                     for (int dd = 0; dd < 2; ++dd) {
@@ -570,23 +581,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                             *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
                         }
                     }
-                    __threadfence();
-                    named_bar_sync(5, kRowThreads);
-                    if (tx == 0) {                     // release: the clip's attention image of layer it+1 is complete
-                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.clip_done + clip), "r"(it + 2) : "memory");
-                    }
                 }
-
+                rows_publish(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
+                if (tx == 0) tl_mark(a, 126);
             }
-            // ---- parameters of the next layer (all row threads are past their last use of the current ones)
-            named_bar_sync(5, kRowThreads);
-            {
-                const float* pn = a.prm + (size_t)(it + 1) * kPrmFloats;
-                for (int i = threadIdx.x; i < kPrmFloats; i += kRowThreads) prm[i] = pn[i];
-                if (it + 2 < L)
-                    for (int i = threadIdx.x; i < 384; i += kRowThreads) prm_sa[i] = pn[kPrmFloats + i];
-            }
-            named_bar_sync(5, kRowThreads);
         }
     }
     if (threadIdx.x == 0) tl_mark(a, 2);

@@ -32,6 +32,34 @@ nl = 9
 buf = (C.c_uint64 * (nl * 512))()
 xs = x.clone()
 _lib.check(eng.lib.dc_debug_timeline(eng.handle, C.c_void_p(xs.data_ptr()), S - 1, buf, nl), eng.handle)
+first = int(buf[0])
+if first > 254:          # persistent step kernel: one long event list
+    n = min(first, 2040)
+    ev = sorted((int(buf[1 + 2 * i]), int(buf[2 + 2 * i])) for i in range(n))
+    t0 = ev[0][0]
+    names = {1: "start", 2: "rows_done", 112: "rows: got QKV", 208: "        mma: issued QKV", 209: "        mma: issued KtV pass"}
+    dn = ["qA_sa", "Wo_sa", "Wq_ca", "qA_ca", "Wo_ca", "W1", "W2", "Wo_ff"]
+    lo, hi = (int(v) for v in os.environ.get("TL_RANGE", "0,140").split(","))
+    print(f"--- persistent step kernel: {n} events; showing events [{lo},{hi}) ; total {ev[-1][0] - t0} cycles")
+    for k, (t, i) in enumerate(ev):
+        if not (lo <= k < hi):
+            continue
+        if i in names:
+            nm = names[i]
+        elif 120 <= i < 130:
+            nm = "rows epi: " + ["col max/E/V done", "?", "published V", "got KtV", "partials written", "counters done"][i - 120]
+        elif 100 < i < 150:
+            nm = "rows: got " + ROWW[i - 101]
+        elif 150 < i < 200:
+            nm = "rows: published " + ROWP[i - 151]
+        elif 200 <= i < 208:
+            nm = "        mma: issued " + dn[i - 200]
+        elif 310 <= i < 320:
+            nm = f"        mma: S#{i - 310} last stage issued"
+        else:
+            nm = str(i)
+        print(f"{t - t0:8d}  {nm}")
+    sys.exit(0)
 for launch in (1, 4):
     seg = buf[launch * 512:(launch + 1) * 512]
     n = min(int(seg[0]), 254)
