@@ -12,7 +12,7 @@
 namespace dc {
 
 constexpr int kPRingAStages = 2;        // persistent kernel: 2 x 48 KB (the FiLM projection is shared-memory-bandwidth bound)
-constexpr int kRedFloats = 1024 + 256 + 256 + 8;
+constexpr int kRedFloats = 2048 + 256 + 256 + 8;
 
 struct StepArgs {
     int L, M, T;
@@ -381,14 +381,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             rows_publish(a_ready_addr, lane);
             rows_wait(bars, 2, ph[2]);
             if (threadIdx.x == 0) tl_mark(a, 112);
-            // q: softmax over head-dim -> operand buffer (A operand of the next layer's q . blockdiag(A_sa))
-            tmem_ld32(trow + kColS + c0, v);
-            tmem_wait_ld();
-            add_bias32(v, prm_sa + kPrmSaBq + c0);
-            softmax16(v);
-            softmax16(v + 16);
-            store_a16<kBf16>(awork, r, c0, v);
-            store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             {
                 // Fused time-axis softmax + K^T V (reference :111,:117) on the tensor cores.  With T >= 128 a tile touches
                 // at most two clips.  Two 32 KB operand-image buffers X, Y are all the scratch it needs:
@@ -397,8 +389,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 //   per-segment column sums by a column scan of the E image (same rounded values as the MMA sees).
                 // The partial (max, sum, diagonal 16x16 blocks of P) goes to global memory; the CTA that completes a clip
                 // merges its partials (online-softmax rescaling) into the clip's block-diagonal B-operand image.
-                float* pm = red;                                       // [4 qr][2 seg][128] exchange (max, then sums)
-                float* msm = pm + 1024;                                // [2][128] maxima
+                float* pm = red;                                       // [8 rg][2 seg][128] exchange (max, then sums)
+                float* msm = pm + 2048;                                // [2][128] maxima
                 float* ssm = msm + 256;                                // [2][128] sums
                 int* flags = reinterpret_cast<int*>(ssm + 256);
                 uint8_t* Xp = xbuf;
@@ -412,20 +404,27 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 const bool in_tile = (int)r < nvalid;
                 const int myseg = (int)r >= e ? 1 : 0;
                 const int col = tx & 127, qr = tx >> 7;
-                // element (row, col) of a [128 x 128] 16-bit operand image
-                auto img_at = [&](int row) -> const uint16_t* {
-                    return reinterpret_cast<const uint16_t*>(Xp + (col >> 6) * kABlockBytes + sw128_offset(row, (col & 63) >> 3) + (col & 7) * 2);
+                // column pair (2 cp, 2 cp + 1), rows [16 rg, 16 rg + 16) of a [128 x 128] 16-bit operand image
+                const int cp = tx & 63, rg = tx >> 6;
+                const uint8_t* pair_base = Xp + (cp >> 5) * kABlockBytes + (cp & 3) * 4;
+                const uint32_t pair_chunk = (uint32_t)(cp & 31) >> 2;
+                auto pair_at = [&](int row) -> const uint32_t* {
+                    return reinterpret_cast<const uint32_t*>(pair_base + row * 128 + ((pair_chunk ^ ((uint32_t)row & 7u)) << 4));
                 };
-                auto to_f = [](uint16_t u) -> float {
-                    if constexpr (kBf16) return __uint_as_float((uint32_t)u << 16);
-                    else return __half2float(__ushort_as_half(u));
+                constexpr uint32_t kNegInf2 = kBf16 ? 0xFF80FF80u : 0xFC00FC00u;
+                auto max2 = [](uint32_t x, uint32_t y) -> uint32_t {
+                    if constexpr (kBf16) {
+                        __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&x), *reinterpret_cast<__nv_bfloat162*>(&y));
+                        return *reinterpret_cast<uint32_t*>(&r2);
+                    } else {
+                        __half2 r2 = __hmax2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&y));
+                        return *reinterpret_cast<uint32_t*>(&r2);
+                    }
                 };
                 float kx[32];
                 tmem_ld32(trow + kColS + 128 + c0, kx);
                 tmem_wait_ld();
-                tc_fence_before();                                       // q and k consumed: the next layer's FiLM projection may overwrite S
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(s_free_addr);
+
                 add_bias32(kx, prm_sa + kPrmSaBk + c0);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -440,23 +439,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 tmem_wait_ld();
                 add_bias32(vx, prm_sa + kPrmSaBv + c0);
                 named_bar_sync(5, kRowThreads);
-                {   // column maxima per segment: this thread scans rows [32 qr, 32 qr + 32) of column `col`
-                    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = 32 * qr + rr;
-                        const float x = to_f(*img_at(row));
-                        if (row < e) m0 = fmaxf(m0, x);
-                        else m1 = fmaxf(m1, x);
+                {   // column maxima per segment: this thread scans 16 rows of a column PAIR (packed 16-bit max)
+                    uint32_t m0 = kNegInf2, m1 = kNegInf2;
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int row = 16 * rg + rr;
+                        const uint32_t x = *pair_at(row);
+                        if (row < e) m0 = max2(m0, x);
+                        else m1 = max2(m1, x);
                     }
-                    pm[(qr * 2 + 0) * 128 + col] = m0;
-                    pm[(qr * 2 + 1) * 128 + col] = m1;
+                    const float2 f0 = unpack2<kBf16>(m0), f1 = unpack2<kBf16>(m1);
+                    *reinterpret_cast<float2*>(pm + (rg * 2 + 0) * 128 + 2 * cp) = f0;
+                    *reinterpret_cast<float2*>(pm + (rg * 2 + 1) * 128 + 2 * cp) = f1;
                 }
                 named_bar_sync(5, kRowThreads);
                 if (tx < 256) {
                     const int sg = tx >> 7;
-                    msm[tx] = fmaxf(fmaxf(pm[(0 + sg) * 128 + col], pm[(2 + sg) * 128 + col]),
-                                    fmaxf(pm[(4 + sg) * 128 + col], pm[(6 + sg) * 128 + col]));
+                    float mm = pm[sg * 128 + col];
+#pragma unroll
+                    for (int q8 = 1; q8 < 8; ++q8) mm = fmaxf(mm, pm[(q8 * 2 + sg) * 128 + col]);
+                    msm[tx] = mm;
                 }
                 named_bar_sync(5, kRowThreads);
                 {   // E = exp(k - max) (0 for padding rows) -> X ; V of the first segment -> Y
@@ -483,21 +485,37 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
                     if (tx == 0) tl_mark(a, 122);
                     if (ps == 0) {
-                        named_bar_sync(5, kRowThreads);                    // E image complete
-                        float s0 = 0.f, s1 = 0.f;                          // column sums per segment from the rounded E
-#pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int row = 32 * qr + rr;
-                            const float x = to_f(*img_at(row));
-                            if (row < e) s0 += x;
-                            else s1 += x;
+                        // q: softmax over head-dim -> operand buffer (A operand of the next layer's q . blockdiag(A_sa));
+                        // runs while the tensor core does E^T V.  Once q and k have left S the next FiLM projection may start.
+                        float qv[32];
+                        tmem_ld32(trow + kColS + c0, qv);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(s_free_addr);
+                        add_bias32(qv, prm_sa + kPrmSaBq + c0);
+                        softmax16(qv);
+                        softmax16(qv + 16);
+                        store_a16<kBf16>(awork, r, c0, qv);
+                        store_a16<kBf16>(awork, r, c0 + 16, qv + 16);
+                        named_bar_sync(5, kRowThreads);                    // E image complete (all rows published)
+                        float2 s0 = make_float2(0.f, 0.f), s1 = s0;          // column sums per segment from the rounded E
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const int row = 16 * rg + rr;
+                            const float2 x = unpack2<kBf16>(*pair_at(row));
+                            if (row < e) s0.x += x.x, s0.y += x.y;
+                            else s1.x += x.x, s1.y += x.y;
                         }
-                        pm[(qr * 2 + 0) * 128 + col] = s0;
-                        pm[(qr * 2 + 1) * 128 + col] = s1;
+                        *reinterpret_cast<float2*>(pm + (rg * 2 + 0) * 128 + 2 * cp) = s0;
+                        *reinterpret_cast<float2*>(pm + (rg * 2 + 1) * 128 + 2 * cp) = s1;
                         named_bar_sync(5, kRowThreads);
                         if (tx < 256) {
                             const int sg = tx >> 7;
-                            ssm[tx] = (pm[(0 + sg) * 128 + col] + pm[(2 + sg) * 128 + col]) + (pm[(4 + sg) * 128 + col] + pm[(6 + sg) * 128 + col]);
+                            float ss = pm[sg * 128 + col];
+#pragma unroll
+                            for (int q8 = 1; q8 < 8; ++q8) ss += pm[(q8 * 2 + sg) * 128 + col];
+                            ssm[tx] = ss;
                         }
                     }
                     rows_wait(bars, 2, ph[2]);
