@@ -267,7 +267,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "dc::layer_kernel", "achieved": round(achieved, 2), "peak": pk["bf16_tflops"],
+    kname = "dc::step_kernel (persistent: all 8 layers of a denoise step)" if cnt["layer"] == 1 else "dc::layer_kernel"
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": round(achieved, 2), "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": traffic,
                 "peak_source": pk["source"], "launch_ms": round(layer_ms, 4), "launches_per_denoise_step": cnt["layer"],
                 "share_of_denoise_step": round(agg["layer"] / step_ms, 3),
