@@ -182,7 +182,8 @@ def main():
     _, noise = synth_inputs(B, T, seed=100 + rank)
     xf_proj_d, xf_out_d, noise_d = xf_proj.to(dev), xf_out.to(dev), noise.to(dev)
     kw = dict(xf_proj=xf_proj_d, xf_out=xf_out_d, length=[T] * B)
-    eng = model.engine(dev)
+    eng = model.engine(dev)                      # base handle: C-ABI host-buffer call and the per-kernel profile
+    plan = model.engine_for(dev, B, T)           # what ddim_sample_loop uses (chunks of clips when the batch exceeds the SMs)
     gathered = [torch.empty(B, T, 26, device=dev) for _ in range(world)] if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -203,7 +204,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches0 = eng.kernel_launches()
+    launches0 = plan.kernel_launches()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for e0, e1 in evs:
         flush.fill_(1)
@@ -211,7 +212,7 @@ def main():
         one_loop()
         e1.record()
     barrier()
-    launches = eng.kernel_launches() - launches0
+    launches = plan.kernel_launches() - launches0
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -249,8 +250,10 @@ def main():
 
     # ---- roofline of the dominant kernel (the tcgen05 layer kernel), timed live with CUDA events
     pk = peaks()
-    x = noise_d.clone()
-    eng.prepare(xf_proj_d, xf_out_d, [T] * B, B, T)
+    chunked = hasattr(plan, "bounds")
+    Bp = (plan.bounds[0][1] - plan.bounds[0][0]) if chunked else B      # the profile runs on one chunk of clips
+    x = noise_d[:Bp].clone()
+    eng.prepare(xf_proj_d[:Bp], xf_out_d[:Bp], [T] * Bp, Bp, T)
     agg, cnt = {}, {}
     reps = 5
     for i in range(reps + 2):
@@ -260,7 +263,7 @@ def main():
                 agg[k] = agg.get(k, 0.0) + ms[k] / reps
                 cnt[k] = c[k]
     layer_ms = agg["layer"] / max(cnt["layer"], 1)
-    flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * B * T / max(cnt["layer"], 1)
+    flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * Bp * T / max(cnt["layer"], 1)
     achieved = flop_per_launch / (layer_ms * 1e-3) / 1e12
     step_ms = sum(agg.values())
     traffic = None        # dram__bytes_read + write per launch of the layer kernel, from the committed ncu --set full capture
@@ -272,7 +275,8 @@ def main():
                 "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": traffic,
                 "peak_source": pk["source"], "launch_ms": round(layer_ms, 4), "launches_per_denoise_step": cnt["layer"],
                 "share_of_denoise_step": round(agg["layer"] / step_ms, 3),
-                "denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()},
+                "denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()}, "profiled_clips": Bp,
+                "clip_chunks": len(plan.bounds) if chunked else 1,
                 "whole_loop_frac_of_peak": round(B * T * S * FLOP_PER_TOKEN_STEP / (ms_per_step / 1e3) / 1e12 / pk["bf16_tflops"], 4)}
 
     if rank == 0:

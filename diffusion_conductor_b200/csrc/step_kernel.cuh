@@ -573,19 +573,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     const int clip = first_clip + sg;
                     const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
                     float M0 = -INFINITY, M1 = -INFINITY, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
-                    for (int ti = t_first; ti <= t_last; ++ti) {
-                        const float* P = a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
-                        const float mi0 = __ldcg(P + 16 * hh + d0), mi1 = __ldcg(P + 16 * hh + d0 + 1);
-                        const float si0 = __ldcg(P + 128 + 16 * hh + d0), si1 = __ldcg(P + 128 + 16 * hh + d0 + 1);
-                        const float* Pa = P + 256 + hh * 256;
-                        const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
-                        const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
-                        const float n0 = fmaxf(M0, mi0), n1 = fmaxf(M1, mi1);
-                        const float c0s = __expf(M0 - n0), c1s = __expf(M1 - n1), w0 = __expf(mi0 - n0), w1 = __expf(mi1 - n1);
-                        M0 = n0, M1 = n1;
-                        s0 = fmaf(s0, c0s, si0 * w0), s1 = fmaf(s1, c1s, si1 * w1);
-                        a00 = fmaf(a00, c0s, r0.x * w0), a01 = fmaf(a01, c0s, r0.y * w0);
-                        a10 = fmaf(a10, c1s, r1.x * w1), a11 = fmaf(a11, c1s, r1.y * w1);
+                    auto part_of = [&](int ti) { return a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats; };
+                    if (t_last - t_first < 4) {
+                        // short clips (<= 4 tiles): issue every load first, one L2 round trip for the whole merge
+                        float mi0[4], mi1[4], si0[4], si1[4];
+                        float2 r0[4], r1[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool on = t_first + j <= t_last;
+                            const float* P = part_of(on ? t_first + j : t_first);
+                            const float* Pa = P + 256 + hh * 256;
+                            mi0[j] = on ? __ldcg(P + 16 * hh + d0) : -INFINITY;
+                            mi1[j] = on ? __ldcg(P + 16 * hh + d0 + 1) : -INFINITY;
+                            si0[j] = __ldcg(P + 128 + 16 * hh + d0), si1[j] = __ldcg(P + 128 + 16 * hh + d0 + 1);
+                            r0[j] = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
+                            r1[j] = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) M0 = fmaxf(M0, mi0[j]), M1 = fmaxf(M1, mi1[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float w0 = __expf(mi0[j] - M0), w1 = __expf(mi1[j] - M1);      // exp(-inf) = 0 for absent tiles
+                            s0 = fmaf(si0[j], w0, s0), s1 = fmaf(si1[j], w1, s1);
+                            a00 = fmaf(r0[j].x, w0, a00), a01 = fmaf(r0[j].y, w0, a01);
+                            a10 = fmaf(r1[j].x, w1, a10), a11 = fmaf(r1[j].y, w1, a11);
+                        }
+                    } else {
+                        for (int ti = t_first; ti <= t_last; ++ti) {                              // online rescaling
+                            const float* P = part_of(ti);
+                            const float mi0 = __ldcg(P + 16 * hh + d0), mi1 = __ldcg(P + 16 * hh + d0 + 1);
+                            const float si0 = __ldcg(P + 128 + 16 * hh + d0), si1 = __ldcg(P + 128 + 16 * hh + d0 + 1);
+                            const float* Pa = P + 256 + hh * 256;
+                            const float2 r0 = __ldcg(reinterpret_cast<const float2*>(Pa + d0 * 16 + l0));
+                            const float2 r1 = __ldcg(reinterpret_cast<const float2*>(Pa + (d0 + 1) * 16 + l0));
+                            const float n0 = fmaxf(M0, mi0), n1 = fmaxf(M1, mi1);
+                            const float c0s = __expf(M0 - n0), c1s = __expf(M1 - n1), w0 = __expf(mi0 - n0), w1 = __expf(mi1 - n1);
+                            M0 = n0, M1 = n1;
+                            s0 = fmaf(s0, c0s, si0 * w0), s1 = fmaf(s1, c1s, si1 * w1);
+                            a00 = fmaf(a00, c0s, r0.x * w0), a01 = fmaf(a01, c0s, r0.y * w0);
+                            a10 = fmaf(a10, c1s, r1.x * w1), a11 = fmaf(a11, c1s, r1.y * w1);
+                        }
                     }
                     uint8_t* img = sg == 0 ? xbuf : ringB;
                     const float o[2][2] = {{a00 / s0, a01 / s0}, {a10 / s1, a11 / s1}};

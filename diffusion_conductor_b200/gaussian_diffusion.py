@@ -161,7 +161,7 @@ class GaussianDiffusion:
             if text is None:
                 raise TypeError("model_kwargs needs xf_proj/xf_out (encode_music outputs) or text (mel)")
             xf_proj, xf_out = model.encode_music(text, x.device)
-        eng = model.engine(x.device)
+        eng = model.engine_for(x.device, B, T)
         eng.prepare(xf_proj, xf_out, length, B, T)
         eng.set_schedule((id(self), float(eta)), self.step_coefficients(eta))
         return eng

@@ -189,6 +189,7 @@ class MotionTransformer(nn.Module):
         self.proj = nn.Linear(64, 64)
 
         self._engine: Optional[_Engine] = None
+        self._chunk_engines = []            # extra handles for clip chunks of large batches (see engine_for)
         self._weights_dirty = True
 
     # ---- weight bookkeeping -------------------------------------------------------------------
@@ -215,8 +216,34 @@ class MotionTransformer(nn.Module):
             self._weights_dirty = True
         if self._weights_dirty:
             self._engine.upload(self)
+            for e in self._chunk_engines:
+                e.upload(self)
             self._weights_dirty = False
         return self._engine
+
+    def engine_for(self, device: torch.device, B: int, T: int):
+        """Engine for a (B, T) batch.  The whole-step persistent kernel needs every 128-token tile of the batch on
+        its own SM; clips are independent, so a larger batch is cut into equal chunks of clips that fit, each
+        chunk with its own handle (workspace + captured graph) run back to back.  Short clips (T < 128) and single
+        clips longer than the GPU use one handle and the per-layer launch path."""
+        base = self.engine(device)
+        sms = torch.cuda.get_device_properties(base.device).multi_processor_count
+        tiles = -(-B * T // 128)
+        per_chunk = (sms * 128) // T if T >= 128 else 0
+        if tiles <= sms or per_chunk < 1 or B <= per_chunk:
+            return base
+        n_chunks = -(-B // per_chunk)
+        while len(self._chunk_engines) < n_chunks - 1:
+            e = _Engine(self, base.device_index)
+            e.upload(self)
+            self._chunk_engines.append(e)
+        size, extra = divmod(B, n_chunks)
+        bounds, a = [], 0
+        for i in range(n_chunks):
+            b = a + size + (1 if i < extra else 0)
+            bounds.append((a, b))
+            a = b
+        return _ChunkedEngine([base] + self._chunk_engines[: n_chunks - 1], bounds)
 
     # ---- reference API ------------------------------------------------------------------------
     def encode_music(self, text, device):
@@ -247,7 +274,7 @@ class MotionTransformer(nn.Module):
             x = torch.flatten(x, start_dim=2, end_dim=3)
         if length is None:
             raise TypeError("length is required (the reference calls len(length), transformer.py:462)")
-        eng = self.engine(x.device)
+        eng = self.engine_for(x.device, B, T)
         with torch.no_grad():
             eng.prepare(xf_proj, xf_out, length, B, T)
             return eng.forward(x, timesteps)
@@ -375,3 +402,61 @@ class _Engine:
 
     def set_graphs(self, enabled: bool):
         self._ck(self.lib.dc_set_graphs(self.handle, 1 if enabled else 0))
+
+
+class _ChunkedEngine:
+    """Same interface as _Engine over a batch cut into contiguous chunks of clips, one handle per chunk."""
+
+    def __init__(self, engines, bounds):
+        self.engines, self.bounds = engines, bounds
+        self.device = engines[0].device
+        self.device_index = engines[0].device_index
+        self.B = self.T = 0
+
+    def _each(self):
+        return zip(self.engines, self.bounds)
+
+    def set_schedule(self, key, coef):
+        for e in self.engines:
+            e.set_schedule(key, coef)
+
+    def prepare(self, xf_proj, xf_out, length, B, T):
+        xf_proj = _Engine._f32(xf_proj, self.device)
+        xf_out = _Engine._f32(xf_out, self.device)
+        length = [int(v) for v in length]
+        if len(length) != B:
+            raise ValueError("len(length) must equal the batch size")
+        for e, (a, b) in self._each():
+            e.prepare(xf_proj[a:b], xf_out[a:b], length[a:b], b - a, T)
+        self._keepalive = (xf_proj, xf_out)
+        self.B, self.T = B, T
+
+    def forward(self, x, timesteps):
+        x = _Engine._f32(x, self.device)
+        out = torch.empty_like(x)
+        for e, (a, b) in self._each():
+            out[a:b] = e.forward(x[a:b], timesteps[a:b])
+        return out
+
+    def sample_step(self, sampler, x, step, noise):
+        x0 = torch.empty_like(x)
+        for e, (a, b) in self._each():
+            x0[a:b] = e.sample_step(sampler, x[a:b], step, None if noise is None else noise[a:b])
+        return x0
+
+    def sample_loop(self, sampler, x, step_noise=None, trace_x0=None, trace_x=None):
+        for e, (a, b) in self._each():
+            sn = None if step_noise is None else step_noise[:, a:b].contiguous()
+            t0 = None if trace_x0 is None else torch.empty_like(trace_x0[:, a:b].contiguous())
+            t1 = None if trace_x is None else torch.empty_like(trace_x[:, a:b].contiguous())
+            e.sample_loop(sampler, x[a:b], step_noise=sn, trace_x0=t0, trace_x=t1)
+            if t0 is not None:
+                trace_x0[:, a:b] = t0
+            if t1 is not None:
+                trace_x[:, a:b] = t1
+
+    def sampler_update(self, sampler, x, x0, step, noise=None):
+        self.engines[0].sampler_update(sampler, x, x0, step, noise)
+
+    def kernel_launches(self) -> int:
+        return sum(e.kernel_launches() for e in self.engines)

@@ -30,6 +30,8 @@ print("stall samples:", ", ".join(f"{k.split('stalled_')[1]}={float(v) / tot:.1%
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
 h2 = rows[1]
+if "# Samples" not in h2:
+    sys.exit(0)
 ia, ie, isamp = h2.index("Source"), h2.index("Instructions Executed"), h2.index("# Samples")
 ops, samp = collections.Counter(), collections.Counter()
 seen = set()
