@@ -230,7 +230,9 @@ class MotionTransformer(nn.Module):
         sms = torch.cuda.get_device_properties(base.device).multi_processor_count
         tiles = -(-B * T // 128)
         per_chunk = (sms * 128) // T if T >= 128 else 0
-        if tiles <= sms or per_chunk < 1 or B <= per_chunk:
+        # measured (r01, B200): with more than ~2 SM-fulls of tiles the per-layer launch path (3+ full waves) is as
+        # fast as running the persistent kernel chunk after chunk (C3: 75.7 ms vs 79.0 ms), so chunk only up to 2x
+        if tiles <= sms or tiles > 2 * sms or per_chunk < 1 or B <= per_chunk:
             return base
         n_chunks = -(-B // per_chunk)
         while len(self._chunk_engines) < n_chunks - 1:
