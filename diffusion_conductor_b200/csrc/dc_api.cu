@@ -393,8 +393,9 @@ LayerArgs layer_args(dc_handle* h, int l) {
 
 // One denoise step: A_emb + h0, L+1 tile launches with the time-axis reductions in between, output
 // head (+ sampler update).  te/te_stride select the per-sample or per-step time embedding.
+// `step` >= 0: the timestep is known on the host (persistent kernel: baked into the launch); -1: read from the device counter.
 int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride, bool te_from_ctr, int mode, float* x_upd,
-                 float* x0_out, const float* noise, size_t noise_stride, size_t trace_stride, float* trace_x, cudaStream_t st) {
+                 float* x0_out, const float* noise, int step, cudaStream_t st) {
     const int L = h->cfg.num_layers;
     const int M = h->M;
     const int blocks8 = (M + 7) / 8;
@@ -407,19 +408,20 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         h->prof_cls.push_back(cls);
     };
     mark(-1);
-    const int* ctr = te_from_ctr ? h->step_ctr : nullptr;
-    DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_begin_kernel<true> : step_begin_kernel<false>, dim3(blocks8), dim3(128), 0, st, x_in,
-                        (const float*)h->xp, te, ctr, te_stride, (const float*)h->WjT, (const float*)h->bj, (const float*)h->pos, M, h->T,
-                        h->aemb, h->hbuf));
-    h->launches++;
-    mark(0);
-    if (h->persist) {
+    if (h->persist && (step >= 0 || !te_from_ctr)) {
+        // whole denoise step in ONE launch: A_emb + h0 prologue, all layers, output head + sampler update
         StepArgs sa{};
         sa.L = L, sa.M = M, sa.T = h->T;
-        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.prm = h->prm, sa.h = h->hbuf;
+        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm, sa.h = h->hbuf;
         sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
         sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
         sa.length = h->has_length ? h->length : nullptr;
+        sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.noise = noise, sa.xp = h->xp;
+        sa.te = te_from_ctr ? te + (size_t)step * kE : te;
+        sa.te_stride = te_stride;
+        sa.coef = (mode & 0xF) ? h->coef + (size_t)step * 8 : nullptr;
+        sa.mode = mode;
+        sa.WjT = h->WjT, sa.bj = h->bj, sa.pos = h->pos, sa.WoT = h->WoT, sa.bo = h->bo;
         const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
         for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
         sa.timeline = h->timeline_on ? h->timeline : nullptr;
@@ -427,7 +429,15 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
         h->launches++;
         mark(1);
-    } else
+        DC_CUDA(h, cudaGetLastError());
+        return 0;
+    }
+    const int* ctr = te_from_ctr ? h->step_ctr : nullptr;
+    DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_begin_kernel<true> : step_begin_kernel<false>, dim3(blocks8), dim3(128), 0, st, x_in,
+                        (const float*)h->xp, te, ctr, te_stride, (const float*)h->WjT, (const float*)h->bj, (const float*)h->pos, M, h->T,
+                        h->aemb, h->hbuf));
+    h->launches++;
+    mark(0);
     for (int l = -1; l < L; ++l) {
         const LayerArgs la = layer_args(h, l);
         const int rc = h->bf16 ? launch_layer<true>(h, la, h->tiles, st) : launch_layer<false>(h, la, h->tiles, st);
@@ -445,7 +455,6 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
                         (const float*)h->bo, M, mode, (const float*)h->coef, (const int*)h->step_ctr, noise, x_upd, x0_out));
     h->launches++;
     mark(3);
-    (void)noise_stride, (void)trace_stride, (void)trace_x;
     DC_CUDA(h, cudaGetLastError());
     return 0;
 }
@@ -765,7 +774,7 @@ int dc_forward(dc_handle* h, const float* x, const int64_t* timesteps, float* ou
     cudaStream_t st = (cudaStream_t)stream;
     time_embed_kernel<<<h->B, kE, 0, st>>>((const long long*)timesteps, 0, h->freqs, h->teW0, h->teb0, h->teW2, h->teb2, h->te_b);
     h->launches++;
-    return enqueue_step(h, x, h->te_b, kE, false, DC_SAMPLER_NONE, nullptr, out, nullptr, 0, 0, nullptr, st);
+    return enqueue_step(h, x, h->te_b, kE, false, DC_SAMPLER_NONE, nullptr, out, nullptr, -1, st);
 }
 
 static int check_sampling(dc_handle* h, int sampler, const char* who) {
@@ -784,7 +793,7 @@ int dc_sample_step(dc_handle* h, int sampler, float* x, float* pred_x0, int step
     cudaStream_t st = (cudaStream_t)stream;
     set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, step, 0);
     h->launches++;
-    return enqueue_step(h, x, h->te_table, 0, true, sampler, x, pred_x0, noise, 0, 0, nullptr, st);
+    return enqueue_step(h, x, h->te_table, 0, true, sampler, x, pred_x0, noise, step, st);
 }
 
 int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0, int step, const float* noise, int64_t n, void* stream) {
@@ -815,11 +824,13 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
     DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
     set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
     h->launches++;
-    const int64_t per_step = h->persist ? 4 : (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
+    const int64_t per_step = h->persist ? 1 : (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
     if (h->use_graphs && !traced) {
         GraphKey key;
         key.sampler = sampler;
-        key.steps = (S % 5 == 0) ? 5 : 1;
+        // persistent kernel: the timestep is a launch argument, so the graph holds all S steps (one kernel each);
+        // per-layer path: the step index lives in device memory and a 5-step graph is replayed S/5 times
+        key.steps = h->persist ? S : ((S % 5 == 0) ? 5 : 1);
         if (!h->gexec || !(h->gkey == key)) {
             drop_graph(h);
             cudaGraph_t graph = nullptr;
@@ -827,8 +838,8 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
             const int64_t before = h->launches;
             int rc = 0;
             for (int i = 0; i < key.steps && !rc; ++i) {
-                rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, 0, 0, nullptr, h->cap_stream);
-                launch_k(h->use_pdl, set_step_kernel, dim3(1), dim3(1), 0, h->cap_stream, h->step_ctr, 0, -1);
+                rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, h->persist ? S - 1 - i : -1, h->cap_stream);
+                if (!h->persist) launch_k(h->use_pdl, set_step_kernel, dim3(1), dim3(1), 0, h->cap_stream, h->step_ctr, 0, -1);
             }
             h->launches = before;
             cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
@@ -848,7 +859,7 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
         for (int i = 0; i < S; ++i) {
             const float* nz = step_noise ? step_noise + (size_t)i * n : nullptr;
             float* x0dst = trace_x0 ? trace_x0 + (size_t)i * n : h->x0work;
-            if (int rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, x0dst, nz, 0, 0, nullptr, st)) return rc;
+            if (int rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, x0dst, nz, S - 1 - i, st)) return rc;
             if (trace_x) DC_CUDA(h, cudaMemcpyAsync(trace_x + (size_t)i * n, h->xwork, n * 4, cudaMemcpyDeviceToDevice, st));
             set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, 0, -1);
             h->launches++;
@@ -891,7 +902,7 @@ int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out
     h->prof = true;
     h->prof_ev.clear();
     h->prof_cls.clear();
-    const int rc = enqueue_step(h, x, h->te_table, 0, true, sampler, x, h->x0work, nullptr, 0, 0, nullptr, st);
+    const int rc = enqueue_step(h, x, h->te_table, 0, true, sampler, x, h->x0work, nullptr, step, st);
     h->prof = false;
     cudaError_t e = cudaStreamSynchronize(st);
     for (int i = 0; i < 4; ++i) ms_out[i] = 0.f, count_out[i] = 0;
@@ -918,7 +929,7 @@ int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out,
     DC_CUDA(h, cudaMemset(h->timeline, 0, (size_t)(h->cfg.num_layers + 1) * 512 * 8));
     set_step_kernel<<<1, 1>>>(h->step_ctr, step, 0);
     h->timeline_on = true;
-    const int rc = enqueue_step(h, x, h->te_table, 0, true, DC_SAMPLER_DDIM, x, h->x0work, nullptr, 0, 0, nullptr, 0);
+    const int rc = enqueue_step(h, x, h->te_table, 0, true, DC_SAMPLER_DDIM, x, h->x0work, nullptr, step, 0);
     h->timeline_on = false;
     if (rc) return rc;
     DC_CUDA(h, cudaDeviceSynchronize());

@@ -19,7 +19,22 @@ struct StepArgs {
     const uint8_t* wbuf;        // packed weights [L][1 MiB]
     const uint8_t* aemb;        // A_emb image [tiles][8][16 KB]
     const float* prm;           // [L][kPrmFloats]
-    float* h;                   // blocked [Mpad][128] residual stream (in: h0 from step_begin, out: after the last layer)
+    // step prologue / epilogue fused into the kernel (reference transformer.py:482,488-490,496; gaussian_diffusion.py:812-830)
+    const float* x_in;          // [M][26] current sample x_t
+    float* x_out;               // [M][26] updated sample (may alias x_in; null when mode == 0)
+    float* x0_out;              // [M][26] pred_xstart (model output)
+    const float* noise;         // [M][26] or null
+    const float* xp;            // [M][512] linear(xf_proj)
+    const float* te;            // time embedding row(s): te + b * te_stride
+    int te_stride;
+    const float* coef;          // the 8 update coefficients of this step (already offset), or null
+    int mode;                   // 0: model output only, 1: DDIM, 2: DDPM, | 0x10 clamp
+    const float* WjT;           // [26][128] joint_embed weight, transposed
+    const float* bj;            // [128]
+    const float* pos;           // [num_frames][128] sequence_embedding
+    const float* WoT;           // [128][32] output head, transposed + padded
+    const float* bo;            // [32]
+    uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
     const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
     size_t bd_ca_stride;
     uint8_t* bd_sa_out;         // [B][32 KB] self-attention images (written by the merging CTA, read by the clip's tiles)
@@ -68,6 +83,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         mbar_init(smem_u32(&bars->a_ready), kRowWarps);
         mbar_init(smem_u32(&bars->s_free), kRowWarps);
         mbar_init(smem_u32(&bars->q_full), 1);
+        mbar_init(smem_u32(&bars->aemb_ready), kRowWarps);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
         mbar_fence_init();
     }
@@ -90,6 +106,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         if (lane == 0) {
             const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
             uint32_t it_ = 0;
+            mbar_wait(smem_u32(&bars->aemb_ready), 0);          // the row threads have written this tile's A_emb image
+            asm volatile("fence.proxy.async;" ::: "memory");
             auto stage_in = [&](const uint8_t* a_src, const uint8_t* w_src, uint32_t w_bytes) {
                 const uint32_t st = it_ % kNA, ph = (it_ / kNA) & 1u;
                 ++it_;
@@ -267,13 +285,54 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         float mean, rstd;
         float v[32];
 
-        // ---- residual stream -> TMEM (stays there for the whole step)
+        // ---- step prologue (was step_begin_kernel): this tile's A_emb = SiLU(te + xp) image -> global (streamed back
+        //      24 times by ring A), h0 = joint_embed(x) + sequence_embedding -> TMEM (stays there for the whole step)
         {
-            const float4* src = reinterpret_cast<const float4*>(a.h + blk_index(g, c0, kD));
+            uint8_t* img = a.aemb_out + (size_t)blockIdx.x * 8 * kStageABytes;
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {                       // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
+                const int task = k * kRowThreads + (int)threadIdx.x;
+                const int row = task >> 6, ch = task & 63;
+                const long gg = (long)blockIdx.x * kTileRows + row;
+                uint4 pk = make_uint4(0, 0, 0, 0);
+                if (gg < a.M) {
+                    const int bb = (int)(gg / a.T);
+                    const float4* xr = reinterpret_cast<const float4*>(a.xp + gg * kE + ch * 8);
+                    const float4* tr = reinterpret_cast<const float4*>(a.te + (size_t)bb * a.te_stride + ch * 8);
+                    const float4 a0 = __ldg(xr), a1 = __ldg(xr + 1), t0 = __ldg(tr), t1 = __ldg(tr + 1);
+                    const float e8[8] = {a0.x + t0.x, a0.y + t0.y, a0.z + t0.z, a0.w + t0.w, a1.x + t1.x, a1.y + t1.y, a1.z + t1.z, a1.w + t1.w};
+                    uint32_t p[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        p[i] = pack2<kBf16>(__fdividef(e8[2 * i], 1.f + __expf(-e8[2 * i])), __fdividef(e8[2 * i + 1], 1.f + __expf(-e8[2 * i + 1])));
+                    pk = make_uint4(p[0], p[1], p[2], p[3]);
+                }
+                *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
+            }
+            __threadfence();                                       // the image must have reached L2 ...
+            asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
+            // h0 for this thread's 32 features
+            float xr[kP];
+#pragma unroll
+            for (int i = 0; i < kP; ++i) xr[i] = valid ? a.x_in[(size_t)g * kP + i] : 0.f;     // plain loads: x may be updated in place below
+            const float4* bj4 = reinterpret_cast<const float4*>(a.bj + c0);
+            const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 f = valid ? src[i * 128] : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
+                const float4 bv = __ldg(bj4 + i), pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * i] = bv.x + pv.x, v[4 * i + 1] = bv.y + pv.y, v[4 * i + 2] = bv.z + pv.z, v[4 * i + 3] = bv.w + pv.w;
+            }
+#pragma unroll
+            for (int c = 0; c < kP; ++c) {
+                const float4* w4 = reinterpret_cast<const float4*>(a.WjT + c * kD + c0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 wv = __ldg(w4 + i);
+                    v[4 * i] = fmaf(xr[c], wv.x, v[4 * i]), v[4 * i + 1] = fmaf(xr[c], wv.y, v[4 * i + 1]);
+                    v[4 * i + 2] = fmaf(xr[c], wv.z, v[4 * i + 2]), v[4 * i + 3] = fmaf(xr[c], wv.w, v[4 * i + 3]);
+                }
             }
             tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
@@ -364,10 +423,43 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 if (it + 1 < L) tmem_st32(trow + kColH + c0, v);        // h keeps living in TMEM
             }
             if (it + 1 == L) {
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(a.h + blk_index(g, c0, kD));
+                // ---- step epilogue (was out_update_kernel): pred_x0 = h . Wout^T + b (fp32), sampler update of x
+                float acc[kP];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i * 128] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int p = 0; p < kP; ++p) acc[p] = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const float4* w4 = reinterpret_cast<const float4*>(a.WoT + (size_t)(c0 + i) * 32);
+                    float wr[28];
+#pragma unroll
+                    for (int q4 = 0; q4 < 7; ++q4) {
+                        const float4 wv = __ldg(w4 + q4);
+                        wr[4 * q4] = wv.x, wr[4 * q4 + 1] = wv.y, wr[4 * q4 + 2] = wv.z, wr[4 * q4 + 3] = wv.w;
+                    }
+#pragma unroll
+                    for (int p = 0; p < kP; ++p) acc[p] = fmaf(v[i], wr[p], acc[p]);
+                }
+                float* part = reinterpret_cast<float*>(ringA);        // [4 cq][128 rows][28] partial dot products (rings are idle now)
+#pragma unroll
+                for (int p4 = 0; p4 < 7; ++p4) {
+                    float4 o = make_float4(acc[4 * p4], acc[4 * p4 + 1], p4 < 6 ? acc[4 * p4 + 2] : 0.f, p4 < 6 ? acc[4 * p4 + 3] : 0.f);
+                    *reinterpret_cast<float4*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) = o;
+                }
+                named_bar_sync(5, kRowThreads);
+                if (cq == 0 && valid) {
+                    const float* cf = a.coef;
+                    for (int p = 0; p < kP; ++p) {
+                        float x0 = __ldg(a.bo + p) + ((part[(0 * kTileRows + r) * 28 + p] + part[(1 * kTileRows + r) * 28 + p]) +
+                                                      (part[(2 * kTileRows + r) * 28 + p] + part[(3 * kTileRows + r) * 28 + p]));
+                        if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                        const size_t idx = (size_t)g * kP + p;
+                        a.x0_out[idx] = x0;
+                        if ((a.mode & 0xF) != 0) {
+                            const float nz = a.noise ? a.noise[idx] : 0.f;
+                            const float xo = a.x_in[idx];
+                            a.x_out[idx] = (a.mode & 0xF) == 1 ? ddim_rule(xo, x0, cf, nz) : ddpm_rule(xo, x0, cf, nz);
+                        }
+                    }
                 }
                 break;
             }

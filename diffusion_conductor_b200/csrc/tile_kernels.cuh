@@ -272,6 +272,7 @@ struct LayerBarriers {
     uint64_t a_ready;
     uint64_t s_free;       // row threads -> FiLM-projection issuer: the S accumulator has been consumed
     uint64_t q_full;
+    uint64_t aemb_ready;   // persistent kernel: this tile's A_emb image has been written (row threads -> producer)
     uint64_t d_ready[3];   // 0: S, 1: H, 2: W
     uint32_t tmem_base;
 };
