@@ -412,7 +412,7 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         // whole denoise step in ONE launch: A_emb + h0 prologue, all layers, output head + sampler update
         StepArgs sa{};
         sa.L = L, sa.M = M, sa.T = h->T;
-        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm, sa.h = h->hbuf;
+        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm;
         sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
         sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
         sa.length = h->has_length ? h->length : nullptr;
