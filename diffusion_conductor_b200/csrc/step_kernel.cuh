@@ -286,20 +286,34 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         float v[32];
 
         // ---- step prologue (was step_begin_kernel): this tile's A_emb = SiLU(te + xp) image -> global (streamed back
-        //      24 times by ring A), h0 = joint_embed(x) + sequence_embedding -> TMEM (stays there for the whole step)
+        //      24 times by ring A), h0 = joint_embed(x) + sequence_embedding -> TMEM (stays there for the whole step).
+        //      Small operands are staged through ring A (idle until the image exists): with 221 KB of shared memory
+        //      the L1 is only a few KB, so repeated global reads of weights would all go to L2.
         {
+            float* sWj = reinterpret_cast<float*>(ringA);                 // [26][128]
+            float* sbj = sWj + kP * kD;                                   // [128]
+            float* sx = sbj + kD;                                         // [128][26] x rows of this tile
+            float* ste = sx + kTileRows * kP;                             // [2][512] time embedding of the tile's (<= 2) clips
+            const int tx = threadIdx.x;
+            const long row0g = (long)blockIdx.x * kTileRows;
+            const int clip0 = (int)(row0g / a.T);
+            for (int i = tx; i < kP * kD; i += kRowThreads) sWj[i] = a.WjT[i];
+            if (tx < kD) sbj[tx] = a.bj[tx];
+            for (int i = tx; i < kTileRows * kP; i += kRowThreads) sx[i] = (row0g * kP + i < (long)a.M * kP) ? a.x_in[row0g * kP + i] : 0.f;
+            for (int i = tx; i < 2 * kE; i += kRowThreads) ste[i] = a.te[(size_t)(clip0 + (i >> 9)) * a.te_stride * ((clip0 + (i >> 9)) * a.T < a.M ? 1 : 0) + (i & 511)];
+            named_bar_sync(5, kRowThreads);
             uint8_t* img = a.aemb_out + (size_t)blockIdx.x * 8 * kStageABytes;
 #pragma unroll 4
             for (int k = 0; k < 16; ++k) {                       // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
-                const int task = k * kRowThreads + (int)threadIdx.x;
+                const int task = k * kRowThreads + tx;
                 const int row = task >> 6, ch = task & 63;
-                const long gg = (long)blockIdx.x * kTileRows + row;
+                const long gg = row0g + row;
                 uint4 pk = make_uint4(0, 0, 0, 0);
                 if (gg < a.M) {
-                    const int bb = (int)(gg / a.T);
-                    const float4* xr = reinterpret_cast<const float4*>(a.xp + gg * kE + ch * 8);
-                    const float4* tr = reinterpret_cast<const float4*>(a.te + (size_t)bb * a.te_stride + ch * 8);
-                    const float4 a0 = __ldg(xr), a1 = __ldg(xr + 1), t0 = __ldg(tr), t1 = __ldg(tr + 1);
+                    const int bb = (int)(gg / a.T) - clip0;
+                    const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + ch * 8);
+                    const float4* tr = reinterpret_cast<const float4*>(ste + bb * kE + ch * 8);
+                    const float4 a0 = __ldg(xr4), a1 = __ldg(xr4 + 1), t0 = tr[0], t1 = tr[1];
                     const float e8[8] = {a0.x + t0.x, a0.y + t0.y, a0.z + t0.z, a0.w + t0.w, a1.x + t1.x, a1.y + t1.y, a1.z + t1.z, a1.w + t1.w};
                     uint32_t p[4];
 #pragma unroll
@@ -309,33 +323,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 }
                 *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
             }
-            __threadfence();                                       // the image must have reached L2 ...
-            asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
             // h0 for this thread's 32 features
-            float xr[kP];
-#pragma unroll
-            for (int i = 0; i < kP; ++i) xr[i] = valid ? a.x_in[(size_t)g * kP + i] : 0.f;     // plain loads: x may be updated in place below
-            const float4* bj4 = reinterpret_cast<const float4*>(a.bj + c0);
             const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 bv = __ldg(bj4 + i), pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 bv = *reinterpret_cast<const float4*>(sbj + c0 + 4 * i), pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[4 * i] = bv.x + pv.x, v[4 * i + 1] = bv.y + pv.y, v[4 * i + 2] = bv.z + pv.z, v[4 * i + 3] = bv.w + pv.w;
             }
-#pragma unroll
+#pragma unroll 2
             for (int c = 0; c < kP; ++c) {
-                const float4* w4 = reinterpret_cast<const float4*>(a.WjT + c * kD + c0);
+                const float xc = sx[r * kP + c];
+                const float4* w4 = reinterpret_cast<const float4*>(sWj + c * kD + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 wv = __ldg(w4 + i);
-                    v[4 * i] = fmaf(xr[c], wv.x, v[4 * i]), v[4 * i + 1] = fmaf(xr[c], wv.y, v[4 * i + 1]);
-                    v[4 * i + 2] = fmaf(xr[c], wv.z, v[4 * i + 2]), v[4 * i + 3] = fmaf(xr[c], wv.w, v[4 * i + 3]);
+                    const float4 wv = w4[i];
+                    v[4 * i] = fmaf(xc, wv.x, v[4 * i]), v[4 * i + 1] = fmaf(xc, wv.y, v[4 * i + 1]);
+                    v[4 * i + 2] = fmaf(xc, wv.z, v[4 * i + 2]), v[4 * i + 3] = fmaf(xc, wv.w, v[4 * i + 3]);
                 }
             }
             tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
+            __threadfence();                                       // the image must have reached L2 ...
+            asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
+            named_bar_sync(5, kRowThreads);                        // every row thread is done with the staging area in ring A
+            if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
         }
 
         for (int it = -1; it < L; ++it) {
@@ -423,44 +434,54 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 if (it + 1 < L) tmem_st32(trow + kColH + c0, v);        // h keeps living in TMEM
             }
             if (it + 1 == L) {
-                // ---- step epilogue (was out_update_kernel): pred_x0 = h . Wout^T + b (fp32), sampler update of x
-                float acc[kP];
+                // ---- step epilogue (was out_update_kernel): pred_x0 = h . Wout^T + b (fp32), sampler update of x.
+                //      Operands and results are staged through the (now idle) rings for coalesced global traffic.
+                float* part = reinterpret_cast<float*>(ringA);            // [4 cq][128 rows][28] partial dot products
+                float* sWo = part + 4 * kTileRows * 28;                   // [128][32]
+                float* sxo = sWo + kD * 32;                               // [128][26] x rows (old -> new)
+                float* sx0 = reinterpret_cast<float*>(ringB);             // [128][26] pred_xstart
+                const int tx = threadIdx.x;
+                const long row0g = (long)blockIdx.x * kTileRows;
+                const long nel = min((long)kTileRows * kP, (long)a.M * kP - row0g * kP);
+                for (int i = tx; i < kD * 32; i += kRowThreads) sWo[i] = a.WoT[i];
+                if ((a.mode & 0xF) != 0)
+                    for (int i = tx; i < nel; i += kRowThreads) sxo[i] = a.x_in[row0g * kP + i];
+                named_bar_sync(5, kRowThreads);
+                float acc[28];
 #pragma unroll
-                for (int p = 0; p < kP; ++p) acc[p] = 0.f;
-#pragma unroll 4
+                for (int p = 0; p < 28; ++p) acc[p] = 0.f;
+#pragma unroll 2
                 for (int i = 0; i < 32; ++i) {
-                    const float4* w4 = reinterpret_cast<const float4*>(a.WoT + (size_t)(c0 + i) * 32);
-                    float wr[28];
+                    const float4* w4 = reinterpret_cast<const float4*>(sWo + (size_t)(c0 + i) * 32);
 #pragma unroll
                     for (int q4 = 0; q4 < 7; ++q4) {
-                        const float4 wv = __ldg(w4 + q4);
-                        wr[4 * q4] = wv.x, wr[4 * q4 + 1] = wv.y, wr[4 * q4 + 2] = wv.z, wr[4 * q4 + 3] = wv.w;
+                        const float4 wv = w4[q4];
+                        acc[4 * q4] = fmaf(v[i], wv.x, acc[4 * q4]), acc[4 * q4 + 1] = fmaf(v[i], wv.y, acc[4 * q4 + 1]);
+                        acc[4 * q4 + 2] = fmaf(v[i], wv.z, acc[4 * q4 + 2]), acc[4 * q4 + 3] = fmaf(v[i], wv.w, acc[4 * q4 + 3]);
                     }
-#pragma unroll
-                    for (int p = 0; p < kP; ++p) acc[p] = fmaf(v[i], wr[p], acc[p]);
                 }
-                float* part = reinterpret_cast<float*>(ringA);        // [4 cq][128 rows][28] partial dot products (rings are idle now)
 #pragma unroll
-                for (int p4 = 0; p4 < 7; ++p4) {
-                    float4 o = make_float4(acc[4 * p4], acc[4 * p4 + 1], p4 < 6 ? acc[4 * p4 + 2] : 0.f, p4 < 6 ? acc[4 * p4 + 3] : 0.f);
-                    *reinterpret_cast<float4*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) = o;
-                }
+                for (int p4 = 0; p4 < 7; ++p4)
+                    *reinterpret_cast<float4*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) =
+                        make_float4(acc[4 * p4], acc[4 * p4 + 1], acc[4 * p4 + 2], acc[4 * p4 + 3]);
                 named_bar_sync(5, kRowThreads);
-                if (cq == 0 && valid) {
+                {   // 128 rows x 26 outputs over 512 threads
                     const float* cf = a.coef;
-                    for (int p = 0; p < kP; ++p) {
-                        float x0 = __ldg(a.bo + p) + ((part[(0 * kTileRows + r) * 28 + p] + part[(1 * kTileRows + r) * 28 + p]) +
-                                                      (part[(2 * kTileRows + r) * 28 + p] + part[(3 * kTileRows + r) * 28 + p]));
+                    for (int i = tx; i < kTileRows * kP; i += kRowThreads) {
+                        const int rr = i / kP, p = i - rr * kP;
+                        float x0 = __ldg(a.bo + p) + ((part[(0 * kTileRows + rr) * 28 + p] + part[(1 * kTileRows + rr) * 28 + p]) +
+                                                      (part[(2 * kTileRows + rr) * 28 + p] + part[(3 * kTileRows + rr) * 28 + p]));
                         if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                        const size_t idx = (size_t)g * kP + p;
-                        a.x0_out[idx] = x0;
-                        if ((a.mode & 0xF) != 0) {
-                            const float nz = a.noise ? a.noise[idx] : 0.f;
-                            const float xo = a.x_in[idx];
-                            a.x_out[idx] = (a.mode & 0xF) == 1 ? ddim_rule(xo, x0, cf, nz) : ddpm_rule(xo, x0, cf, nz);
+                        if (i < nel) {
+                            a.x0_out[row0g * kP + i] = x0;
+                            if ((a.mode & 0xF) != 0) {
+                                const float nz = a.noise ? a.noise[row0g * kP + i] : 0.f;
+                                a.x_out[row0g * kP + i] = (a.mode & 0xF) == 1 ? ddim_rule(sxo[i], x0, cf, nz) : ddpm_rule(sxo[i], x0, cf, nz);
+                            }
                         }
                     }
                 }
+                (void)sx0;
                 break;
             }
 
