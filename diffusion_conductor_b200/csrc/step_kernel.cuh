@@ -106,8 +106,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         if (lane == 0) {
             const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
             uint32_t it_ = 0;
-            mbar_wait(smem_u32(&bars->aemb_ready), 0);          // the row threads have written this tile's A_emb image
-            asm volatile("fence.proxy.async;" ::: "memory");
             auto stage_in = [&](const uint8_t* a_src, const uint8_t* w_src, uint32_t w_bytes) {
                 const uint32_t st = it_ % kNA, ph = (it_ / kNA) & 1u;
                 ++it_;
@@ -120,6 +118,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             };
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
+                    if (it == 0) {
+                        mbar_wait(smem_u32(&bars->aemb_ready), 0);      // the row threads have written this tile's A_emb image
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
                     const uint32_t so[3] = {a.off[kOWeSa], a.off[kOWeCa], a.off[kOWeFf]};
                     for (int o = 0; o < 3; ++o)
@@ -290,63 +292,70 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         //      Small operands are staged through ring A (idle until the image exists): with 221 KB of shared memory
         //      the L1 is only a few KB, so repeated global reads of weights would all go to L2.
         {
-            float* sWj = reinterpret_cast<float*>(ringA);                 // [26][128]
+            float* sWj = reinterpret_cast<float*>(xbuf);                  // [26][128]
             float* sbj = sWj + kP * kD;                                   // [128]
             float* sx = sbj + kD;                                         // [128][26] x rows of this tile
             float* ste = sx + kTileRows * kP;                             // [2][512] time embedding of the tile's (<= 2) clips
             const int tx = threadIdx.x;
             const long row0g = (long)blockIdx.x * kTileRows;
             const int clip0 = (int)(row0g / a.T);
-            for (int i = tx; i < kP * kD; i += kRowThreads) sWj[i] = a.WjT[i];
-            if (tx < kD) sbj[tx] = a.bj[tx];
-            for (int i = tx; i < kTileRows * kP; i += kRowThreads) sx[i] = (row0g * kP + i < (long)a.M * kP) ? a.x_in[row0g * kP + i] : 0.f;
-            for (int i = tx; i < 2 * kE; i += kRowThreads) ste[i] = a.te[(size_t)(clip0 + (i >> 9)) * a.te_stride * ((clip0 + (i >> 9)) * a.T < a.M ? 1 : 0) + (i & 511)];
-            named_bar_sync(5, kRowThreads);
-            uint8_t* img = a.aemb_out + (size_t)blockIdx.x * 8 * kStageABytes;
-#pragma unroll 4
-            for (int k = 0; k < 16; ++k) {                       // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
-                const int task = k * kRowThreads + tx;
-                const int row = task >> 6, ch = task & 63;
-                const long gg = row0g + row;
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                if (gg < a.M) {
-                    const int bb = (int)(gg / a.T) - clip0;
-                    const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + ch * 8);
-                    const float4* tr = reinterpret_cast<const float4*>(ste + bb * kE + ch * 8);
-                    const float4 a0 = __ldg(xr4), a1 = __ldg(xr4 + 1), t0 = tr[0], t1 = tr[1];
-                    const float e8[8] = {a0.x + t0.x, a0.y + t0.y, a0.z + t0.z, a0.w + t0.w, a1.x + t1.x, a1.y + t1.y, a1.z + t1.z, a1.w + t1.w};
-                    uint32_t p[4];
+            {   // every global load of the staging phase is issued before the first store (one L2 round trip)
+                float tw[7], tv[7], tt[2];
+                const long xlim = (long)a.M * kP - row0g * kP;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        p[i] = pack2<kBf16>(__fdividef(e8[2 * i], 1.f + __expf(-e8[2 * i])), __fdividef(e8[2 * i + 1], 1.f + __expf(-e8[2 * i + 1])));
-                    pk = make_uint4(p[0], p[1], p[2], p[3]);
+                for (int j = 0; j < 7; ++j) {
+                    const int i = tx + j * kRowThreads;
+                    tw[j] = i < kP * kD ? __ldg(a.WjT + i) : 0.f;
+                    tv[j] = (i < kTileRows * kP && i < xlim) ? __ldcg(a.x_in + row0g * kP + i) : 0.f;
                 }
-                *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
-            }
-            // h0 for this thread's 32 features
-            const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 bv = *reinterpret_cast<const float4*>(sbj + c0 + 4 * i), pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[4 * i] = bv.x + pv.x, v[4 * i + 1] = bv.y + pv.y, v[4 * i + 2] = bv.z + pv.z, v[4 * i + 3] = bv.w + pv.w;
-            }
-#pragma unroll 2
-            for (int c = 0; c < kP; ++c) {
-                const float xc = sx[r * kP + c];
-                const float4* w4 = reinterpret_cast<const float4*>(sWj + c * kD + c0);
+                for (int j = 0; j < 2; ++j) {
+                    const int i = tx + j * kRowThreads, cl = clip0 + (i >> 9);
+                    tt[j] = __ldcg(a.te + ((long)cl * a.T < (long)a.M ? (size_t)cl * a.te_stride : 0) + (i & 511));
+                }
+                const float tb = tx < kD ? __ldg(a.bj + tx) : 0.f;
+                const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 wv = w4[i];
-                    v[4 * i] = fmaf(xc, wv.x, v[4 * i]), v[4 * i + 1] = fmaf(xc, wv.y, v[4 * i + 1]);
-                    v[4 * i + 2] = fmaf(xc, wv.z, v[4 * i + 2]), v[4 * i + 3] = fmaf(xc, wv.w, v[4 * i + 3]);
+                    const float4 pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * i] = pv.x, v[4 * i + 1] = pv.y, v[4 * i + 2] = pv.z, v[4 * i + 3] = pv.w;
                 }
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int i = tx + j * kRowThreads;
+                    if (i < kP * kD) sWj[i] = tw[j], sx[i] = tv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) ste[tx + j * kRowThreads] = tt[j];
+                if (tx < kD) sbj[tx] = tb;
+            }
+            named_bar_sync(5, kRowThreads);
+            if (tx == 0) tl_mark(a, 128);
+            // h0 for this thread's 32 features (v already holds the sequence embedding)
+            {
+                uint64_t hv[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 bv = *reinterpret_cast<const float4*>(sbj + c0 + 4 * i);
+                    hv[2 * i] = pk2(bv.x + v[4 * i], bv.y + v[4 * i + 1]), hv[2 * i + 1] = pk2(bv.z + v[4 * i + 2], bv.w + v[4 * i + 3]);
+                }
+#pragma unroll 2
+                for (int c = 0; c < kP; ++c) {
+                    const float xc = sx[r * kP + c];
+                    const uint64_t xc2 = pk2(xc, xc);
+                    const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sWj + c * kD + c0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const ulonglong2 wv = w2[i];
+                        hv[2 * i] = ffma2(xc2, wv.x, hv[2 * i]), hv[2 * i + 1] = ffma2(xc2, wv.y, hv[2 * i + 1]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) upk2(hv[i], v[2 * i], v[2 * i + 1]);
             }
             tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
-            __threadfence();                                       // the image must have reached L2 ...
-            asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
-            named_bar_sync(5, kRowThreads);                        // every row thread is done with the staging area in ring A
-            if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
+            if (tx == 0) tl_mark(a, 129);
         }
 
         for (int it = -1; it < L; ++it) {
@@ -360,8 +369,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
                 tc_fence_before();                                           // S consumed: the next FiLM projection may start
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(s_free_addr);
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
+                if (lane == 0) mbar_arrive(s_free_addr);
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
     
                 // ================= cross-attention
                 rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
                 tmem_wait_st();
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
                 rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 softmax16(v + 16);
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
                 rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
@@ -392,8 +401,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
                 tc_fence_before();                                           // S consumed: the next FiLM projection may start
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(s_free_addr);
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
+                if (lane == 0) mbar_arrive(s_free_addr);
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
     
                 // ================= FFN (no pre-norm, reference transformer.py:170-173)
                 rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
@@ -404,7 +413,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
                 tmem_wait_st();
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
                 rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
                 {
                     float u[16];                                             // hidden 64 = 4 quarters of 16
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
                     store_a16<kBf16>(awork, r, 16 * cq, u);
                 }
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
                 rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 row_stats32(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
-                rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
+                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
                 rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
             }
 
@@ -438,50 +447,67 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 //      Operands and results are staged through the (now idle) rings for coalesced global traffic.
                 float* part = reinterpret_cast<float*>(ringA);            // [4 cq][128 rows][28] partial dot products
                 float* sWo = part + 4 * kTileRows * 28;                   // [128][32]
-                float* sxo = sWo + kD * 32;                               // [128][26] x rows (old -> new)
-                float* sx0 = reinterpret_cast<float*>(ringB);             // [128][26] pred_xstart
+                float* sbo = sWo + kD * 32;                               // [32]
+                float* sxo = reinterpret_cast<float*>(ringB);             // [128][26] x rows before the update
+                float* snz = sxo + kTileRows * kP;                        // [128][26] noise
                 const int tx = threadIdx.x;
                 const long row0g = (long)blockIdx.x * kTileRows;
-                const long nel = min((long)kTileRows * kP, (long)a.M * kP - row0g * kP);
-                for (int i = tx; i < kD * 32; i += kRowThreads) sWo[i] = a.WoT[i];
-                if ((a.mode & 0xF) != 0)
-                    for (int i = tx; i < nel; i += kRowThreads) sxo[i] = a.x_in[row0g * kP + i];
-                named_bar_sync(5, kRowThreads);
-                float acc[28];
+                const int nel = (int)min((long)kTileRows * kP, (long)a.M * kP - row0g * kP);
+                const int smode = a.mode & 0xF;
+                {   // all global loads first, then the shared-memory stores
+                    const float4* wo4 = reinterpret_cast<const float4*>(a.WoT);
+                    const float4 w0 = __ldg(wo4 + tx), w1 = __ldg(wo4 + tx + kRowThreads);
+                    float to[7], tn[7];
 #pragma unroll
-                for (int p = 0; p < 28; ++p) acc[p] = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < 32; ++i) {
-                    const float4* w4 = reinterpret_cast<const float4*>(sWo + (size_t)(c0 + i) * 32);
-#pragma unroll
-                    for (int q4 = 0; q4 < 7; ++q4) {
-                        const float4 wv = w4[q4];
-                        acc[4 * q4] = fmaf(v[i], wv.x, acc[4 * q4]), acc[4 * q4 + 1] = fmaf(v[i], wv.y, acc[4 * q4 + 1]);
-                        acc[4 * q4 + 2] = fmaf(v[i], wv.z, acc[4 * q4 + 2]), acc[4 * q4 + 3] = fmaf(v[i], wv.w, acc[4 * q4 + 3]);
+                    for (int j = 0; j < 7; ++j) {
+                        const int i = tx + j * kRowThreads;
+                        to[j] = (smode != 0 && i < nel) ? __ldcg(a.x_in + row0g * kP + i) : 0.f;
+                        tn[j] = (smode != 0 && a.noise != nullptr && i < nel) ? __ldcg(a.noise + row0g * kP + i) : 0.f;
                     }
-                }
+                    const float tb = tx < kP ? __ldg(a.bo + tx) : 0.f;
+                    reinterpret_cast<float4*>(sWo)[tx] = w0, reinterpret_cast<float4*>(sWo)[tx + kRowThreads] = w1;
 #pragma unroll
-                for (int p4 = 0; p4 < 7; ++p4)
-                    *reinterpret_cast<float4*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) =
-                        make_float4(acc[4 * p4], acc[4 * p4 + 1], acc[4 * p4 + 2], acc[4 * p4 + 3]);
+                    for (int j = 0; j < 7; ++j) {
+                        const int i = tx + j * kRowThreads;
+                        if (i < kTileRows * kP) sxo[i] = to[j], snz[i] = tn[j];
+                    }
+                    if (tx < 32) sbo[tx] = tb;
+                }
+                named_bar_sync(5, kRowThreads);
+                {
+                    uint64_t acc[14];
+#pragma unroll
+                    for (int p = 0; p < 14; ++p) acc[p] = 0ull;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sWo + (size_t)(c0 + i) * 32);
+                        const uint64_t hv = pk2(v[i], v[i]);
+#pragma unroll
+                        for (int q4 = 0; q4 < 7; ++q4) {
+                            const ulonglong2 wv = w2[q4];
+                            acc[2 * q4] = ffma2(hv, wv.x, acc[2 * q4]), acc[2 * q4 + 1] = ffma2(hv, wv.y, acc[2 * q4 + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int p4 = 0; p4 < 7; ++p4)
+                        *reinterpret_cast<ulonglong2*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) = make_ulonglong2(acc[2 * p4], acc[2 * p4 + 1]);
+                }
                 named_bar_sync(5, kRowThreads);
                 {   // 128 rows x 26 outputs over 512 threads
                     const float* cf = a.coef;
-                    for (int i = tx; i < kTileRows * kP; i += kRowThreads) {
-                        const int rr = i / kP, p = i - rr * kP;
-                        float x0 = __ldg(a.bo + p) + ((part[(0 * kTileRows + rr) * 28 + p] + part[(1 * kTileRows + rr) * 28 + p]) +
-                                                      (part[(2 * kTileRows + rr) * 28 + p] + part[(3 * kTileRows + rr) * 28 + p]));
-                        if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) {
+                        const int i = tx + j * kRowThreads;
                         if (i < nel) {
+                            const int rr = i / kP, p = i - rr * kP;
+                            float x0 = sbo[p] + ((part[(0 * kTileRows + rr) * 28 + p] + part[(1 * kTileRows + rr) * 28 + p]) +
+                                                 (part[(2 * kTileRows + rr) * 28 + p] + part[(3 * kTileRows + rr) * 28 + p]));
+                            if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
                             a.x0_out[row0g * kP + i] = x0;
-                            if ((a.mode & 0xF) != 0) {
-                                const float nz = a.noise ? a.noise[row0g * kP + i] : 0.f;
-                                a.x_out[row0g * kP + i] = (a.mode & 0xF) == 1 ? ddim_rule(sxo[i], x0, cf, nz) : ddpm_rule(sxo[i], x0, cf, nz);
-                            }
+                            if (smode != 0) a.x_out[row0g * kP + i] = smode == 1 ? ddim_rule(sxo[i], x0, cf, snz[i]) : ddpm_rule(sxo[i], x0, cf, snz[i]);
                         }
                     }
                 }
-                (void)sx0;
                 break;
             }
 
@@ -491,7 +517,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(a_ready_addr, lane);
+            rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
+            if (it < 0) {
+                // ---- rest of the step prologue, overlapped with the first q|k|v MMAs: this tile's A_emb image -> global
+                const int tx = threadIdx.x;
+                const long row0g = (long)blockIdx.x * kTileRows;
+                const int clip0 = (int)(row0g / a.T);
+                const float* ste = reinterpret_cast<const float*>(xbuf) + kP * kD + kD + kTileRows * kP;
+            uint8_t* img = a.aemb_out + (size_t)blockIdx.x * 8 * kStageABytes;
+                for (int k0 = 0; k0 < 16; k0 += 4) {                 // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
+                    float4 xa[4][2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int task = (k0 + k) * kRowThreads + tx;
+                        const long gg = min(row0g + (task >> 6), (long)a.M - 1);
+                        const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + (task & 63) * 8);
+                        xa[k][0] = __ldg(xr4), xa[k][1] = __ldg(xr4 + 1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int task = (k0 + k) * kRowThreads + tx;
+                        const int row = task >> 6, ch = task & 63;
+                        const long gg = row0g + row;
+                        const int bb = (gg < a.M && gg >= (long)(clip0 + 1) * a.T) ? 1 : 0;
+                        const float4* tr = reinterpret_cast<const float4*>(ste + bb * kE + ch * 8);
+                        const float4 a0 = xa[k][0], a1 = xa[k][1], t0 = tr[0], t1 = tr[1];
+                        const float e8[8] = {a0.x + t0.x, a0.y + t0.y, a0.z + t0.z, a0.w + t0.w, a1.x + t1.x, a1.y + t1.y, a1.z + t1.z, a1.w + t1.w};
+                        uint32_t p[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            p[i] = pack2<kBf16>(__fdividef(e8[2 * i], 1.f + __expf(-e8[2 * i])), __fdividef(e8[2 * i + 1], 1.f + __expf(-e8[2 * i + 1])));
+                        const uint4 pk = gg < a.M ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
+                    }
+                }
+                __threadfence();                                       // the image must have reached L2 ...
+                asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
+                named_bar_sync(5, kRowThreads);                        // every row thread is done with the staging area in xbuf
+                if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
+                if (tx == 0) tl_mark(a, 127);
+            }
             rows_wait(bars, 2, ph[2]);
             if (threadIdx.x == 0) tl_mark(a, 112);
             {
@@ -595,7 +660,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         store_a16<kBf16>(vimg, r, c0, z);
                         store_a16<kBf16>(vimg, r, c0 + 16, z + 16);
                     }
-                    rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
+                    rows_publish<false>(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
                     if (tx == 0) tl_mark(a, 122);
                     if (ps == 0) {
                         // q: softmax over head-dim -> operand buffer (A operand of the next layer's q . blockdiag(A_sa));
@@ -605,7 +670,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         tmem_wait_ld();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(s_free_addr);
+                        if (lane == 0) mbar_arrive(s_free_addr);
                         add_bias32(qv, prm_sa + kPrmSaBq + c0);
                         softmax16(qv);
                         softmax16(qv + 16);
@@ -652,9 +717,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 }
                 if (tx == 0) tl_mark(a, 124);
                 // ---- publish: one arrival per (tile, clip); the counters only grow within a step (zeroed by the host)
-                __threadfence();
                 named_bar_sync(5, kRowThreads);
-                if ((tx == 0 || tx == 32) && (tx >> 5) < n_seg) atomicAdd(a.clip_cnt + first_clip + (tx >> 5), 1);
+                if ((tx == 0 || tx == 32) && (tx >> 5) < n_seg) {
+                    __threadfence();                                       // cumulative: orders the whole CTA's partials (bar.sync above)
+                    atomicAdd(a.clip_cnt + first_clip + (tx >> 5), 1);
+                }
                 // ---- meanwhile: clear the two image buffers (E / V are dead: the last K^T V pass has completed) and
                 //      fetch the next layer's parameters
                 {
@@ -663,14 +730,20 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         reinterpret_cast<uint4*>(xbuf)[i] = z4;
                         reinterpret_cast<uint4*>(ringB)[i] = z4;
                     }
-                    const float* pn = a.prm + (size_t)(it + 1) * kPrmFloats;
-                    for (int i = tx; i < kPrmFloats; i += kRowThreads) prm[i] = pn[i];
-                    if (it + 2 < L)
-                        for (int i = tx; i < 384; i += kRowThreads) prm_sa[i] = pn[kPrmFloats + i];
+                    // all loads in flight before the first store (one L2 round trip, not six)
+                    const float4* pn4 = reinterpret_cast<const float4*>(a.prm + (size_t)(it + 1) * kPrmFloats);
+                    static_assert(kPrmFloats % 4 == 0 && kPrmFloats / 4 <= 2 * kRowThreads, "parameter block layout");
+                    const float4 p0 = __ldg(pn4 + tx);
+                    const float4 p1 = tx + kRowThreads < kPrmFloats / 4 ? __ldg(pn4 + tx + kRowThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 p2 = (it + 2 < L && tx < 96) ? __ldg(pn4 + kPrmFloats / 4 + tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(prm)[tx] = p0;
+                    if (tx + kRowThreads < kPrmFloats / 4) reinterpret_cast<float4*>(prm)[tx + kRowThreads] = p1;
+                    if (it + 2 < L && tx < 96) reinterpret_cast<float4*>(prm_sa)[tx] = p2;
                 }
                 // ---- wait until every tile of this tile's clip(s) has published, then merge the partials (online-softmax
                 //      rescaling) straight into block-diagonal B-operand images in shared memory: segment 0 -> xbuf,
                 //      segment 1 -> ring B.  Every tile does this for itself: no second global round trip.
+                if (tx == 0) tl_mark(a, 121);
                 if ((tx == 0 || tx == 32) && (tx >> 5) < n_seg) {
                     const int clip = first_clip + (tx >> 5);
                     const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;
@@ -740,7 +813,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         }
                     }
                 }
-                rows_publish(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
+                rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
                 if (tx == 0) tl_mark(a, 126);
             }
         }

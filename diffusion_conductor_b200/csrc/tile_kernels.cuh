@@ -459,11 +459,19 @@ __device__ __forceinline__ void add_bias32(float* v, const float* bias) {
 }
 
 // row threads signal "A operand (and any TMEM writes) ready": one elected arrive per warp on the leader CTA's barrier
-__device__ __forceinline__ void rows_publish(uint32_t a_ready_cluster_addr, int lane) {
+// kRemote: the barrier lives in the pair leader's shared memory (release.cluster arrive: costs a memory barrier).
+// Within one CTA the plain arrive (release.cta) is enough: the operand image was fenced for the async proxy above.
+template <bool kRemote>
+__device__ __forceinline__ void bar_arrive(uint32_t addr) {
+    if constexpr (kRemote) mbar_arrive_cluster(addr);
+    else mbar_arrive(addr);
+}
+template <bool kRemote = true>
+__device__ __forceinline__ void rows_publish(uint32_t a_ready_addr, int lane) {
     fence_async_smem();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(a_ready_cluster_addr);
+    if (lane == 0) bar_arrive<kRemote>(a_ready_addr);
 }
 __device__ __forceinline__ void rows_wait(LayerBarriers* bars, int which, uint32_t& phase) {
     mbar_wait(smem_u32(&bars->d_ready[which]), phase & 1u);
@@ -800,8 +808,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
             tc_fence_before();                                           // S consumed: the next FiLM projection may start
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(s_free_addr);
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
+            if (lane == 0) bar_arrive<kPair>(s_free_addr);
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
 
             // ================= cross-attention
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
@@ -814,7 +822,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
@@ -823,7 +831,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             softmax16(v + 16);
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
@@ -832,8 +840,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
             tc_fence_before();                                           // S consumed: the next FiLM projection may start
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(s_free_addr);
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
+            if (lane == 0) bar_arrive<kPair>(s_free_addr);
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
 
             // ================= FFN (no pre-norm, reference transformer.py:170-173)
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
@@ -844,7 +852,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
             {
                 float u[16];                                             // hidden 64 = 4 quarters of 16
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                 for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
                 store_a16<kBf16>(awork, r, 16 * cq, u);
             }
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
             tmem_ld32(trow + kColW + c0, v);
             tmem_wait_ld();
@@ -864,8 +872,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
             tc_fence_before();                                           // S consumed: the next FiLM projection may start
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(s_free_addr);
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
+            if (lane == 0) bar_arrive<kPair>(s_free_addr);
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
             rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
         }
 
@@ -885,7 +893,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
             normalize32(v, mean, rstd);                                  // LN affine folded into Wq/Wk/Wv
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-            rows_publish(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
+            rows_publish<kPair>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
             rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 112);
             const bool keep = valid && (a.length == nullptr || (long long)t < a.length[b]);
             // q: softmax over head-dim, written as this tile's packed A-operand image for the next launch
@@ -1017,7 +1025,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                         store_a16<kBf16>(vimg, r, c0, z);
                         store_a16<kBf16>(vimg, r, c0 + 16, z + 16);
                     }
-                    rows_publish(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
+                    rows_publish<kPair>(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
                     if (tx == 0) tl_mark(a, 122);
                     if (ps == 0) {
                         named_bar_sync(5, kRowThreads);                    // E image complete
@@ -1057,11 +1065,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) layer_kernel(const __grid_con
                     }
                 }
                 if (tx == 0) tl_mark(a, 124);
-                __threadfence();
                 named_bar_sync(5, kRowThreads);
                 if (tx == 0 || tx == 32) {          // one arrival counter per clip; both segments in parallel
                     const int sg = tx >> 5;
                     int f = 0;
+                    __threadfence();                // cumulative: orders the whole CTA's partials (bar.sync above)
                     if (sg < n_seg) {
                         const int clip = first_clip + sg;
                         const int ntiles = ((clip + 1) * a.T - 1) / kTileRows - (clip * a.T) / kTileRows + 1;

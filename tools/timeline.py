@@ -47,7 +47,7 @@ if first > 254:          # persistent step kernel: one long event list
         if i in names:
             nm = names[i]
         elif 120 <= i < 130:
-            nm = "rows epi: " + ["col max/E/V done", "?", "published V", "got KtV", "partials written", "all partials visible", "published merged images", "?", "?", "?"][i - 120]
+            nm = "rows epi: " + ["col max/E/V done", "buffers cleared, params reloaded", "published V", "got KtV", "partials written", "all partials visible", "published merged images", "A_emb image written", "prologue operands staged", "h0 in TMEM"][i - 120]
         elif 100 < i < 150:
             nm = "rows: got " + ROWW[i - 101]
         elif 150 < i < 200:
