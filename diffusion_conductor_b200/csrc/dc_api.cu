@@ -92,7 +92,7 @@ struct dc_handle {
     uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
     uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
     int mask_invert = 0;
-    float* kv_part = nullptr;     // [tiles][2][kKvPartFloats] partial time-axis reductions
+    float* kv_part = nullptr;     // [2][tiles][2][kKvPartFloats] partial time-axis reductions (per-layer path uses the first half)
     int* clip_cnt = nullptr;      // [B]
     int* clip_done = nullptr;     // [B] merges completed in the current step (persistent kernel)
     bool fuse_kv = false;
@@ -257,7 +257,7 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->bd_sa, (size_t)B * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->bd_ca, (size_t)B * L * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
-    DC_CUDA(h, cudaMalloc((void**)&h->kv_part, tiles * 2 * (size_t)kKvPartFloats * 4));
+    DC_CUDA(h, cudaMalloc((void**)&h->kv_part, 2 * tiles * 2 * (size_t)kKvPartFloats * 4));   // two parities (persistent kernel)
     DC_CUDA(h, cudaMalloc((void**)&h->clip_cnt, (size_t)B * 4));
     DC_CUDA(h, cudaMemset(h->clip_cnt, 0, (size_t)B * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->clip_done, (size_t)B * 4));
@@ -391,6 +391,35 @@ LayerArgs layer_args(dc_handle* h, int l) {
     return a;
 }
 
+// Persistent path: n_steps consecutive denoise steps (timestep indices step0, step0 - 1, ...) in ONE launch.
+// te: time-embedding base; the row of a step is te + timestep * te_step_stride (+ clip * te_stride).
+int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_stride, int te_step_stride, int mode, float* x_upd,
+                       float* x0_out, size_t x0_stride, float* x_trace, const float* noise, size_t noise_stride, int step0, int n_steps,
+                       cudaStream_t st) {
+    const int L = h->cfg.num_layers;
+    StepArgs sa{};
+    sa.L = L, sa.M = h->M, sa.T = h->T;
+    sa.n_steps = n_steps, sa.step0 = step0;
+    sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm;
+    sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
+    sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
+    sa.length = h->has_length ? h->length : nullptr;
+    sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.x0_stride = x0_stride, sa.x_trace = x_trace;
+    sa.noise = noise, sa.noise_stride = noise_stride, sa.xp = h->xp;
+    sa.te = te, sa.te_stride = te_stride, sa.te_step_stride = te_step_stride;
+    sa.coef = (mode & 0xF) ? h->coef : nullptr;
+    sa.mode = mode;
+    sa.WjT = h->WjT, sa.bj = h->bj, sa.pos = h->pos, sa.WoT = h->WoT, sa.bo = h->bo;
+    const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
+    for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
+    sa.timeline = h->timeline_on ? h->timeline : nullptr;
+    DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));      // arrival counters grow over the launch
+    DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
+    h->launches++;
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
 // One denoise step: A_emb + h0, L+1 tile launches with the time-axis reductions in between, output
 // head (+ sampler update).  te/te_stride select the per-sample or per-step time embedding.
 // `step` >= 0: the timestep is known on the host (persistent kernel: baked into the launch); -1: read from the device counter.
@@ -410,27 +439,10 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
     mark(-1);
     if (h->persist && (step >= 0 || !te_from_ctr)) {
         // whole denoise step in ONE launch: A_emb + h0 prologue, all layers, output head + sampler update
-        StepArgs sa{};
-        sa.L = L, sa.M = M, sa.T = h->T;
-        sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm;
-        sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
-        sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
-        sa.length = h->has_length ? h->length : nullptr;
-        sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.noise = noise, sa.xp = h->xp;
-        sa.te = te_from_ctr ? te + (size_t)step * kE : te;
-        sa.te_stride = te_stride;
-        sa.coef = (mode & 0xF) ? h->coef + (size_t)step * 8 : nullptr;
-        sa.mode = mode;
-        sa.WjT = h->WjT, sa.bj = h->bj, sa.pos = h->pos, sa.WoT = h->WoT, sa.bo = h->bo;
-        const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
-        for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
-        sa.timeline = h->timeline_on ? h->timeline : nullptr;
-        DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));
-        DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
-        h->launches++;
+        const int rc = enqueue_persistent(h, x_in, te, te_stride, te_from_ctr ? kE : 0, mode, x_upd, x0_out, 0, nullptr, noise, 0,
+                                          te_from_ctr ? step : 0, 1, st);
         mark(1);
-        DC_CUDA(h, cudaGetLastError());
-        return 0;
+        return rc;
     }
     const int* ctr = te_from_ctr ? h->step_ctr : nullptr;
     DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_begin_kernel<true> : step_begin_kernel<false>, dim3(blocks8), dim3(128), 0, st, x_in,
@@ -824,13 +836,17 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
     DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
     set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
     h->launches++;
-    const int64_t per_step = h->persist ? 1 : (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
-    if (h->use_graphs && !traced) {
+    const int64_t per_step = (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
+    if (h->persist) {
+        // the whole sampling loop is ONE launch of the persistent kernel (noise / trace slices are strides inside it)
+        if (int rc = enqueue_persistent(h, h->xwork, h->te_table, 0, kE, sampler, h->xwork, trace_x0 ? trace_x0 : h->x0work, trace_x0 ? n : 0,
+                                        trace_x, step_noise, step_noise ? n : 0, S - 1, S, st))
+            return rc;
+    } else if (h->use_graphs && !traced) {
         GraphKey key;
         key.sampler = sampler;
-        // persistent kernel: the timestep is a launch argument, so the graph holds all S steps (one kernel each);
         // per-layer path: the step index lives in device memory and a 5-step graph is replayed S/5 times
-        key.steps = h->persist ? S : ((S % 5 == 0) ? 5 : 1);
+        key.steps = (S % 5 == 0) ? 5 : 1;
         if (!h->gexec || !(h->gkey == key)) {
             drop_graph(h);
             cudaGraph_t graph = nullptr;
@@ -838,8 +854,8 @@ int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise,
             const int64_t before = h->launches;
             int rc = 0;
             for (int i = 0; i < key.steps && !rc; ++i) {
-                rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, h->persist ? S - 1 - i : -1, h->cap_stream);
-                if (!h->persist) launch_k(h->use_pdl, set_step_kernel, dim3(1), dim3(1), 0, h->cap_stream, h->step_ctr, 0, -1);
+                rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, h->x0work, nullptr, -1, h->cap_stream);
+                launch_k(h->use_pdl, set_step_kernel, dim3(1), dim3(1), 0, h->cap_stream, h->step_ctr, 0, -1);
             }
             h->launches = before;
             cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);

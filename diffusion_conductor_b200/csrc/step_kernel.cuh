@@ -20,14 +20,20 @@ struct StepArgs {
     const uint8_t* aemb;        // A_emb image [tiles][8][16 KB]
     const float* prm;           // [L][kPrmFloats]
     // step prologue / epilogue fused into the kernel (reference transformer.py:482,488-490,496; gaussian_diffusion.py:812-830)
+    // One launch runs n_steps consecutive denoise steps (timestep indices step0, step0 - 1, ...): a tile's x rows are
+    // private to its CTA, so the only cross-CTA traffic of the whole sampling loop is the per-clip partial exchange.
+    int n_steps, step0;
     const float* x_in;          // [M][26] current sample x_t
-    float* x_out;               // [M][26] updated sample (may alias x_in; null when mode == 0)
-    float* x0_out;              // [M][26] pred_xstart (model output)
-    const float* noise;         // [M][26] or null
+    float* x_out;               // [M][26] updated sample (may alias x_in; null when mode == 0; must be set when n_steps > 1)
+    float* x0_out;              // [M][26] pred_xstart (model output) of launch step i at x0_out + i * x0_stride
+    size_t x0_stride;
+    float* x_trace;             // optional: x after launch step i -> x_trace + i * M * 26
+    const float* noise;         // [M][26] (+ i * noise_stride for launch step i) or null
+    size_t noise_stride;
     const float* xp;            // [M][512] linear(xf_proj)
-    const float* te;            // time embedding row(s): te + b * te_stride
-    int te_stride;
-    const float* coef;          // the 8 update coefficients of this step (already offset), or null
+    const float* te;            // time embedding row(s): te + timestep * te_step_stride + b * te_stride
+    int te_stride, te_step_stride;
+    const float* coef;          // [S][8] update coefficients, row = timestep index; null when mode == 0
     int mode;                   // 0: model output only, 1: DDIM, 2: DDPM, | 0x10 clamp
     const float* WjT;           // [26][128] joint_embed weight, transposed
     const float* bj;            // [128]
@@ -38,8 +44,8 @@ struct StepArgs {
     const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
     size_t bd_ca_stride;
     uint8_t* bd_sa_out;         // [B][32 KB] self-attention images (written by the merging CTA, read by the clip's tiles)
-    float* kv_part;             // [tiles][2][kKvPartFloats]
-    int* clip_cnt;              // [B] arrival counters (zero between uses)
+    float* kv_part;             // [2 parity][tiles][2][kKvPartFloats]
+    int* clip_cnt;              // [B] arrival counters: grow monotonically over the launch (zeroed by the host before it)
     int* clip_done;             // [B] number of completed merges in this step (zeroed by step_begin)
     const long long* length;    // [B] or null
     uint32_t off[12];           // byte offsets of the packed matrices inside a layer slab (see dc_api.cu)
@@ -76,7 +82,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
     const int L = a.L;
 
     pdl_trigger();
-    for (int i = threadIdx.x; i < 384; i += kTileThreads) prm_sa[i] = a.prm[i];         // SA biases of layer 0
     if (warp == kProducerWarp && lane == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->fullA[i]), 1), mbar_init(smem_u32(&bars->emptyA[i]), 1);
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars->fullB[i]), 1), mbar_init(smem_u32(&bars->emptyB[i]), 1);
@@ -116,10 +121,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 if (a_src) bulk_g2s(smem_u32(stage), a_src, kStageABytes, full);
                 bulk_g2s(smem_u32(stage + kStageABytes), w_src, w_bytes, full);
             };
+            for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
                     if (it == 0) {
-                        mbar_wait(smem_u32(&bars->aemb_ready), 0);      // the row threads have written this tile's A_emb image
+                        mbar_wait(smem_u32(&bars->aemb_ready), (uint32_t)si & 1u);   // the row threads have written this step's A_emb image
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
@@ -147,11 +153,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     bulk_g2s(smem_u32(ringB + st * kSB), src + (size_t)k * kb_bytes, kb_bytes, full);
                 }
             };
+            uint32_t qf = 0;
+            for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
                     // ring B doubles as the segment-1 attention image until q . blockdiag(A_sa) of this layer has completed
-                    mbar_wait(smem_u32(&bars->q_full), (uint32_t)it & 1u);
+                    mbar_wait(smem_u32(&bars->q_full), qf++ & 1u);
                     load(slab + a.off[kOWoSa], 2, 16384);
                     load(slab + a.off[kOWqCa], 2, 16384);
                     for (int s = 0; s < segs.n_seg; ++s)
@@ -169,8 +177,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
             uint32_t sj = 0;
+            for (int si = 0; si < a.n_steps; ++si)
             for (int it = 0; it < L; ++it) {
-                const uint32_t base_it = (uint32_t)it * 26 + 2;        // ring-A items before this layer: 2 (Wk,Wv of layer 0) + 26 per layer
+                // ring-A items before this layer: 26 L per earlier step, 2 (Wk,Wv of layer 0), 26 per layer
+                const uint32_t base_it = (uint32_t)si * 26u * (uint32_t)L + (uint32_t)it * 26 + 2;
                 for (int o = 0; o < 3; ++o, ++sj) {
                     mbar_wait(smem_u32(&bars->s_free), sj & 1u);
                     tc_fence_after();
@@ -224,6 +234,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             const int passes = nvalid > e_rows ? 2 : 1;
             const uint32_t idmn = make_idesc_mn<kBf16>(kTileRows, kTileRows);
             const uint32_t idesc128 = make_idesc<kBf16>(kTileRows, 128);
+            for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
                 if (it >= 0) {
                     wait_a();                                                      // merged attention images written by the row threads
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 if (it + 1 < L) {
                     wait_a();
                     gemm_b(2, 128, kColS, false, nullptr);                         // q -> S[0:128]
-                    const uint32_t itA0 = (uint32_t)(it + 1) * 26;                 // Wk, Wv of layer it+1 in ring A
+                    const uint32_t itA0 = (uint32_t)si * 26u * (uint32_t)L + (uint32_t)(it + 1) * 26;   // Wk, Wv of layer it+1 in ring A
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t itA = itA0 + j;
                         const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
@@ -287,10 +298,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
         float mean, rstd;
         float v[32];
 
+        for (int si = 0; si < a.n_steps; ++si) {
+        const int tstep = a.step0 - si;                                  // timestep index of this step
+        const float* x_src = si == 0 ? a.x_in : a.x_out;
         // ---- step prologue (was step_begin_kernel): this tile's A_emb = SiLU(te + xp) image -> global (streamed back
         //      24 times by ring A), h0 = joint_embed(x) + sequence_embedding -> TMEM (stays there for the whole step).
-        //      Small operands are staged through ring A (idle until the image exists): with 221 KB of shared memory
-        //      the L1 is only a few KB, so repeated global reads of weights would all go to L2.
+        //      Small operands are staged through the k-image buffer (idle until the first reduction): with 221 KB of
+        //      shared memory the L1 is only a few KB, so repeated global reads of weights would all go to L2.
         {
             float* sWj = reinterpret_cast<float*>(xbuf);                  // [26][128]
             float* sbj = sWj + kP * kD;                                   // [128]
@@ -306,14 +320,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 for (int j = 0; j < 7; ++j) {
                     const int i = tx + j * kRowThreads;
                     tw[j] = i < kP * kD ? __ldg(a.WjT + i) : 0.f;
-                    tv[j] = (i < kTileRows * kP && i < xlim) ? __ldcg(a.x_in + row0g * kP + i) : 0.f;
+                    tv[j] = (i < kTileRows * kP && i < xlim) ? __ldcg(x_src + row0g * kP + i) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int i = tx + j * kRowThreads, cl = clip0 + (i >> 9);
-                    tt[j] = __ldcg(a.te + ((long)cl * a.T < (long)a.M ? (size_t)cl * a.te_stride : 0) + (i & 511));
+                    tt[j] = __ldcg(a.te + (size_t)tstep * a.te_step_stride + ((long)cl * a.T < (long)a.M ? (size_t)cl * a.te_stride : 0) + (i & 511));
                 }
                 const float tb = tx < kD ? __ldg(a.bj + tx) : 0.f;
+                const float4 psa = tx < 96 ? __ldg(reinterpret_cast<const float4*>(a.prm) + tx) : make_float4(0.f, 0.f, 0.f, 0.f);   // SA biases of layer 0
                 const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -328,6 +343,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 2; ++j) ste[tx + j * kRowThreads] = tt[j];
                 if (tx < kD) sbj[tx] = tb;
+                if (tx < 96) reinterpret_cast<float4*>(prm_sa)[tx] = psa;
             }
             named_bar_sync(5, kRowThreads);
             if (tx == 0) tl_mark(a, 128);
@@ -444,33 +460,24 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
             }
             if (it + 1 == L) {
                 // ---- step epilogue (was out_update_kernel): pred_x0 = h . Wout^T + b (fp32), sampler update of x.
-                //      Operands and results are staged through the (now idle) rings for coalesced global traffic.
-                float* part = reinterpret_cast<float*>(ringA);            // [4 cq][128 rows][28] partial dot products
-                float* sWo = part + 4 * kTileRows * 28;                   // [128][32]
+                //      Scratch: the operand buffers (partial dot products) and the parameter block (output head); the
+                //      rings are left alone -- the producers are already streaming the next step's first weights.
+                float* part = reinterpret_cast<float*>(awork_p);          // [4 cq][128 rows][28] (awork | xbuf, 64 KB)
+                float* sWo = prm;                                         // [128][32] over prm | prm_sa | xchg | red
                 float* sbo = sWo + kD * 32;                               // [32]
-                float* sxo = reinterpret_cast<float*>(ringB);             // [128][26] x rows before the update
-                float* snz = sxo + kTileRows * kP;                        // [128][26] noise
+                static_assert(4 * kTileRows * 28 * 4 <= 2 * kAworkBytes, "partials fit awork | xbuf");
+                static_assert(kD * 32 + 32 <= kPrmFloats + 384 + 1024 + kRedFloats, "output head fits the parameter block");
                 const int tx = threadIdx.x;
                 const long row0g = (long)blockIdx.x * kTileRows;
                 const int nel = (int)min((long)kTileRows * kP, (long)a.M * kP - row0g * kP);
                 const int smode = a.mode & 0xF;
-                {   // all global loads first, then the shared-memory stores
+                const float* nzp = a.noise != nullptr ? a.noise + (size_t)si * a.noise_stride : nullptr;
+                {
                     const float4* wo4 = reinterpret_cast<const float4*>(a.WoT);
                     const float4 w0 = __ldg(wo4 + tx), w1 = __ldg(wo4 + tx + kRowThreads);
-                    float to[7], tn[7];
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const int i = tx + j * kRowThreads;
-                        to[j] = (smode != 0 && i < nel) ? __ldcg(a.x_in + row0g * kP + i) : 0.f;
-                        tn[j] = (smode != 0 && a.noise != nullptr && i < nel) ? __ldcg(a.noise + row0g * kP + i) : 0.f;
-                    }
                     const float tb = tx < kP ? __ldg(a.bo + tx) : 0.f;
+                    named_bar_sync(5, kRowThreads);                        // every thread has read its last bias from prm
                     reinterpret_cast<float4*>(sWo)[tx] = w0, reinterpret_cast<float4*>(sWo)[tx + kRowThreads] = w1;
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const int i = tx + j * kRowThreads;
-                        if (i < kTileRows * kP) sxo[i] = to[j], snz[i] = tn[j];
-                    }
                     if (tx < 32) sbo[tx] = tb;
                 }
                 named_bar_sync(5, kRowThreads);
@@ -492,9 +499,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     for (int p4 = 0; p4 < 7; ++p4)
                         *reinterpret_cast<ulonglong2*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) = make_ulonglong2(acc[2 * p4], acc[2 * p4 + 1]);
                 }
-                named_bar_sync(5, kRowThreads);
-                {   // 128 rows x 26 outputs over 512 threads
-                    const float* cf = a.coef;
+                {   // 128 rows x 26 outputs over 512 threads; x and noise are in flight while the partials settle
+                    float to[7], tn[7];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) {
+                        const int i = tx + j * kRowThreads;
+                        to[j] = (smode != 0 && i < nel) ? __ldcg(x_src + row0g * kP + i) : 0.f;
+                        tn[j] = (smode != 0 && nzp != nullptr && i < nel) ? __ldcg(nzp + row0g * kP + i) : 0.f;
+                    }
+                    named_bar_sync(5, kRowThreads);
+                    const float* cf = smode != 0 ? a.coef + (size_t)tstep * 8 : nullptr;
+                    float* x0p = a.x0_out + (size_t)si * a.x0_stride;
 #pragma unroll
                     for (int j = 0; j < 7; ++j) {
                         const int i = tx + j * kRowThreads;
@@ -503,11 +518,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                             float x0 = sbo[p] + ((part[(0 * kTileRows + rr) * 28 + p] + part[(1 * kTileRows + rr) * 28 + p]) +
                                                  (part[(2 * kTileRows + rr) * 28 + p] + part[(3 * kTileRows + rr) * 28 + p]));
                             if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                            a.x0_out[row0g * kP + i] = x0;
-                            if (smode != 0) a.x_out[row0g * kP + i] = smode == 1 ? ddim_rule(sxo[i], x0, cf, snz[i]) : ddpm_rule(sxo[i], x0, cf, snz[i]);
+                            x0p[row0g * kP + i] = x0;
+                            if (smode != 0) {
+                                const float xn = smode == 1 ? ddim_rule(to[j], x0, cf, tn[j]) : ddpm_rule(to[j], x0, cf, tn[j]);
+                                a.x_out[row0g * kP + i] = xn;
+                                if (a.x_trace != nullptr) a.x_trace[(size_t)si * a.M * kP + row0g * kP + i] = xn;
+                            }
                         }
                     }
                 }
+                named_bar_sync(5, kRowThreads);                            // the scratch is the next step's staging area
                 break;
             }
 
@@ -579,6 +599,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 const int e = min(nvalid, (first_clip + 1) * a.T - row0);   // rows [0,e): first clip, [e,nvalid): next clip
                 const int n_seg = nvalid == 0 ? 0 : (nvalid > e ? 2 : 1);
                 const int tx = threadIdx.x;
+                const int seq = si * L + it + 1;                             // reductions completed so far in this launch
                 const bool in_tile = (int)r < nvalid;
                 const int myseg = (int)r >= e ? 1 : 0;
                 const int col = tx & 127, qr = tx >> 7;
@@ -699,7 +720,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     rows_wait(bars, 2, ph[2]);
                     if (tx == 0) tl_mark(a, 123);
                     if (ps < n_seg) {
-                        float* P = a.kv_part + ((size_t)blockIdx.x * 2 + ps) * kKvPartFloats;
+                        float* P = a.kv_part + (((size_t)(seq & 1) * gridDim.x + blockIdx.x) * 2 + ps) * kKvPartFloats;
                         if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
                             float pr[32];
                             tmem_ld32(trow + kColW + 32 * lq, pr);
@@ -750,7 +771,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     int cnt;
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cnt) : "l"(a.clip_cnt + clip) : "memory");
-                    } while (cnt < ntiles * (it + 2));
+                    } while (cnt < ntiles * (seq + 1));
                 }
                 named_bar_sync(5, kRowThreads);
                 if (tx == 0) tl_mark(a, 125);
@@ -759,7 +780,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                     const int clip = first_clip + sg;
                     const int t_first = (clip * a.T) / kTileRows, t_last = ((clip + 1) * a.T - 1) / kTileRows;
                     float M0 = -INFINITY, M1 = -INFINITY, a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, s0 = 0.f, s1 = 0.f;
-                    auto part_of = [&](int ti) { return a.kv_part + ((size_t)ti * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats; };
+                    auto part_of = [&](int ti) {
+                        return a.kv_part + (((size_t)(seq & 1) * gridDim.x + ti) * 2 + (clip - (ti * kTileRows) / a.T)) * kKvPartFloats;
+                    };
                     if (t_last - t_first < 4) {
                         // short clips (<= 4 tiles): issue every load first, one L2 round trip for the whole merge
                         float mi0[4], mi1[4], si0[4], si1[4];
@@ -817,6 +840,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                 if (tx == 0) tl_mark(a, 126);
             }
         }
+        }   // launch step si
     }
     if (threadIdx.x == 0) tl_mark(a, 2);
     tc_fence_before();
