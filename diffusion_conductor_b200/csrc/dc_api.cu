@@ -413,6 +413,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
     for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
     sa.timeline = h->timeline_on ? h->timeline : nullptr;
+    if (const char* dbg = getenv("DC_DBG")) sa.dbg = atoi(dbg);
     DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));      // arrival counters grow over the launch
     DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
     h->launches++;

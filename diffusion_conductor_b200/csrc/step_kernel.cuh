@@ -50,6 +50,7 @@ struct StepArgs {
     const long long* length;    // [B] or null
     uint32_t off[12];           // byte offsets of the packed matrices inside a layer slab (see dc_api.cu)
     unsigned long long* timeline;
+    int dbg;                    // bit 0: skip the FiLM projection MMAs (timing experiments only; results are wrong)
 };
 enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, kOWq, kOWk, kOWv };
 
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) step_kernel(const __grid_cons
                         mbar_wait(smem_u32(&bars->fullA[st]), ph);
                         tc_fence_after();
                         const uint32_t stage = smem_u32(ringA + st * kSA);
-                        umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, sgi > 0);
+                        if (!(a.dbg & 1)) umma_kblock(tmem_base + kColS, stage, stage + kStageABytes, idesc_s, sgi > 0);
                         umma_commit(smem_u32(&bars->emptyA[st]));
                     }
                     umma_commit(smem_u32(&bars->d_ready[0]));

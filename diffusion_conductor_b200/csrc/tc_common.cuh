@@ -66,9 +66,18 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// Blocking wait: the whole retry loop is two instructions (try_wait suspends the thread in hardware up to the
+// time hint and wakes it when the phase completes), so waiting warps leave the issue slots to the working ones.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 
 // ---------------------------------------------------------------- bulk async copy global -> smem

@@ -17,6 +17,8 @@ import ctypes as C
 import math
 from typing import Optional, Sequence
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -232,7 +234,8 @@ class MotionTransformer(nn.Module):
         per_chunk = (sms * 128) // T if T >= 128 else 0
         # measured (r01, B200): with more than ~2 SM-fulls of tiles the per-layer launch path (3+ full waves) is as
         # fast as running the persistent kernel chunk after chunk (C3: 75.7 ms vs 79.0 ms), so chunk only up to 2x
-        if tiles <= sms or tiles > 2 * sms or per_chunk < 1 or B <= per_chunk:
+        max_fulls = float(os.environ.get("DC_CHUNK_MAX", "2"))
+        if tiles <= sms or tiles > max_fulls * sms or per_chunk < 1 or B <= per_chunk:
             return base
         n_chunks = -(-B // per_chunk)
         while len(self._chunk_engines) < n_chunks - 1:

@@ -2,7 +2,8 @@
 
 ncu's CLI source page only prints SASS; this joins it, instruction by instruction, with `nvdisasm -g` line info of
 the same kernel in the in-tree library (so the library must be the build that was profiled).
-usage: python tools/ncu_lines.py gpurun_out/step_full.ncu-rep step_kernelILb1 [n_top]"""
+usage: python tools/ncu_lines.py gpurun_out/step_full.ncu-rep step_kernelILb1 [n_top] [exec]
+columns: share of stall samples, share of warp instructions executed, warp instructions, source line"""
 import collections
 import csv
 import glob
@@ -16,6 +17,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, fun = sys.argv[1], sys.argv[2]
 ntop = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+by_exec = len(sys.argv) > 4 and sys.argv[4] == "exec"      # rank by warp instructions executed instead of stall samples
 
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
@@ -54,9 +56,12 @@ for (loc, _), (_, s, e) in zip(lines, prof):
 tot = sum(by_line.values()) or 1
 src = {}
 print(f"{tot} samples over {len(prof)} instructions; top source lines:")
-for (f, n), s in by_line.most_common(ntop):
+tot_e = sum(exe_line.values()) or 1
+order = exe_line.most_common(ntop) if by_exec else by_line.most_common(ntop)
+for (f, n), _ in order:
+    s = by_line[(f, n)]
     if f not in src:
         cand = glob.glob(os.path.join(ROOT, "diffusion_conductor_b200", "csrc", f))
         src[f] = open(cand[0]).read().splitlines() if cand else []
     text = src[f][n - 1].strip()[:110] if 0 < n <= len(src[f]) else ""
-    print(f"{s / tot:6.1%} {exe_line[(f, n)]:>9} {f}:{n}  {text}")
+    print(f"{s / tot:6.1%} {exe_line[(f, n)] / tot_e:6.1%} {exe_line[(f, n)]:>9} {f}:{n}  {text}")
