@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/dc_b200.h"
-#include "step_kernel.cuh"
+#include "clip_kernel.cuh"
 
 using namespace dc;
 
@@ -83,6 +83,7 @@ struct dc_handle {
     int B = 0, T = 0, M = 0, tiles = 0;
     size_t cap_tokens = 0;
     int cap_B = 0;
+    size_t cap_clip_tiles = 0;
     float* xp = nullptr;
     uint8_t* zimg = nullptr;
     uint8_t* aemb = nullptr;
@@ -97,6 +98,9 @@ struct dc_handle {
     int* clip_done = nullptr;     // [B] merges completed in the current step (persistent kernel)
     bool fuse_kv = false;
     bool persist = false;         // whole step in one persistent kernel (tiles <= SMs, T >= 128)
+    bool clip_mode = false;       // persistent kernel variant: one thread-block cluster per clip, DSMEM exchange (any batch size)
+    int clip_nt = 1;              // tiles (= cluster size) per clip in clip mode
+    int clip_nt_checked = 0;      // last cluster size validated with cudaOccupancyMaxActiveClusters
     int num_sms = 0;
     unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
     bool timeline_on = false;
@@ -231,7 +235,7 @@ void free_workspace(dc_handle* h) {
     h->xp = nullptr, h->zimg = nullptr, h->aemb = nullptr, h->hbuf = nullptr, h->q_img = nullptr, h->kv = nullptr;
     h->bd_sa = nullptr, h->bd_ca = nullptr, h->length = nullptr, h->te_b = nullptr, h->xwork = nullptr, h->x0work = nullptr;
     h->in_proj = nullptr, h->in_out = nullptr;
-    h->cap_tokens = 0, h->cap_B = 0;
+    h->cap_tokens = 0, h->cap_B = 0, h->cap_clip_tiles = 0;
 }
 
 void drop_graph(dc_handle* h) {
@@ -243,14 +247,16 @@ void drop_graph(dc_handle* h) {
 int ensure_workspace(dc_handle* h, int B, int T) {
     const size_t M = (size_t)B * T;
     const size_t tiles = (((M + kTileRows - 1) / kTileRows) + 1) & ~size_t(1);     // even: CTA pairs may add a padding tile
-    if (M <= h->cap_tokens && B <= h->cap_B) return 0;
+    const size_t clip_tiles = (size_t)B * ((T + kTileRows - 1) / kTileRows);       // clip-aligned tiling of the cluster kernel
+    if (M <= h->cap_tokens && B <= h->cap_B && clip_tiles <= h->cap_clip_tiles) return 0;
     drop_graph(h);
     free_workspace(h);
     const size_t Mpad = tiles * kTileRows;
     const int L = h->cfg.num_layers;
     DC_CUDA(h, cudaMalloc((void**)&h->xp, Mpad * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->zimg, tiles * 8 * (size_t)kABlockBytes));
-    DC_CUDA(h, cudaMalloc((void**)&h->aemb, tiles * 8 * (size_t)kABlockBytes));
+    const size_t aemb_tiles = std::max(tiles, clip_tiles);
+    DC_CUDA(h, cudaMalloc((void**)&h->aemb, aemb_tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->hbuf, Mpad * kD * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->q_img, tiles * (size_t)kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->kv, Mpad * 256 * 4));
@@ -269,13 +275,14 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->in_out, M * kMusic * 4));
     // padded rows of the operand images must hold finite values
     DC_CUDA(h, cudaMemset(h->zimg, 0, tiles * 8 * (size_t)kABlockBytes));
-    DC_CUDA(h, cudaMemset(h->aemb, 0, tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMemset(h->aemb, 0, aemb_tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMemset(h->q_img, 0, tiles * (size_t)kAworkBytes));
     // off-diagonal head blocks of the attention images are never written: they must be zero
     DC_CUDA(h, cudaMemset(h->bd_sa, 0, (size_t)B * kAworkBytes));
     DC_CUDA(h, cudaMemset(h->bd_ca, 0, (size_t)B * L * kAworkBytes));
     h->cap_tokens = M;
     h->cap_B = B;
+    h->cap_clip_tiles = clip_tiles;
     return 0;
 }
 
@@ -288,6 +295,10 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
+    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     return 0;
 }
 
@@ -414,6 +425,16 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
     sa.timeline = h->timeline_on ? h->timeline : nullptr;
     if (const char* dbg = getenv("DC_DBG")) sa.dbg = atoi(dbg);
+    if (h->clip_mode) {
+        // one cluster of clip_nt CTAs per clip; no global exchange state
+        sa.nt = h->clip_nt;
+        sa.rows_per = (h->T + h->clip_nt - 1) / h->clip_nt;
+        DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, h->bf16 ? clip_kernel<true> : clip_kernel<false>, dim3((unsigned)(h->B * h->clip_nt)),
+                             dim3(kTileThreads), kClipSmemBytes, st, sa));
+        h->launches++;
+        DC_CUDA(h, cudaGetLastError());
+        return 0;
+    }
     DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));      // arrival counters grow over the launch
     DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
     h->launches++;
@@ -737,10 +758,34 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         // One persistent kernel per step when every tile's CTA can be resident at once (in-kernel per-clip
         // dependency) and a tile touches at most two clips.
         const char* pe = getenv("DC_PERSIST");
-        const bool persist = T >= kTileRows && h->tiles <= h->num_sms && !h->use_pair && !(pe && pe[0] == '0');
-        if (fuse != h->fuse_kv || persist != h->persist) drop_graph(h);
+        // Cluster-per-clip kernel: any batch size, T <= 16 tiles; clusters of more than 8 CTAs need the opt-in and a GPC
+        // with that many free SMs (checked with the occupancy query).  DC_CLUSTER=0 selects the older grid-resident kernel.
+        const char* ce = getenv("DC_CLUSTER");
+        const int nt = (T + kTileRows - 1) / kTileRows;
+        bool clip_mode = nt <= kMaxClipTiles && !h->use_pair && !(pe && pe[0] == '0') && !(ce && ce[0] == '0');
+        if (clip_mode && nt > 1 && nt != h->clip_nt_checked) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)nt), cfg.blockDim = dim3(kTileThreads), cfg.dynamicSmemBytes = kClipSmemBytes;
+            cudaLaunchAttribute at{};
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = (unsigned)nt, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+            cfg.attrs = &at, cfg.numAttrs = 1;
+            int nclusters = 0;
+            const cudaError_t qe = h->bf16 ? cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<true>, &cfg)
+                                           : cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<false>, &cfg);
+            if (qe != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                clip_mode = false;
+            } else {
+                h->clip_nt_checked = nt;
+            }
+        }
+        const bool persist = clip_mode || (T >= kTileRows && h->tiles <= h->num_sms && !h->use_pair && !(pe && pe[0] == '0'));
+        if (fuse != h->fuse_kv || persist != h->persist || clip_mode != h->clip_mode) drop_graph(h);
         h->fuse_kv = fuse;
         h->persist = persist;
+        h->clip_mode = clip_mode;
+        h->clip_nt = nt;
         DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)B * 4, st));
     }
     bool masked = false;

@@ -282,6 +282,33 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// ---------------------------------------------------------------- distributed shared memory (one cluster = one clip)
+// Writer: plain st.shared of the payload, CTA barrier, then ONE thread fences at cluster scope and arrives on the
+// peers' mbarriers.  Reader: one thread waits with acquire.cluster, CTA barrier, then everyone pulls with
+// ld.shared::cluster.  (Cluster-scope fences flush L1, so they are kept to one per exchange.)
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_dsmem_f32x2(uint32_t cluster_addr) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+    return v;
+}
+
 // The barriers the MMA issuer waits on are local to the leader CTA; the peer arrives on them with
 // release.cluster after fencing its own shared-memory writes for the async proxy.  Those writes are read by the
 // peer SM's own tensor-core datapath, so the ordinary CTA-scope probe is what is needed here (cluster-scope

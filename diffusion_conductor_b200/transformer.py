@@ -224,11 +224,14 @@ class MotionTransformer(nn.Module):
         return self._engine
 
     def engine_for(self, device: torch.device, B: int, T: int):
-        """Engine for a (B, T) batch.  The whole-step persistent kernel needs every 128-token tile of the batch on
+        """Engine for a (B, T) batch.  Clips of up to 2048 frames run on the cluster-per-clip kernel (one handle, any
+        batch).  Beyond that: the older grid-resident persistent kernel needs every 128-token tile of the batch on
         its own SM; clips are independent, so a larger batch is cut into equal chunks of clips that fit, each
         chunk with its own handle (workspace + captured graph) run back to back.  Short clips (T < 128) and single
         clips longer than the GPU use one handle and the per-layer launch path."""
         base = self.engine(device)
+        if T <= 16 * 128 and os.environ.get("DC_CLUSTER", "1") != "0" and os.environ.get("DC_PERSIST", "1") != "0":
+            return base         # cluster-per-clip kernel: clips are scheduled by the hardware, any batch size in one launch
         sms = torch.cuda.get_device_properties(base.device).multi_processor_count
         tiles = -(-B * T // 128)
         per_chunk = (sms * 128) // T if T >= 128 else 0
