@@ -248,7 +248,7 @@ def main():
     e2e_value = motion_seconds / (float(t.item()) / args.steps)
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (the tcgen05 layer kernel), timed live with CUDA events
+    # ---- roofline of the dominant kernel, timed live with CUDA events
     pk = peaks()
     chunked = hasattr(plan, "bounds")
     Bp = (plan.bounds[0][1] - plan.bounds[0][0]) if chunked else B      # the profile runs on one chunk of clips
@@ -262,20 +262,42 @@ def main():
             for k in ms:
                 agg[k] = agg.get(k, 0.0) + ms[k] / reps
                 cnt[k] = c[k]
-    layer_ms = agg["layer"] / max(cnt["layer"], 1)
-    flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * Bp * T / max(cnt["layer"], 1)
-    achieved = flop_per_launch / (layer_ms * 1e-3) / 1e12
     step_ms = sum(agg.values())
-    traffic = None        # dram__bytes_read + write per launch of the layer kernel, from the committed ncu --set full capture
-    tp = os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
-    kname = "dc::step_kernel (persistent: all 8 layers of a denoise step)" if cnt["layer"] == 1 else "dc::layer_kernel"
+    persistent = cnt["layer"] == 1
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    tj = json.load(open(tp)) if os.path.exists(tp) else {}
+    if persistent:
+        # the whole sampling loop is ONE launch of the cluster-per-clip kernel: time that launch with CUDA events on the
+        # launching (= torch current) stream; algorithmic FLOPs per launch = B * T * S * 8,500,224
+        ms = []
+        for _ in range(5):
+            xl = noise_d[:Bp].clone()
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.sample_loop(_lib.DC_SAMPLER_DDIM, xl)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        launch_ms = sum(ms) / len(ms)
+        flop_per_launch = float(Bp) * T * S * FLOP_PER_TOKEN_STEP
+        kname = "dc::clip_kernel (persistent; one thread-block cluster per clip; the whole sampling loop is one launch)"
+        launches_per_loop = 1
+        share = min(1.0, launch_ms / ms_per_step) if Bp == B else None
+    else:
+        launch_ms = agg["layer"] / max(cnt["layer"], 1)
+        flop_per_launch = 2.0 * LAYER_MAC_PER_TOKEN * 8 * Bp * T / max(cnt["layer"], 1)
+        kname = "dc::layer_kernel"
+        launches_per_loop = cnt["layer"] * S
+        share = round(agg["layer"] / step_ms, 3)
+    achieved = flop_per_launch / (launch_ms * 1e-3) / 1e12
+    traffic = tj.get(kname.split(" ")[0], {}).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": kname, "achieved": round(achieved, 2), "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops"], 4), "traffic": traffic,
-                "peak_source": pk["source"], "launch_ms": round(layer_ms, 4), "launches_per_denoise_step": cnt["layer"],
-                "share_of_denoise_step": round(agg["layer"] / step_ms, 3),
-                "denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()}, "profiled_clips": Bp,
+                "peak_source": pk["source"], "frac_of_sustained_peak": round(achieved / pk["bf16_tflops_sustained"], 4) if pk.get("bf16_tflops_sustained") else None,
+                "launch_ms": round(launch_ms, 4), "flop_per_launch": flop_per_launch,
+                "launches_per_loop": launches_per_loop, "share_of_loop": share if share is None else round(share, 3),
+                "single_denoise_step_ms_by_kernel": {k: round(v, 4) for k, v in agg.items()}, "profiled_clips": Bp,
                 "clip_chunks": len(plan.bounds) if chunked else 1,
                 "whole_loop_frac_of_peak": round(B * T * S * FLOP_PER_TOKEN_STEP / (ms_per_step / 1e3) / 1e12 / pk["bf16_tflops"], 4)}
 

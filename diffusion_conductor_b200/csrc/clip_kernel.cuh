@@ -11,16 +11,67 @@
 // mbarriers (release.cluster), and every CTA pulls the nt partials with ld.shared::cluster and merges them (online
 // softmax rescaling) straight into its block-diagonal B-operand image.  No global memory, no atomics, no polling.
 #pragma once
-#include "step_kernel.cuh"
+#include "tile_kernels.cuh"
 
 namespace dc {
 
+constexpr int kPRingAStages = 2;        // persistent kernel: 2 x 48 KB (the FiLM projection is shared-memory-bandwidth bound)
+
+struct StepArgs {
+    int L, M, T;
+    const uint8_t* wbuf;        // packed weights [L][1 MiB]
+    const uint8_t* aemb;        // A_emb image [B * nt tiles][8][16 KB]
+    const float* prm;           // [L][kPrmFloats]
+    // step prologue / epilogue fused into the kernel (reference transformer.py:482,488-490,496; gaussian_diffusion.py:812-830)
+    // One launch runs n_steps consecutive denoise steps (timestep indices step0, step0 - 1, ...): a tile's x rows are
+    // private to its CTA, so the only cross-CTA traffic of the whole sampling loop is the per-clip partial exchange.
+    int n_steps, step0;
+    const float* x_in;          // [M][26] current sample x_t
+    float* x_out;               // [M][26] updated sample (may alias x_in; null when mode == 0; must be set when n_steps > 1)
+    float* x0_out;              // [M][26] pred_xstart (model output) of launch step i at x0_out + i * x0_stride
+    size_t x0_stride;
+    float* x_trace;             // optional: x after launch step i -> x_trace + i * M * 26
+    const float* noise;         // [M][26] (+ i * noise_stride for launch step i) or null
+    size_t noise_stride;
+    const float* xp;            // [M][512] linear(xf_proj)
+    const float* te;            // time embedding row(s): te + timestep * te_step_stride + b * te_stride
+    int te_stride, te_step_stride;
+    const float* coef;          // [S][8] update coefficients, row = timestep index; null when mode == 0
+    int mode;                   // 0: model output only, 1: DDIM, 2: DDPM, | 0x10 clamp
+    const float* WjT;           // [26][128] joint_embed weight, transposed
+    const float* bj;            // [128]
+    const float* pos;           // [num_frames][128] sequence_embedding
+    const float* WoT;           // [128][32] output head, transposed + padded
+    const float* bo;            // [32]
+    uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
+    const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
+    size_t bd_ca_stride;
+    const long long* length;    // [B] or null
+    uint32_t off[12];           // byte offsets of the packed matrices inside a layer slab (see dc_api.cu)
+    unsigned long long* timeline;
+    int dbg;                    // bit 0: skip the FiLM projection MMAs (timing experiments only; results are wrong)
+    int nt, rows_per;           // tiles (= cluster size) per clip, frames per tile
+};
+enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, kOWq, kOWk, kOWv };
+
+__device__ __forceinline__ void tl_mark(const StepArgs& a, unsigned long long id) {
+    if (a.timeline != nullptr && blockIdx.x == 0) {
+        const unsigned long long slot = atomicAdd(a.timeline, 1ull);
+        if (slot < 2040) {
+            a.timeline[1 + 2 * slot] = (unsigned long long)clock64();
+            a.timeline[2 + 2 * slot] = id;
+        }
+    }
+}
+
 constexpr int kClipRedFloats = 1024 + 128 + 128 + 8;
 constexpr int kMaxClipTiles = 16;       // cluster size limit (non-portable); T <= 16 * 128
+constexpr int kDirectMergeTiles = 4;    // up to this cluster size every CTA pulls every partial; beyond: reduce-scatter + all-gather
 
 struct ClipBarriers : LayerBarriers {
     uint64_t part_ready[2];             // peers -> this CTA: "my partial of reduction seq is in my shared memory" (count nt - 1)
     uint64_t pull_done[2];              // peers -> this CTA: "I have finished reading your partial" (count nt - 1)
+    uint64_t slice_ready[2];            // large clusters: "my merged slice of reduction seq is ready" (count nt - 1)
 };
 
 template <bool kBf16>
@@ -59,6 +110,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->part_ready[i]), (uint32_t)max(nt - 1, 1));
             mbar_init(smem_u32(&bars->pull_done[i]), (uint32_t)max(nt - 1, 1));
+            mbar_init(smem_u32(&bars->slice_ready[i]), (uint32_t)max(nt - 1, 1));
         }
         mbar_fence_init();
     }
@@ -644,8 +696,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                                    : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
                     mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
                 }
-                // ---- meanwhile: clear the image buffer (the merge writes only the diagonal blocks) and fetch the next
-                //      layer's parameters; all loads in flight before the first store (one L2 round trip)
+                named_bar_sync(5, kRowThreads);                            // partial complete
+                if (tx == 0) tl_mark(a, 124);
+                // ---- publish to the peers: release at cluster scope, one remote arrive per peer
+                if (nt > 1 && tx < nt && tx != rank) {
+                    fence_acq_rel_cluster();
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
+                }
+                // ---- while the peers' partials are in flight: clear the image buffer (the merge writes only the diagonal
+                //      blocks) and fetch the next layer's parameters; all loads issued before the first store
                 {
                     const float4* pn4 = reinterpret_cast<const float4*>(a.prm + (size_t)(it + 1) * kPrmFloats);
                     static_assert(kPrmFloats % 4 == 0 && kPrmFloats / 4 <= 2 * kRowThreads, "parameter block layout");
@@ -658,21 +717,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     if (tx + kRowThreads < kPrmFloats / 4) reinterpret_cast<float4*>(prm)[tx + kRowThreads] = p1;
                     if (it + 2 < L && tx < 96) reinterpret_cast<float4*>(prm_sa)[tx] = p2;
                 }
-                named_bar_sync(5, kRowThreads);                            // partial complete, buffer cleared
-                if (tx == 0) tl_mark(a, 124);
-                // ---- publish to the peers: release at cluster scope, one remote arrive per peer
-                if (nt > 1) {
-                    if (tx < nt && tx != rank) {
-                        fence_acq_rel_cluster();
-                        mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
-                    }
-                    if (tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
-                    named_bar_sync(5, kRowThreads);
-                }
+                if (nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
+                named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared
                 if (tx == 0) tl_mark(a, 125);
                 // ---- merge the nt partials (online-softmax rescaling, four tiles per round trip) into the block-diagonal
-                //      B-operand image.  Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
-                {
+                //      B-operand image.
+                if (nt <= kDirectMergeTiles) {
+                    // small clusters: every CTA pulls every partial.  Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
                     const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
                     const uint32_t pbase = smem_u32(mypart);
                     const uint32_t o_m = (uint32_t)(16 * hh + d0) * 4, o_s = o_m + 512;
@@ -714,6 +765,59 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                             const int nj = 16 * hh + l0 + ll;
                             *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
                         }
+                    }
+                } else {
+                    // large clusters: reduce-scatter + all-gather (the shared-memory port of an SM serves ~20 B/clk to its
+                    // peers, so all-to-all pulls of 9 KB partials do not scale).  CTA `rank` merges key features
+                    // [rank fs, rank fs + fs) from all partials into a 16-bit slice; then everyone gathers the nt slices.
+                    const int fs = (kD + nt - 1) / nt;
+                    uint16_t* myslice = reinterpret_cast<uint16_t*>(ringB + 12288);      // [fs][16], behind the partial
+                    {
+                        const int dl = tx >> 4, l = tx & 15, d = rank * fs + dl;
+                        if (dl < fs && d < kD) {
+                            const uint32_t pbase = smem_u32(mypart);
+                            const uint32_t o_m = (uint32_t)d * 4, o_s = o_m + 512, o_p = (uint32_t)(256 + (d >> 4) * 256 + (d & 15) * 16 + l) * 4;
+                            float Mx = -INFINITY, ss = 0.f, acc = 0.f;
+                            for (int j0 = 0; j0 < nt; j0 += 4) {
+                                float mi[4], sj[4], pj[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const bool on = j0 + j < nt;
+                                    const uint32_t pa = mapa_u32(pbase, (uint32_t)(on ? j0 + j : rank));
+                                    mi[j] = ld_dsmem_f32(pa + o_m), sj[j] = ld_dsmem_f32(pa + o_s), pj[j] = ld_dsmem_f32(pa + o_p);
+                                    if (!on) mi[j] = -INFINITY;
+                                }
+                                float nm = Mx;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) nm = fmaxf(nm, mi[j]);
+                                const float cs = __expf(Mx - nm);
+                                ss *= cs, acc *= cs, Mx = nm;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float w = __expf(mi[j] - Mx);
+                                    ss = fmaf(sj[j], w, ss), acc = fmaf(pj[j], w, acc);
+                                }
+                            }
+                            myslice[dl * 16 + l] = pack1<kBf16>(acc / ss);
+                        }
+                    }
+                    named_bar_sync(5, kRowThreads);
+                    if (tx < nt && tx != rank) {
+                        fence_acq_rel_cluster();
+                        mbar_arrive_cluster(mapa_u32(smem_u32(&bars->slice_ready[seq & 1u]), (uint32_t)tx));
+                    }
+                    if (tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->slice_ready[seq & 1u]), (seq >> 1) & 1u);
+                    named_bar_sync(5, kRowThreads);
+                    {
+                        const int d = tx >> 2, l4 = (tx & 3) * 4, j = d / fs, dl = d - j * fs;
+                        const uint32_t src = mapa_u32(smem_u32(myslice), (uint32_t)j) + (uint32_t)(dl * 16 + l4) * 2;
+                        uint32_t w0, w1;
+                        asm volatile("ld.shared::cluster.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src) : "memory");
+                        const uint16_t vals[4] = {(uint16_t)(w0 & 0xFFFFu), (uint16_t)(w0 >> 16), (uint16_t)(w1 & 0xFFFFu), (uint16_t)(w1 >> 16)};
+                        uint8_t* base = xbuf + (size_t)(d >> 6) * kABlockBytes + (d & 7) * 2;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            *reinterpret_cast<uint16_t*>(base + sw128_offset(16 * (d >> 4) + l4 + i, (d & 63) >> 3)) = vals[i];
                     }
                 }
                 if (nt > 1) {                                              // every pull of this CTA has completed: the peers may reuse ring B

@@ -93,13 +93,11 @@ struct dc_handle {
     uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
     uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
     int mask_invert = 0;
-    float* kv_part = nullptr;     // [2][tiles][2][kKvPartFloats] partial time-axis reductions (per-layer path uses the first half)
+    float* kv_part = nullptr;     // [tiles][2][kKvPartFloats] partial time-axis reductions (per-layer path)
     int* clip_cnt = nullptr;      // [B]
-    int* clip_done = nullptr;     // [B] merges completed in the current step (persistent kernel)
     bool fuse_kv = false;
-    bool persist = false;         // whole step in one persistent kernel (tiles <= SMs, T >= 128)
-    bool clip_mode = false;       // persistent kernel variant: one thread-block cluster per clip, DSMEM exchange (any batch size)
-    int clip_nt = 1;              // tiles (= cluster size) per clip in clip mode
+    bool persist = false;         // persistent sampling-loop kernel: one thread-block cluster per clip (T <= 16 tiles, any batch)
+    int clip_nt = 1;              // tiles (= cluster size) per clip
     int clip_nt_checked = 0;      // last cluster size validated with cudaOccupancyMaxActiveClusters
     int num_sms = 0;
     unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
@@ -226,8 +224,7 @@ DOp make_dop(uint32_t w_off, uint32_t w_bytes, int kb, int n, uint32_t d_col, bo
 void free_workspace(dc_handle* h) {
     if (h->kv_part) cudaFree(h->kv_part);
     if (h->clip_cnt) cudaFree(h->clip_cnt);
-    if (h->clip_done) cudaFree(h->clip_done);
-    h->kv_part = nullptr, h->clip_cnt = nullptr, h->clip_done = nullptr;
+    h->kv_part = nullptr, h->clip_cnt = nullptr;
     void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q_img, h->kv, h->bd_sa, h->bd_ca, h->length,
                     h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
     for (void* p : ptrs)
@@ -263,11 +260,9 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->bd_sa, (size_t)B * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->bd_ca, (size_t)B * L * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
-    DC_CUDA(h, cudaMalloc((void**)&h->kv_part, 2 * tiles * 2 * (size_t)kKvPartFloats * 4));   // two parities (persistent kernel)
+    DC_CUDA(h, cudaMalloc((void**)&h->kv_part, tiles * 2 * (size_t)kKvPartFloats * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->clip_cnt, (size_t)B * 4));
     DC_CUDA(h, cudaMemset(h->clip_cnt, 0, (size_t)B * 4));
-    DC_CUDA(h, cudaMalloc((void**)&h->clip_done, (size_t)B * 4));
-    DC_CUDA(h, cudaMemset(h->clip_done, 0, (size_t)B * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->te_b, (size_t)B * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->xwork, Mpad * kP * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->x0work, Mpad * kP * 4));
@@ -293,8 +288,6 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
@@ -413,7 +406,6 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     sa.n_steps = n_steps, sa.step0 = step0;
     sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm;
     sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
-    sa.bd_sa_out = h->bd_sa, sa.kv_part = h->kv_part, sa.clip_cnt = h->clip_cnt, sa.clip_done = h->clip_done;
     sa.length = h->has_length ? h->length : nullptr;
     sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.x0_stride = x0_stride, sa.x_trace = x_trace;
     sa.noise = noise, sa.noise_stride = noise_stride, sa.xp = h->xp;
@@ -425,18 +417,11 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
     sa.timeline = h->timeline_on ? h->timeline : nullptr;
     if (const char* dbg = getenv("DC_DBG")) sa.dbg = atoi(dbg);
-    if (h->clip_mode) {
-        // one cluster of clip_nt CTAs per clip; no global exchange state
-        sa.nt = h->clip_nt;
-        sa.rows_per = (h->T + h->clip_nt - 1) / h->clip_nt;
-        DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, h->bf16 ? clip_kernel<true> : clip_kernel<false>, dim3((unsigned)(h->B * h->clip_nt)),
-                             dim3(kTileThreads), kClipSmemBytes, st, sa));
-        h->launches++;
-        DC_CUDA(h, cudaGetLastError());
-        return 0;
-    }
-    DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)h->B * 4, st));      // arrival counters grow over the launch
-    DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? step_kernel<true> : step_kernel<false>, dim3(h->tiles), dim3(kTileThreads), kStepSmemBytes, st, sa));
+    // one cluster of clip_nt CTAs per clip; the kernel keeps no global exchange state
+    sa.nt = h->clip_nt;
+    sa.rows_per = (h->T + h->clip_nt - 1) / h->clip_nt;
+    DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, h->bf16 ? clip_kernel<true> : clip_kernel<false>, dim3((unsigned)(h->B * h->clip_nt)),
+                         dim3(kTileThreads), kClipSmemBytes, st, sa));
     h->launches++;
     DC_CUDA(h, cudaGetLastError());
     return 0;
@@ -755,15 +740,12 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         // T = 1800 -> 1.34x faster loop; T = 180 -> 7 % slower than the stand-alone kv_reduce kernel).
         const char* nf = getenv("DC_FUSE_KV");      // "0" / "1" force the choice
         const bool fuse = T >= kTileRows && (nf ? nf[0] == '1' : T >= 4 * kTileRows);
-        // One persistent kernel per step when every tile's CTA can be resident at once (in-kernel per-clip
-        // dependency) and a tile touches at most two clips.
+        // Cluster-per-clip persistent kernel: any batch size, T <= 16 tiles; clusters of more than 8 CTAs need the opt-in
+        // and a GPC with that many free SMs (checked with the occupancy query).  DC_PERSIST=0 forces the per-layer path.
         const char* pe = getenv("DC_PERSIST");
-        // Cluster-per-clip kernel: any batch size, T <= 16 tiles; clusters of more than 8 CTAs need the opt-in and a GPC
-        // with that many free SMs (checked with the occupancy query).  DC_CLUSTER=0 selects the older grid-resident kernel.
-        const char* ce = getenv("DC_CLUSTER");
         const int nt = (T + kTileRows - 1) / kTileRows;
-        bool clip_mode = nt <= kMaxClipTiles && !h->use_pair && !(pe && pe[0] == '0') && !(ce && ce[0] == '0');
-        if (clip_mode && nt > 1 && nt != h->clip_nt_checked) {
+        bool persist = nt <= kMaxClipTiles && !h->use_pair && !(pe && pe[0] == '0');
+        if (persist && nt > 1 && nt != h->clip_nt_checked) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)nt), cfg.blockDim = dim3(kTileThreads), cfg.dynamicSmemBytes = kClipSmemBytes;
             cudaLaunchAttribute at{};
@@ -775,16 +757,14 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
                                            : cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<false>, &cfg);
             if (qe != cudaSuccess || nclusters < 1) {
                 cudaGetLastError();
-                clip_mode = false;
+                persist = false;
             } else {
                 h->clip_nt_checked = nt;
             }
         }
-        const bool persist = clip_mode || (T >= kTileRows && h->tiles <= h->num_sms && !h->use_pair && !(pe && pe[0] == '0'));
-        if (fuse != h->fuse_kv || persist != h->persist || clip_mode != h->clip_mode) drop_graph(h);
+        if (fuse != h->fuse_kv || persist != h->persist) drop_graph(h);
         h->fuse_kv = fuse;
         h->persist = persist;
-        h->clip_mode = clip_mode;
         h->clip_nt = nt;
         DC_CUDA(h, cudaMemsetAsync(h->clip_cnt, 0, (size_t)B * 4, st));
     }

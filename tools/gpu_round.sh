@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# One GPU visit: parity tests, smoke, bench (both arms), ncu launch list + full capture of the layer kernel.
+# One GPU visit: parity tests, smoke, bench (both arms), ncu launch list + full capture of the persistent clip kernel.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -25
@@ -10,14 +10,12 @@ echo "=== bench C3"; timeout 900 python bench.py --steps 3 --warmup 3 --workload
 echo "=== bench reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_ref.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "=== ncu launches"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 40 --csv --log-file gpurun_out/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
 tail -3 gpurun_out/ncu_launch_run.log
 echo "=== ncu full (layer kernel)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(step_kernel|layer_kernel)" -s 3 -c 1 -f -o gpurun_out/layer_full \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(clip_kernel|layer_kernel)" -s 3 -c 1 -f -o gpurun_out/clip_full \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 tail -3 gpurun_out/ncu_full_run.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:kv_reduce -s 30 -c 1 -f -o gpurun_out/kvreduce_full \
-   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run2.log 2>&1
 ls -la gpurun_out | head -30
 fi
