@@ -21,7 +21,8 @@ struct StepArgs {
     int L, M, T;
     const uint8_t* wbuf;        // packed weights [L][1 MiB]
     const uint8_t* aemb;        // A_emb image [B * nt tiles][8][16 KB]
-    const float* prm;           // [L][kPrmFloats]
+    const float* prm;           // [L][kPrmFloats] (clip variant: FFN-up bias and deferred output biases folded, see dc_api.cu)
+    const uint8_t* wfuse;       // [L][16 KB] W1 . Wo_ca as a [64 x 128] K-major operand image (FFN-up fused across the residual add)
     // step prologue / epilogue fused into the kernel (reference transformer.py:482,488-490,496; gaussian_diffusion.py:812-830)
     // One launch runs n_steps consecutive denoise steps (timestep indices step0, step0 - 1, ...): a tile's x rows are
     // private to its CTA, so the only cross-CTA traffic of the whole sampling loop is the per-clip partial exchange.
@@ -54,17 +55,29 @@ struct StepArgs {
 };
 enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, kOWq, kOWk, kOWv };
 
-__device__ __forceinline__ void tl_mark(const StepArgs& a, unsigned long long id) {
-    if (a.timeline != nullptr && blockIdx.x == 0) {
-        const unsigned long long slot = atomicAdd(a.timeline, 1ull);
-        if (slot < 2040) {
-            a.timeline[1 + 2 * slot] = (unsigned long long)clock64();
-            a.timeline[2 + 2 * slot] = id;
+// Debug timeline of CTA 0 (dc_debug_timeline): every marking thread (row thread 0, the two MMA issuers) appends
+// (clock64, id) pairs to its OWN lane of the buffer with plain stores -- no atomics, so a mark costs a few cycles.
+// Layout: [3 lanes][1 + 2 * kTlEvents] u64, word 0 of a lane = number of events.
+constexpr int kTlEvents = 680;
+struct Timeline {
+    unsigned long long* p;
+    uint32_t n;
+    __device__ __forceinline__ Timeline(const StepArgs& a, int lane_id)
+        : p(a.timeline != nullptr && blockIdx.x == 0 ? a.timeline + (size_t)lane_id * (1 + 2 * kTlEvents) : nullptr), n(0) {}
+    __device__ __forceinline__ void mark(unsigned long long id) {
+        if (p != nullptr && n < (uint32_t)kTlEvents) {
+            p[1 + 2 * n] = (unsigned long long)clock64();
+            p[2 + 2 * n] = id;
+            ++n;
         }
     }
-}
+    __device__ __forceinline__ void finish() {
+        if (p != nullptr) p[0] = n;
+    }
+};
 
-constexpr int kClipRedFloats = 1024 + 128 + 128 + 8;
+constexpr int kClipRedFloats = 128 + 128 + 8;   // column maxima, column sums (the 4 KB scan partials alias the LayerNorm exchange buffer)
+constexpr uint32_t kRingAItems = 26;    // ring-A items per layer: 3 x 8 FiLM stages + Wk + Wv
 constexpr int kMaxClipTiles = 16;       // cluster size limit (non-portable); T <= 16 * 128
 constexpr int kDirectMergeTiles = 4;    // up to this cluster size every CTA pulls every partial; beyond: reduce-scatter + all-gather
 
@@ -72,6 +85,7 @@ struct ClipBarriers : LayerBarriers {
     uint64_t part_ready[2];             // peers -> this CTA: "my partial of reduction seq is in my shared memory" (count nt - 1)
     uint64_t pull_done[2];              // peers -> this CTA: "I have finished reading your partial" (count nt - 1)
     uint64_t slice_ready[2];            // large clusters: "my merged slice of reduction seq is ready" (count nt - 1)
+    uint64_t w1c_full;                  // the (W1 Wo_ca) image of the current layer has landed
 };
 
 template <bool kBf16>
@@ -83,9 +97,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
     uint8_t* ringB = ringA + kNA * kSA;                               // also the V image, then this tile's partial (pulled by the peers)
     uint8_t* awork_p = ringB + kNB * kSB;
     uint8_t* xbuf = awork_p + kAworkBytes;                            // k / E image of the reduction, then the merged attention image
-    float* prm = reinterpret_cast<float*>(xbuf + kAworkBytes);        // [kPrmFloats] layer `it`
+    uint8_t* w1c = xbuf + kAworkBytes;                                // [16 KB] (W1 Wo_ca) operand image of the current layer (1024-B aligned)
+    float* prm = reinterpret_cast<float*>(w1c + 16384);               // [kPrmFloats] layer `it`
     float* prm_sa = prm + kPrmFloats;                                 // [384] SA biases of layer it + 1
-    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);           // [4][128]
+    float2* xchg = reinterpret_cast<float2*>(prm_sa + 384);           // [4][128] LayerNorm exchange; column-scan partials during the reduction
     float* red = reinterpret_cast<float*>(xchg + 512);                // kClipRedFloats
     ClipBarriers* bars = reinterpret_cast<ClipBarriers*>(red + kClipRedFloats);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,6 +122,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         mbar_init(smem_u32(&bars->q_full), 1);
         mbar_init(smem_u32(&bars->aemb_ready), kRowWarps);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
+        mbar_init(smem_u32(&bars->w1c_full), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->part_ready[i]), (uint32_t)max(nt - 1, 1));
             mbar_init(smem_u32(&bars->pull_done[i]), (uint32_t)max(nt - 1, 1));
@@ -124,10 +140,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
     cluster_sync_all();                                               // every peer's barriers exist before anyone arrives remotely
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();
-    if (threadIdx.x == 0) tl_mark(a, 1);
 
     if (warp == kProducerWarp) {
         // ---------------- ring A: per layer 3 FiLM projections (8 stages each), then Wk, Wv of the next layer
+        //                  (kRingAItems = 26 items per layer; item order is what the two consumers below assume)
         if (lane == 0) {
             const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
             uint32_t it_ = 0;
@@ -150,8 +166,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     }
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
                     const uint32_t so[3] = {a.off[kOWeSa], a.off[kOWeCa], a.off[kOWeFf]};
-                    for (int o = 0; o < 3; ++o)
+                    for (int o = 0; o < 3; ++o) {
                         for (int s = 0; s < kSopStages; ++s) stage_in(a_img + (size_t)s * kStageABytes, slab + so[o] + (size_t)s * kStageWBytes, kStageWBytes);
+                    }
                 }
                 if (it + 1 < L) {
                     const uint8_t* slab = a.wbuf + ((size_t)(it + 1) << 20);
@@ -185,11 +202,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         const uint32_t seq = (uint32_t)(si * L + it);
                         mbar_wait(smem_u32(&bars->pull_done[seq & 1u]), (seq >> 1) & 1u);
                     }
+                    {   // (W1 Wo_ca) of this layer -> its own buffer (the previous layer's MMAs on it completed before q_full fired)
+                        const uint32_t full = smem_u32(&bars->w1c_full);
+                        mbar_arrive_expect_tx(full, 16384);
+                        bulk_g2s(smem_u32(w1c), a.wfuse + (size_t)it * 16384, 16384, full);
+                    }
                     load(slab + a.off[kOWoSa], 2, 16384);
                     load(slab + a.off[kOWqCa], 2, 16384);
                     load(a.bd_ca + (size_t)clip * a.bd_ca_stride + (size_t)it * kAworkBytes, 2, 16384);
                     load(slab + a.off[kOWoCa], 2, 16384);
-                    load(slab + a.off[kOW1], 2, 8192);
+                    load(slab + a.off[kOW1], 1, 16384);                            // both 8 KB k-blocks of W1 in one stage
                     load(slab + a.off[kOW2], 1, 16384);
                     load(slab + a.off[kOWoFf], 2, 16384);
                 }
@@ -199,12 +221,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
     } else if (warp == kRelayWarp) {
         // ---------------- issuer of the FiLM projections S = A_emb . We (ring A), gated only by s_free
         if (lane == 0) {
+            Timeline tl(a, 2);
             const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
             uint32_t sj = 0;
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = 0; it < L; ++it) {
                 // ring-A items before this layer: 26 L per earlier step, 2 (Wk,Wv of layer 0), 26 per layer
-                const uint32_t base_it = (uint32_t)si * 26u * (uint32_t)L + (uint32_t)it * 26 + 2;
+                const uint32_t base_it = (uint32_t)si * kRingAItems * (uint32_t)L + (uint32_t)it * kRingAItems + 2;
                 for (int o = 0; o < 3; ++o, ++sj) {
                     mbar_wait(smem_u32(&bars->s_free), sj & 1u);
                     tc_fence_after();
@@ -218,28 +241,32 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         umma_commit(smem_u32(&bars->emptyA[st]));
                     }
                     umma_commit(smem_u32(&bars->d_ready[0]));
-                    tl_mark(a, 310 + o);
+                    tl.mark(310 + o);
                 }
             }
+            tl.finish();
         }
     } else if (warp == kMmaWarp) {
         // ---------------- issuer of the dependent GEMMs, strictly in chain order with blocking waits
         if (lane == 0) {
+            Timeline tl(a, 1);
             const uint32_t awork = smem_u32(awork_p);
             uint32_t itB = 0, a_phase = 0;
             auto wait_a = [&]() {
                 mbar_wait(smem_u32(&bars->a_ready), a_phase & 1u);
                 ++a_phase;
                 tc_fence_after();
+                tl.mark(400);
             };
             // B operand through ring B, one k-block per stage
-            auto gemm_b = [&](int kb, int n, uint32_t d_col, bool acc) {
+            auto gemm_b = [&](int kb, int n, uint32_t d_col, bool acc, uint32_t a_base) {
                 const uint32_t idesc = make_idesc<kBf16>(kTileRows, n);
                 for (int k = 0; k < kb; ++k, ++itB) {
                     const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
                     mbar_wait(smem_u32(&bars->fullB[st]), ph);
                     tc_fence_after();
-                    umma_kblock(tmem_base + d_col, awork + k * kABlockBytes, smem_u32(ringB + st * kSB), idesc, acc || k > 0);
+                    tl.mark(401);
+                    umma_kblock(tmem_base + d_col, a_base + k * kABlockBytes, smem_u32(ringB + st * kSB), idesc, acc || k > 0);
                     umma_commit(smem_u32(&bars->emptyB[st]));
                 }
             };
@@ -252,20 +279,35 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     wait_a();                                                      // merged attention image written by the row threads
                     for (int k = 0; k < 2; ++k)                                    // y = q . blockdiag(A_sa)
                         umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, smem_u32(xbuf) + k * kABlockBytes, idesc128, k > 0);
-                    done(2), tl_mark(a, 200);
+                    done(2), tl.mark(200);
                     umma_commit(smem_u32(&bars->q_full));
-                    wait_a(), gemm_b(2, 128, kColH, true), done(1), tl_mark(a, 201);   // h += . Wo_sa
-                    wait_a(), gemm_b(2, 128, kColW, false), done(2), tl_mark(a, 202);  // q_ca
-                    wait_a(), gemm_b(2, 128, kColW, false), done(2), tl_mark(a, 203);  // y = softmax(q) . blockdiag(A_ca)
-                    wait_a(), gemm_b(2, 128, kColH, true), done(1), tl_mark(a, 204);   // h += . Wo_ca
-                    wait_a(), gemm_b(2, 64, kColW, false), done(2), tl_mark(a, 205);   // FFN up
-                    wait_a(), gemm_b(1, 128, kColW, false), done(2), tl_mark(a, 206);  // FFN down
-                    wait_a(), gemm_b(2, 128, kColH, true), done(1), tl_mark(a, 207);   // h += . Wo_ffn
+                    wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(201);   // h += . Wo_sa
+                    wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(202);  // q_ca
+                    wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(203);  // y = softmax(q) . blockdiag(A_ca)
+                    // h += a . Wo_ca, and -- the FFN has no pre-norm, so its up-projection is linear in the residual add --
+                    // u = (h + a . Wo_ca + bo) . W1 = h16 . W1 + a . (W1 Wo_ca) + const in the same breath: one round trip less
+                    wait_a(), gemm_b(2, 128, kColH, true, awork), tl.mark(204);
+                    {
+                        const uint32_t idesc64 = make_idesc<kBf16>(kTileRows, 64);
+                        const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
+                        ++itB;
+                        mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(ringB + st * kSB);
+                        for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, smem_u32(xbuf) + k * kABlockBytes, b_base + k * 8192, idesc64, k > 0);
+                        umma_commit(smem_u32(&bars->emptyB[st]));
+                        mbar_wait(smem_u32(&bars->w1c_full), (uint32_t)(si * L + it) & 1u);
+                        tc_fence_after();
+                        for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, smem_u32(w1c) + k * 8192, idesc64, true);
+                    }
+                    done(2), tl.mark(205);
+                    wait_a(), gemm_b(1, 128, kColW, false, awork), done(2), tl.mark(206);  // FFN down
+                    wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(207);   // h += . Wo_ffn
                 }
                 if (it + 1 < L) {
                     wait_a();
-                    gemm_b(2, 128, kColS, false);                                  // q -> S[0:128]
-                    const uint32_t itA0 = (uint32_t)si * 26u * (uint32_t)L + (uint32_t)(it + 1) * 26;   // Wk, Wv of layer it+1 in ring A
+                    gemm_b(2, 128, kColS, false, awork);                           // q -> S[0:128]
+                    const uint32_t itA0 = (uint32_t)si * kRingAItems * (uint32_t)L + (uint32_t)(it + 1) * kRingAItems;   // Wk, Wv of layer it+1 in ring A
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t itA = itA0 + j;
                         const uint32_t st = itA % kNA, ph = (itA / kNA) & 1u;
@@ -276,14 +318,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                             umma_kblock(tmem_base + (j == 0 ? kColS + 128 : kColW), awork + k * kABlockBytes, b_base + k * 16384, idesc128, k > 0);
                         umma_commit(smem_u32(&bars->emptyA[st]));
                     }
-                    done(2), tl_mark(a, 208);
+                    done(2), tl.mark(208);
                     wait_a();                                                      // K^T V partial: E^T . V, MN-major images
                     const uint32_t eimg = smem_u32(xbuf), vimg = smem_u32(ringB);
                     for (int ks = 0; ks < 8; ++ks)
                         umma_f16(tmem_base + kColW, make_desc_mnmajor_sw128(eimg + ks * 2048), make_desc_mnmajor_sw128(vimg + ks * 2048), idmn, ks > 0);
-                    done(2), tl_mark(a, 209);
+                    done(2), tl.mark(209);
                 }
             }
+            tl.finish();
         }
     } else {
         const uint32_t a_ready_addr = smem_u32(&bars->a_ready);
@@ -297,6 +340,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         const int t = valid ? t0 + (int)r : 0;
         const bool keep = valid && (a.length == nullptr || (long long)t < a.length[clip]);
         uint32_t ph[3] = {0, 0, 0};
+        Timeline tl(a, 0);
+        if (threadIdx.x != 0) tl.p = nullptr;
+        tl.mark(1);
         RowStats rs{xchg, 1 + lq, r, cq, 0};
         float mean, rstd;
         float v[32];
@@ -341,7 +387,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 if (tx < 96) reinterpret_cast<float4*>(prm_sa)[tx] = psa;
             }
             named_bar_sync(5, kRowThreads);
-            if (tx == 0) tl_mark(a, 128);
+            tl.mark(128);
             // h0 for this thread's 32 features (v already holds the sequence embedding)
             {
                 uint64_t hv[16];
@@ -366,36 +412,38 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             }
             tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
-            if (tx == 0) tl_mark(a, 129);
+            tl.mark(129);
         }
 
         for (int it = -1; it < L; ++it) {
             if (it >= 0) {
             // ================= self-attention tail: y = q . blockdiag(A_sa) (tensor cores) ; h += Styl(y)
-                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 101);
+                rows_wait(bars, 2, ph[2]); tl.mark(101);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
                 row_stats32(rs, v, mean, rstd);
-                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 102);                                   // S = A_emb . We_sa
+                rows_wait(bars, 0, ph[0]); tl.mark(102);                                   // S = A_emb . We_sa
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
                 tc_fence_before();                                           // S consumed: the next FiLM projection may start
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_free_addr);
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 151);                                          // -> h += A . Wo_sa
+                rows_publish<false>(a_ready_addr, lane); tl.mark(151);                                          // -> h += A . Wo_sa
 
                 // ================= cross-attention
-                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 103);
+                rows_wait(bars, 1, ph[1]); tl.mark(103);
                 tmem_ld32(trow + kColH + c0, v);
                 tmem_wait_ld();
                 add_bias32(v, prm + kPrmStSa + kStBo + c0);                  // deferred bias of Wo_sa
                 tmem_st32(trow + kColH + c0, v);
+                store_a16<kBf16>(smem_u32(xbuf), r, c0, v);                  // 16-bit image of h for the fused FFN up-projection
+                store_a16<kBf16>(smem_u32(xbuf), r, c0 + 16, v + 16);
                 row_stats32(rs, v, mean, rstd);
                 normalize32(v, mean, rstd);                                  // LN affine folded into Wq_ca
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
                 tmem_wait_st();
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 152);                                          // -> W = LN(h) . Wq_ca
-                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 104);
+                rows_publish<false>(a_ready_addr, lane); tl.mark(152);                                          // -> W = LN(h) . Wq_ca
+                rows_wait(bars, 2, ph[2]); tl.mark(104);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
                 add_bias32(v, prm + kPrmCaBq + c0);
@@ -403,29 +451,22 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 softmax16(v + 16);
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 153);                                          // -> W = softmax(q) . blockdiag(A_ca)
-                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 105);
+                rows_publish<false>(a_ready_addr, lane); tl.mark(153);                                          // -> W = softmax(q) . blockdiag(A_ca)
+                rows_wait(bars, 2, ph[2]); tl.mark(105);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
                 row_stats32(rs, v, mean, rstd);
-                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 106);                                   // S = A_emb . We_ca
+                rows_wait(bars, 0, ph[0]); tl.mark(106);                                   // S = A_emb . We_ca
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
                 tc_fence_before();                                           // S consumed: the next FiLM projection may start
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_free_addr);
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 154);                                          // -> h += A . Wo_ca
+                rows_publish<false>(a_ready_addr, lane); tl.mark(154);                                          // -> h += A . Wo_ca
 
-                // ================= FFN (no pre-norm, reference transformer.py:170-173)
-                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 107);
-                tmem_ld32(trow + kColH + c0, v);
-                tmem_wait_ld();
-                add_bias32(v, prm + kPrmStCa + kStBo + c0);                  // deferred bias of Wo_ca
-                tmem_st32(trow + kColH + c0, v);
-                store_a16<kBf16>(awork, r, c0, v);
-                store_a16<kBf16>(awork, r, c0 + 16, v + 16);
-                tmem_wait_st();
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 155);                                          // -> W[0:64] = h . W1
-                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 108);
+                // ================= FFN (no pre-norm, reference transformer.py:170-173): W[0:64] = h . W1 was issued together
+                //                   with the Wo_ca residual GEMM (see the MMA issuer); the deferred bias of Wo_ca is part
+                //                   of the folded FFN-up bias and of the layer's final residual bias
+                rows_wait(bars, 2, ph[2]); tl.mark(108);
                 {
                     float u[16];                                             // hidden 64 = 4 quarters of 16
                     tmem_ld16(trow + kColW + 16 * cq, u);
@@ -434,16 +475,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     for (int i = 0; i < 16; ++i) u[i] = gelu_erf_f(u[i] + prm[kPrmFfB1 + 16 * cq + i]);
                     store_a16<kBf16>(awork, r, 16 * cq, u);
                 }
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 156);                                          // -> W = GELU(.) . W2
-                rows_wait(bars, 2, ph[2]); if (threadIdx.x == 0) tl_mark(a, 109);
+                rows_publish<false>(a_ready_addr, lane); tl.mark(156);                                          // -> W = GELU(.) . W2
+                rows_wait(bars, 2, ph[2]); tl.mark(109);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
                 add_bias32(v, prm + kPrmFfB2 + c0);
                 row_stats32(rs, v, mean, rstd);
-                rows_wait(bars, 0, ph[0]); if (threadIdx.x == 0) tl_mark(a, 110);                                   // S = A_emb . We_ffn
+                rows_wait(bars, 0, ph[0]); tl.mark(110);                                   // S = A_emb . We_ffn
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
-                rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 157);                                          // -> h += A . Wo_ffn
-                rows_wait(bars, 1, ph[1]); if (threadIdx.x == 0) tl_mark(a, 111);
+                rows_publish<false>(a_ready_addr, lane); tl.mark(157);                                          // -> h += A . Wo_ffn
+                rows_wait(bars, 1, ph[1]); tl.mark(111);
             }
 
             // ---- residual stream after layer `it` (deferred bias of the last FFN block)
@@ -532,7 +573,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);
             tmem_wait_st();
-            rows_publish<false>(a_ready_addr, lane); if (threadIdx.x == 0) tl_mark(a, 158);
+            rows_publish<false>(a_ready_addr, lane); tl.mark(158);
             if (it < 0) {
                 // ---- rest of the step prologue, overlapped with the first q|k|v MMAs: this tile's A_emb image -> global
                 const int tx = threadIdx.x;
@@ -566,10 +607,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 asm volatile("fence.proxy.async;" ::: "memory");      // ... and be ordered before the bulk-copy (async proxy) reads
                 named_bar_sync(5, kRowThreads);                        // every row thread is done with the staging area in xbuf
                 if (lane == 0) mbar_arrive(smem_u32(&bars->aemb_ready));
-                if (tx == 0) tl_mark(a, 127);
+                tl.mark(127);
             }
             rows_wait(bars, 2, ph[2]);
-            if (threadIdx.x == 0) tl_mark(a, 112);
+            tl.mark(112);
             {
                 // Time-axis softmax + K^T V (reference :111,:117) on the tensor cores, one clip per cluster.  Two 32 KB
                 // operand-image buffers X (xbuf), Y (ring B) are all the scratch it needs:
@@ -578,8 +619,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 //   (same rounded values as the MMA sees).
                 // The partial (max, sum, diagonal 16x16 blocks of P) stays in this CTA's shared memory (over Y); every CTA
                 // of the cluster pulls all nt partials and merges them into its own block-diagonal B-operand image (X).
-                float* pm = red;                                       // [8 rg][128] exchange (max, then sums)
-                float* msm = pm + 1024;                                // [128] maxima
+                float* pm = reinterpret_cast<float*>(xchg);            // [8 rg][128] exchange (max, then sums); xchg is idle here
+                float* msm = red;                                      // [128] maxima
                 float* ssm = msm + 128;                                // [128] sums
                 float* mypart = reinterpret_cast<float*>(ringB);       // [kKvPartFloats]
                 uint8_t* Xp = xbuf;
@@ -649,9 +690,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 }
                 store_a16<kBf16>(vimg, r, c0, vx);
                 store_a16<kBf16>(vimg, r, c0 + 16, vx + 16);
-                if (tx == 0) tl_mark(a, 120);
+                tl.mark(120);
                 rows_publish<false>(a_ready_addr, lane);                      // -> W = E^T . V  (8 MMAs over the tokens)
-                if (tx == 0) tl_mark(a, 122);
+                tl.mark(122);
                 {
                     // q: softmax over head-dim -> operand buffer (A operand of the next layer's q . blockdiag(A_sa));
                     // runs while the tensor core does E^T V.  Once q and k have left S the next FiLM projection may start.
@@ -683,7 +724,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     }
                 }
                 rows_wait(bars, 2, ph[2]);                                // E^T V complete: the E and V images are dead
-                if (tx == 0) tl_mark(a, 123);
+                tl.mark(123);
                 if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
                     float pr[32];
                     tmem_ld32(trow + kColW + 32 * lq, pr);
@@ -697,7 +738,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
                 }
                 named_bar_sync(5, kRowThreads);                            // partial complete
-                if (tx == 0) tl_mark(a, 124);
+                tl.mark(124);
                 // ---- publish to the peers: release at cluster scope, one remote arrive per peer
                 if (nt > 1 && tx < nt && tx != rank) {
                     fence_acq_rel_cluster();
@@ -719,7 +760,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 }
                 if (nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
                 named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared
-                if (tx == 0) tl_mark(a, 125);
+                tl.mark(125);
                 // ---- merge the nt partials (online-softmax rescaling, four tiles per round trip) into the block-diagonal
                 //      B-operand image.
                 if (nt <= kDirectMergeTiles) {
@@ -825,12 +866,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pull_done[seq & 1u]), (uint32_t)tx));
                 }
                 rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
-                if (tx == 0) tl_mark(a, 126);
+                tl.mark(126);
             }
         }
         }   // launch step si
+        tl.mark(2);
+        tl.finish();
     }
-    if (threadIdx.x == 0) tl_mark(a, 2);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                                   // no CTA leaves while a peer may still touch its shared memory
@@ -841,7 +883,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
 }
 
 constexpr int kClipSmemBytes = kPRingAStages * kStageBytes + kRingBStages * kRingBStageBytes + 2 * kAworkBytes +
-                               (kPrmFloats + 384) * 4 + 512 * 8 + kClipRedFloats * 4 + sizeof(ClipBarriers) + 1024;
+                               (kPrmFloats + 384) * 4 + 512 * 8 + kClipRedFloats * 4 + 16384 + sizeof(ClipBarriers) + 1024;
 static_assert(kClipSmemBytes <= 232448, "clip kernel exceeds the 227 KB shared-memory limit");
 
 }  // namespace dc

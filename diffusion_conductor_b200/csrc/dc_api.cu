@@ -67,6 +67,8 @@ struct dc_handle {
     // packed / derived weights (device, owned)
     uint8_t* wbuf = nullptr;      // [L][1 MiB]
     float* prm = nullptr;         // [L][kPrmFloats]
+    float* prm_clip = nullptr;    // [L][kPrmFloats] variant read by the persistent kernel (FFN-up fused across the Wo_ca residual add)
+    uint8_t* wfuse = nullptr;     // [L][16 KB] (W1 . Wo_ca) [64 x 128] operand image
     uint8_t* wkv = nullptr;       // [L][8][256 x 128 B] folded cross-attention K|V weights
     float* bkv = nullptr;         // [L][256]
     float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
@@ -404,7 +406,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     StepArgs sa{};
     sa.L = L, sa.M = h->M, sa.T = h->T;
     sa.n_steps = n_steps, sa.step0 = step0;
-    sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm;
+    sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm_clip, sa.wfuse = h->wfuse;
     sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
     sa.length = h->has_length ? h->length : nullptr;
     sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.x0_stride = x0_stride, sa.x_trace = x_trace;
@@ -529,7 +531,7 @@ void dc_destroy(dc_handle* h) {
     cudaSetDevice(h->cfg.device);
     drop_graph(h);
     free_workspace(h);
-    void* ptrs[] = {h->wbuf, h->prm, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
+    void* ptrs[] = {h->wbuf, h->prm, h->prm_clip, h->wfuse, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -567,6 +569,7 @@ int dc_finalize_weights(dc_handle* h) {
     std::vector<uint8_t> wbuf((size_t)L * kLayerSlab, 0);
     std::vector<float> prm((size_t)L * kPrmFloats, 0.f);
     std::vector<uint8_t> wkv((size_t)L * 8 * 32768, 0);
+    std::vector<uint8_t> wfuse((size_t)L * 16384, 0);
     std::vector<float> bkv((size_t)L * 256, 0.f);
 
     int film_rows[256];   // accumulator column n <- emb_layers.1 row: [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]
@@ -652,10 +655,40 @@ int dc_finalize_weights(dc_handle* h) {
             for (int i = 0; i < kF; ++i) pr[kPrmFfB1 + i] = b1->v[i];
             for (int i = 0; i < kD; ++i) pr[kPrmFfB2 + i] = b2->v[i];
             if (stylization(p + "ffn.proj_out.", kOffWeFf, kOffWoFf, kPrmStFf)) return DC_ERR_INVALID;
+            // Persistent kernel: the FFN has no pre-norm (transformer.py:170-173), so its up-projection is linear in the
+            // residual add that precedes it:  (h + a Wo^T + bo) W1^T = h W1^T + a (W1 Wo)^T + W1 bo.  The kernel issues
+            // both GEMMs at once and skips a round trip; here: the product matrix and the folded biases.
+            GET(wo, p + "ca_block.proj_out.out_layers.2.weight", kD, kD);
+            GET(bo, p + "ca_block.proj_out.out_layers.2.bias", kD);
+            std::vector<float> W1c((size_t)kF * kD);
+            for (int n = 0; n < kF; ++n)
+                for (int k = 0; k < kD; ++k) {
+                    double acc = 0.0;
+                    for (int j = 0; j < kD; ++j) acc += (double)W1->v[(size_t)n * kD + j] * wo->v[(size_t)j * kD + k];
+                    W1c[(size_t)n * kD + k] = (float)acc;
+                }
+            pack_image(wfuse.data() + (size_t)l * 16384, W1c.data(), kD, kD, nullptr, nullptr, kF, 2, bf);
         }
+    }
+    // parameter block variant of the persistent kernel: b1 <- b1 + W1 bo_ca ; bo_ffn <- bo_ffn + bo_ca (added once, at the
+    // end of the layer, instead of right after the Wo_ca GEMM)
+    std::vector<float> prm_clip = prm;
+    for (int l = 0; l < L; ++l) {
+        const std::string p = "temporal_decoder_blocks." + std::to_string(l) + ".";
+        GET(W1, p + "ffn.linear1.weight", kF, kD);
+        float* pc = prm_clip.data() + (size_t)l * kPrmFloats;
+        const float* bo_ca = prm.data() + (size_t)l * kPrmFloats + kPrmStCa + kStBo;
+        for (int n = 0; n < kF; ++n) {
+            double acc = 0.0;
+            for (int j = 0; j < kD; ++j) acc += (double)W1->v[(size_t)n * kD + j] * bo_ca[j];
+            pc[kPrmFfB1 + n] += (float)acc;
+        }
+        for (int i = 0; i < kD; ++i) pc[kPrmStFf + kStBo + i] += bo_ca[i];
     }
     if (upload(h, &h->wbuf, wbuf.data(), wbuf.size())) return DC_ERR_CUDA;
     if (upload(h, &h->prm, prm.data(), prm.size() * 4)) return DC_ERR_CUDA;
+    if (upload(h, &h->prm_clip, prm_clip.data(), prm_clip.size() * 4)) return DC_ERR_CUDA;
+    if (upload(h, &h->wfuse, wfuse.data(), wfuse.size())) return DC_ERR_CUDA;
     if (upload(h, &h->wkv, wkv.data(), wkv.size())) return DC_ERR_CUDA;
     if (upload(h, &h->bkv, bkv.data(), bkv.size() * 4)) return DC_ERR_CUDA;
 
@@ -967,15 +1000,18 @@ int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out,
     if (!x || !out || max_launches < 1) return fail(h, DC_ERR_INVALID, "dc_debug_timeline: bad argument");
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
     const int n = std::min(max_launches, h->cfg.num_layers + 1);
-    if (!h->timeline) DC_CUDA(h, cudaMalloc((void**)&h->timeline, (size_t)(h->cfg.num_layers + 1) * 512 * 8));
-    DC_CUDA(h, cudaMemset(h->timeline, 0, (size_t)(h->cfg.num_layers + 1) * 512 * 8));
+    // per-layer path: [launch][512] u64; persistent kernel: 3 lanes of (1 + 2 * kTlEvents) u64 (see Timeline in clip_kernel.cuh)
+    const size_t words = std::max((size_t)(h->cfg.num_layers + 1) * 512, (size_t)3 * (1 + 2 * kTlEvents));
+    if (!h->timeline) DC_CUDA(h, cudaMalloc((void**)&h->timeline, words * 8));
+    DC_CUDA(h, cudaMemset(h->timeline, 0, words * 8));
     set_step_kernel<<<1, 1>>>(h->step_ctr, step, 0);
     h->timeline_on = true;
     const int rc = enqueue_step(h, x, h->te_table, 0, true, DC_SAMPLER_DDIM, x, h->x0work, nullptr, step, 0);
     h->timeline_on = false;
     if (rc) return rc;
     DC_CUDA(h, cudaDeviceSynchronize());
-    DC_CUDA(h, cudaMemcpy(out, h->timeline, (size_t)n * 512 * 8, cudaMemcpyDeviceToHost));
+    DC_CUDA(h, cudaMemcpy(out, h->timeline, std::min((size_t)max_launches * 512, words) * 8, cudaMemcpyDeviceToHost));
+    (void)n;
     return 0;
 }
 

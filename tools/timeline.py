@@ -32,30 +32,39 @@ nl = 9
 buf = (C.c_uint64 * (nl * 512))()
 xs = x.clone()
 _lib.check(eng.lib.dc_debug_timeline(eng.handle, C.c_void_p(xs.data_ptr()), S - 1, buf, nl), eng.handle)
-first = int(buf[0])
-if first > 254:          # persistent step kernel: one long event list
-    n = min(first, 2040)
-    ev = sorted((int(buf[1 + 2 * i]), int(buf[2 + 2 * i])) for i in range(n))
+persistent = T <= 2048 and os.environ.get("DC_PERSIST", "1") != "0"
+if persistent:          # cluster-per-clip kernel: three lanes (row thread 0, dependent-MMA issuer, FiLM issuer) of (clock, id) pairs
+    LANE = 1 + 2 * 680
+    ev = []
+    for lane_id in range(3):
+        cnt = min(int(buf[lane_id * LANE]), 680)
+        ev += [(int(buf[lane_id * LANE + 1 + 2 * i]), int(buf[lane_id * LANE + 2 + 2 * i])) for i in range(cnt)]
+    ev.sort()
+    n = len(ev)
     t0 = ev[0][0]
     names = {1: "start", 2: "rows_done", 112: "rows: got QKV", 208: "        mma: issued QKV", 209: "        mma: issued KtV pass"}
     dn = ["qA_sa", "Wo_sa", "Wq_ca", "qA_ca", "Wo_ca", "W1", "W2", "Wo_ff"]
     lo, hi = (int(v) for v in os.environ.get("TL_RANGE", "0,140").split(","))
-    print(f"--- persistent step kernel: {n} events; showing events [{lo},{hi}) ; total {ev[-1][0] - t0} cycles")
+    print(f"--- persistent clip kernel: {n} events; showing events [{lo},{hi}) ; total {ev[-1][0] - t0} cycles")
     for k, (t, i) in enumerate(ev):
         if not (lo <= k < hi):
             continue
         if i in names:
             nm = names[i]
         elif 120 <= i < 130:
-            nm = "rows epi: " + ["col max/E/V done", "buffers cleared, params reloaded", "published V", "got KtV", "partials written", "all partials visible", "published merged images", "A_emb image written", "prologue operands staged", "h0 in TMEM"][i - 120]
+            nm = "rows epi: " + ["col max/E/V done", "-", "published V", "got KtV", "partial written", "all partials visible", "published merged image", "A_emb image written", "prologue operands staged", "h0 in TMEM"][i - 120]
         elif 100 < i < 150:
             nm = "rows: got " + ROWW[i - 101]
         elif 150 < i < 200:
             nm = "rows: published " + ROWP[i - 151]
         elif 200 <= i < 208:
             nm = "        mma: issued " + dn[i - 200]
+        elif i == 400:
+            nm = "        mma: a_ready observed"
+        elif i == 401:
+            nm = "        mma: ring-B stage full"
         elif 310 <= i < 320:
-            nm = f"        mma: S#{i - 310} last stage issued"
+            nm = f"                mma2: S#{i - 310} last stage issued"
         else:
             nm = str(i)
         print(f"{t - t0:8d}  {nm}")
