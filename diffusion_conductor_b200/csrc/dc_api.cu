@@ -69,6 +69,8 @@ struct dc_handle {
     float* prm = nullptr;         // [L][kPrmFloats]
     float* prm_clip = nullptr;    // [L][kPrmFloats] variant read by the persistent kernel (FFN-up fused across the Wo_ca residual add)
     uint8_t* wfuse = nullptr;     // [L][16 KB] (W1 . Wo_ca) [64 x 128] operand image
+    float* kshift = nullptr;      // [L][128] static shift of the time-axis softmax (bound of |k| per key column)
+    uint32_t static_mask = 0;     // bit l: layer l's bound is small enough to replace the running column max
     uint8_t* wkv = nullptr;       // [L][8][256 x 128 B] folded cross-attention K|V weights
     float* bkv = nullptr;         // [L][256]
     float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
@@ -407,6 +409,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     sa.L = L, sa.M = h->M, sa.T = h->T;
     sa.n_steps = n_steps, sa.step0 = step0;
     sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm_clip, sa.wfuse = h->wfuse;
+    sa.kshift = h->kshift, sa.static_mask = h->static_mask;
     sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
     sa.length = h->has_length ? h->length : nullptr;
     sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.x0_stride = x0_stride, sa.x_trace = x_trace;
@@ -531,7 +534,7 @@ void dc_destroy(dc_handle* h) {
     cudaSetDevice(h->cfg.device);
     drop_graph(h);
     free_workspace(h);
-    void* ptrs[] = {h->wbuf, h->prm, h->prm_clip, h->wfuse, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
+    void* ptrs[] = {h->wbuf, h->prm, h->prm_clip, h->wfuse, h->kshift, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -570,6 +573,8 @@ int dc_finalize_weights(dc_handle* h) {
     std::vector<float> prm((size_t)L * kPrmFloats, 0.f);
     std::vector<uint8_t> wkv((size_t)L * 8 * 32768, 0);
     std::vector<uint8_t> wfuse((size_t)L * 16384, 0);
+    std::vector<float> kshift((size_t)L * kD, 0.f);
+    uint32_t static_mask = 0;
     std::vector<float> bkv((size_t)L * 256, 0.f);
 
     int film_rows[256];   // accumulator column n <- emb_layers.1 row: [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]
@@ -621,6 +626,26 @@ int dc_finalize_weights(dc_handle* h) {
                 fold_bias(W, b, bt, pr + poffs[i]);
             }
             if (stylization(p + "sa_block.proj_out.", kOffWeSa, kOffWoSa, kPrmStSa)) return DC_ERR_INVALID;
+            // Static shift of softmax_T(k) (transformer.py:111): k_d = w_d . n + b_d with n a LayerNorm output, so
+            // ||n||_2 <= sqrt(128) and |k_d| <= ||w_d||_2 sqrt(128) + |b_d| =: c_d (1 % slack for the 16-bit operand
+            // rounding).  exp(k - c) then never overflows and stays >= exp(-2c): if every c_d of the layer is small
+            // the kernel uses c instead of the per-tile column max (softmax is shift-invariant).  Masked frames
+            // (k - 1e6) still underflow to exactly 0, as in the reference.
+            GET(Wk, p + "sa_block.key.weight", kD, kD);
+            float cmax = 0.f;
+            for (int d = 0; d < kD; ++d) {
+                double n2 = 0.0;
+                for (int k = 0; k < kD; ++k) {
+                    const double w = (double)Wk->v[(size_t)d * kD + k] * g->v[k];
+                    n2 += w * w;
+                }
+                const float c = (float)(1.01 * std::sqrt(n2) * std::sqrt((double)kD) + std::fabs((double)pr[kPrmSaBk + d]) + 1e-3);
+                kshift[(size_t)l * kD + d] = c;
+                cmax = std::max(cmax, c);
+            }
+            const char* ss = getenv("DC_STATIC_SHIFT");       // "0": always use the running max (tests)
+            const float limit = bf ? 30.f : 4.f;              // E must stay a normal number of the 16-bit operand type
+            if (cmax <= limit && !(ss && ss[0] == '0')) static_mask |= 1u << l;
         }
         // cross-attention: query side per step, key/value side step-invariant (text_norm folded)
         {
@@ -689,6 +714,8 @@ int dc_finalize_weights(dc_handle* h) {
     if (upload(h, &h->prm, prm.data(), prm.size() * 4)) return DC_ERR_CUDA;
     if (upload(h, &h->prm_clip, prm_clip.data(), prm_clip.size() * 4)) return DC_ERR_CUDA;
     if (upload(h, &h->wfuse, wfuse.data(), wfuse.size())) return DC_ERR_CUDA;
+    if (upload(h, &h->kshift, kshift.data(), kshift.size() * 4)) return DC_ERR_CUDA;
+    h->static_mask = L <= 32 ? static_mask : 0;
     if (upload(h, &h->wkv, wkv.data(), wkv.size())) return DC_ERR_CUDA;
     if (upload(h, &h->bkv, bkv.data(), bkv.size() * 4)) return DC_ERR_CUDA;
 

@@ -327,6 +327,33 @@ __device__ __forceinline__ float silu_f(float v) {
 }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
 
+// MUFU.EX2 without the denormal fix-up code exp2f() carries (results below 2^-126 flush to 0)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// erf-GELU (reference activation="gelu", transformer.py:164/172) for a pair of values in packed f32x2 math:
+//   erf(t) = 1 - 2^(t P(t)) on t = min(|x| / sqrt 2, 4), P a degree-6 polynomial fitted to log2(erfc(t)) / t
+//   (max abs error of erf 3.5e-7, of GELU 1e-7 -- at the fp32 rounding level);  x (1 + erf) / 2 = x/2 + |x|/2 * erf(|t|).
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const float t0 = fminf(fabsf(x0) * 0.70710678118654752f, 4.f), t1 = fminf(fabsf(x1) * 0.70710678118654752f, 4.f);
+    const uint64_t t = pk2(t0, t1);
+    uint64_t p = pk2(3.362845746e-05f, 3.362845746e-05f);
+    p = ffma2(p, t, pk2(-3.501975880e-05f, -3.501975880e-05f));
+    p = ffma2(p, t, pk2(-3.336299676e-03f, -3.336299676e-03f));
+    p = ffma2(p, t, pk2(3.064695559e-02f, 3.064695559e-02f));
+    p = ffma2(p, t, pk2(-1.496411115e-01f, -1.496411115e-01f));
+    p = ffma2(p, t, pk2(-9.181558490e-01f, -9.181558490e-01f));
+    p = ffma2(p, t, pk2(-1.627928376e+00f, -1.627928376e+00f));
+    float q0, q1;
+    upk2(fmul2(p, t), q0, q1);
+    const uint64_t e = ffma2(pk2(ex2_ftz(q0), ex2_ftz(q1)), pk2(-1.f, -1.f), pk2(1.f, 1.f));      // erf(|t|)
+    const uint64_t hx = fmul2(pk2(x0, x1), pk2(0.5f, 0.5f)), ha = fmul2(pk2(fabsf(x0), fabsf(x1)), pk2(0.5f, 0.5f));
+    upk2(ffma2(ha, e, hx), x0, x1);
+}
+
 __device__ __forceinline__ void softmax16(float* q) {
     float mx = q[0];
 #pragma unroll
@@ -340,7 +367,7 @@ __device__ __forceinline__ void softmax16(float* q) {
     for (int i = 0; i < 8; ++i) {
         float a0, a1;
         upk2(ffma2(pk2(q[2 * i], q[2 * i + 1]), l2, nm), a0, a1);
-        e2[i] = pk2(exp2f(a0), exp2f(a1));
+        e2[i] = pk2(ex2_ftz(a0), ex2_ftz(a1));
         acc = fadd2(acc, e2[i]);
     }
     float s0, s1;

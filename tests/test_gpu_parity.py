@@ -310,6 +310,38 @@ def test_cluster_sizes_and_merge_paths():
         close(y, ref, "fp16", f"forward B={B} T={T} ({-(-T // 128)} tiles per clip)")
 
 
+def test_static_and_running_softmax_shift(monkeypatch):
+    """Time-axis softmax of the self-attention keys: the kernel replaces the running column max by a static
+    weight-norm bound of |k| when that bound is small (bf16 operands, ordinary weights) and keeps the exact running max
+    otherwise (forced with DC_STATIC_SHIFT=0, or automatically when the key weights are large).  Both against the
+    oracle, with ragged lengths and a zero-length clip (every frame masked: the reference yields A = 0)."""
+    B, T = 4, 200
+    xf_proj, xf_out = synth_features(B, T, seed=12)
+    _, x = synth_inputs(B, T, seed=12)
+    t = torch.tensor([24, 1, 13, 0])
+    length = [200, 0, 131, 199]
+    outs = {}
+    for mode in ("static", "running", "large-weights"):
+        if mode == "running":
+            monkeypatch.setenv("DC_STATIC_SHIFT", "0")
+        else:
+            monkeypatch.delenv("DC_STATIC_SHIFT", raising=False)
+        sd = synth_state_dict(23, num_layers=3)
+        if mode == "large-weights":
+            for l in range(3):
+                sd[f"temporal_decoder_blocks.{l}.sa_block.key.weight"] = sd[f"temporal_decoder_blocks.{l}.sa_block.key.weight"] * 12.0
+        m = MotionTransformer(26, num_frames=1800, num_layers=3, latent_dim=128, device="cuda", music_model_path=None,
+                              operand_dtype="bf16")
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        y = m(x.cuda(), t.cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+        with torch.no_grad():
+            ref = O.motion_transformer_forward(sd, x, t, length, xf_proj, xf_out)
+        close(y, ref, "bf16", f"forward, softmax shift mode {mode}")
+        outs[mode] = y
+    close(outs["static"], outs["running"], "bf16", "static vs running shift")
+
+
 def test_batch_larger_than_the_gpu():
     """More clusters than the GPU holds at once (300 clips x 2 tiles > 148 SMs): clusters are scheduled as SMs free up
     and every clip still comes out as if it were generated alone (25-step DDIM loop, one launch)."""
