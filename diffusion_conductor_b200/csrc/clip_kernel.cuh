@@ -61,20 +61,25 @@ enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, k
 // (clock64, id) pairs to its OWN lane of the buffer with plain stores -- no atomics, so a mark costs a few cycles.
 // Layout: [3 lanes][1 + 2 * kTlEvents] u64, word 0 of a lane = number of events.
 constexpr int kTlEvents = 680;
+template <bool kOn>
 struct Timeline {
     unsigned long long* p;
     uint32_t n;
-    __device__ __forceinline__ Timeline(const StepArgs& a, int lane_id)
-        : p(a.timeline != nullptr && blockIdx.x == 0 ? a.timeline + (size_t)lane_id * (1 + 2 * kTlEvents) : nullptr), n(0) {}
+    __device__ __forceinline__ Timeline(const StepArgs& a, int lane_id, bool writer = true)
+        : p(kOn && writer && a.timeline != nullptr && blockIdx.x == 0 ? a.timeline + (size_t)lane_id * (1 + 2 * kTlEvents) : nullptr), n(0) {}
     __device__ __forceinline__ void mark(unsigned long long id) {
-        if (p != nullptr && n < (uint32_t)kTlEvents) {
-            p[1 + 2 * n] = (unsigned long long)clock64();
-            p[2 + 2 * n] = id;
-            ++n;
+        if constexpr (kOn) {
+            if (p != nullptr && n < (uint32_t)kTlEvents) {
+                p[1 + 2 * n] = (unsigned long long)clock64();
+                p[2 + 2 * n] = id;
+                ++n;
+            }
         }
     }
     __device__ __forceinline__ void finish() {
-        if (p != nullptr) p[0] = n;
+        if constexpr (kOn) {
+            if (p != nullptr) p[0] = n;
+        }
     }
 };
 
@@ -90,7 +95,9 @@ struct ClipBarriers : LayerBarriers {
     uint64_t w1c_full;                  // the (W1 Wo_ca) image of the current layer has landed
 };
 
-template <bool kBf16>
+// kTl: instrumented build for dc_debug_timeline (the marks cost ~5 % of the instruction stream, so the production
+// instantiation compiles them out)
+template <bool kBf16, bool kTl = false>
 __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_constant__ StepArgs a) {
     constexpr int kNA = kPRingAStages, kSA = kStageBytes, kNB = kRingBStages, kSB = kRingBStageBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
     } else if (warp == kRelayWarp) {
         // ---------------- issuer of the FiLM projections S = A_emb . We (ring A), gated only by s_free
         if (lane == 0) {
-            Timeline tl(a, 2);
+            Timeline<kTl> tl(a, 2);
             const uint32_t idesc_s = make_idesc<kBf16>(kTileRows, 256);
             uint32_t sj = 0;
             for (int si = 0; si < a.n_steps; ++si)
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
     } else if (warp == kMmaWarp) {
         // ---------------- issuer of the dependent GEMMs, strictly in chain order with blocking waits
         if (lane == 0) {
-            Timeline tl(a, 1);
+            Timeline<kTl> tl(a, 1);
             const uint32_t awork = smem_u32(awork_p);
             uint32_t itB = 0, a_phase = 0;
             auto wait_a = [&]() {
@@ -342,8 +349,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         const int t = valid ? t0 + (int)r : 0;
         const bool keep = valid && (a.length == nullptr || (long long)t < a.length[clip]);
         uint32_t ph[3] = {0, 0, 0};
-        Timeline tl(a, 0);
-        if (threadIdx.x != 0) tl.p = nullptr;
+        Timeline<kTl> tl(a, 0, threadIdx.x == 0);
         tl.mark(1);
         RowStats rs{xchg, 1 + lq, r, cq, 0};
         float mean, rstd;
@@ -603,8 +609,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         const float e8[8] = {a0.x + t0v.x, a0.y + t0v.y, a0.z + t0v.z, a0.w + t0v.w, a1.x + t1v.x, a1.y + t1v.y, a1.z + t1v.z, a1.w + t1v.w};
                         uint32_t p[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            p[i] = pack2<kBf16>(__fdividef(e8[2 * i], 1.f + __expf(-e8[2 * i])), __fdividef(e8[2 * i + 1], 1.f + __expf(-e8[2 * i + 1])));
+                        for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(silu_f<kBf16>(e8[2 * i]), silu_f<kBf16>(e8[2 * i + 1]));
                         const uint4 pk = row < nrows ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0, 0, 0, 0);
                         *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
                     }
@@ -656,11 +661,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 tmem_wait_ld();
 
                 add_bias32(kx, prm_sa + kPrmSaBk + c0);
+                if (!keep) {                 // masked frame: k - 1e6 (reference :110); padding row of the tile: -inf (E = 0 exactly)
+                    const float madd = valid ? -1000000.f : -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (!keep) kx[i] += -1000000.f;
-                    if (!valid) kx[i] = -INFINITY;
-                    if constexpr (!kBf16) kx[i] = fmaxf(kx[i], -60000.f);      // fp16 image of k: keep the mask finite
+                    for (int i = 0; i < 32; ++i) {
+                        kx[i] += madd;
+                        if constexpr (!kBf16) kx[i] = fmaxf(kx[i], -60000.f);  // fp16 image of k: keep the mask finite
+                    }
                 }
                 // Softmax over time is shift-invariant per key column: when the host could bound |k| (Cauchy-Schwarz on the
                 // LayerNorm output, ||n|| <= sqrt(128)) by a small constant, that bound replaces the running column max --
@@ -697,7 +704,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 {   // E = exp(k - shift) (0 for padding rows) -> X ; V -> Y
                     const float* mrow = static_shift ? prm_sa + 384 + c0 : msm + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) kx[i] = valid ? ex2_ftz((kx[i] - mrow[i]) * 1.4426950408889634f) : 0.f;
+                    for (int i = 0; i < 32; ++i) kx[i] = ex2_ftz((kx[i] - mrow[i]) * 1.4426950408889634f);
+                    if constexpr (!kBf16) {
+                        if (!valid) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) kx[i] = 0.f;      // fp16: the padding rows were clamped to a finite value above
+                        }
+                    }
                     store_a16<kBf16>(eimg, r, c0, kx);
                     store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
                 }

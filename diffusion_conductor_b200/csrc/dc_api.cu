@@ -292,10 +292,11 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
-    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
-    DC_CUDA(h, cudaFuncSetAttribute(clip_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    void (*clip_variants[4])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>};
+    for (auto k : clip_variants) {
+        DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
+        DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
+    }
     return 0;
 }
 
@@ -425,8 +426,9 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     // one cluster of clip_nt CTAs per clip; the kernel keeps no global exchange state
     sa.nt = h->clip_nt;
     sa.rows_per = (h->T + h->clip_nt - 1) / h->clip_nt;
-    DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, h->bf16 ? clip_kernel<true> : clip_kernel<false>, dim3((unsigned)(h->B * h->clip_nt)),
-                         dim3(kTileThreads), kClipSmemBytes, st, sa));
+    void (*kern)(StepArgs) = h->timeline_on ? (h->bf16 ? clip_kernel<true, true> : clip_kernel<false, true>)
+                                            : (h->bf16 ? clip_kernel<true, false> : clip_kernel<false, false>);
+    DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, kern, dim3((unsigned)(h->B * h->clip_nt)), dim3(kTileThreads), kClipSmemBytes, st, sa));
     h->launches++;
     DC_CUDA(h, cudaGetLastError());
     return 0;
@@ -813,8 +815,8 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
             at.val.clusterDim.x = (unsigned)nt, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
             cfg.attrs = &at, cfg.numAttrs = 1;
             int nclusters = 0;
-            const cudaError_t qe = h->bf16 ? cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<true>, &cfg)
-                                           : cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<false>, &cfg);
+            const cudaError_t qe = h->bf16 ? cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<true, false>, &cfg)
+                                           : cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<false, false>, &cfg);
             if (qe != cudaSuccess || nclusters < 1) {
                 cudaGetLastError();
                 persist = false;
