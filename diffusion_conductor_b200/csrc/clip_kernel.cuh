@@ -93,6 +93,7 @@ struct ClipBarriers : LayerBarriers {
     uint64_t pull_done[2];              // peers -> this CTA: "I have finished reading your partial" (count nt - 1)
     uint64_t slice_ready[2];            // large clusters: "my merged slice of reduction seq is ready" (count nt - 1)
     uint64_t w1c_full;                  // the (W1 Wo_ca) image of the current layer has landed
+    uint64_t w_free;                    // row threads -> MMA issuer: y_ca has been read out of W, h16 . W1 may start (16 warp arrivals)
 };
 
 // kTl: instrumented build for dc_debug_timeline (the marks cost ~5 % of the instruction stream, so the production
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         mbar_init(smem_u32(&bars->aemb_ready), kRowWarps);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars->d_ready[i]), 1);
         mbar_init(smem_u32(&bars->w1c_full), 1);
+        mbar_init(smem_u32(&bars->w_free), kRowWarps);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->part_ready[i]), (uint32_t)max(nt - 1, 1));
             mbar_init(smem_u32(&bars->pull_done[i]), (uint32_t)max(nt - 1, 1));
@@ -219,8 +221,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     load(slab + a.off[kOWoSa], 2, 16384);
                     load(slab + a.off[kOWqCa], 2, 16384);
                     load(a.bd_ca + (size_t)clip * a.bd_ca_stride + (size_t)it * kAworkBytes, 2, 16384);
-                    load(slab + a.off[kOWoCa], 2, 16384);
                     load(slab + a.off[kOW1], 1, 16384);                            // both 8 KB k-blocks of W1 in one stage
+                    load(slab + a.off[kOWoCa], 2, 16384);
                     load(slab + a.off[kOW2], 1, 16384);
                     load(slab + a.off[kOWoFf], 2, 16384);
                 }
@@ -293,11 +295,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(201);   // h += . Wo_sa
                     wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(202);  // q_ca
                     wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(203);  // y = softmax(q) . blockdiag(A_ca)
-                    // h += a . Wo_ca, and -- the FFN has no pre-norm, so its up-projection is linear in the residual add --
-                    // u = (h + a . Wo_ca + bo) . W1 = h16 . W1 + a . (W1 Wo_ca) + const in the same breath: one round trip less
-                    wait_a(), gemm_b(2, 128, kColH, true, awork), tl.mark(204);
+                    // The FFN has no pre-norm, so its up-projection is linear in the residual add before it:
+                    //   u = (h + a . Wo_ca + bo) . W1 = h16 . W1 + a . (W1 Wo_ca) + const.
+                    // h16 . W1 is issued as soon as the row threads have read y_ca out of W (while they do the FiLM math);
+                    // h += a . Wo_ca and the a . (W1 Wo_ca) half follow when a is published: one round trip less per layer.
                     {
                         const uint32_t idesc64 = make_idesc<kBf16>(kTileRows, 64);
+                        mbar_wait(smem_u32(&bars->w_free), (uint32_t)(si * L + it) & 1u);
+                        tc_fence_after();
                         const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
                         ++itB;
                         mbar_wait(smem_u32(&bars->fullB[st]), ph);
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         const uint32_t b_base = smem_u32(ringB + st * kSB);
                         for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, smem_u32(xbuf) + k * kABlockBytes, b_base + k * 8192, idesc64, k > 0);
                         umma_commit(smem_u32(&bars->emptyB[st]));
+                        wait_a(), gemm_b(2, 128, kColH, true, awork), tl.mark(204);
                         mbar_wait(smem_u32(&bars->w1c_full), (uint32_t)(si * L + it) & 1u);
                         tc_fence_after();
                         for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, smem_u32(w1c) + k * 8192, idesc64, true);
@@ -464,6 +470,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 rows_wait(bars, 2, ph[2]); tl.mark(105);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
+                tc_fence_before();                                           // y_ca is in registers: W may take h16 . W1 now
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->w_free));
                 row_stats32(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(106);                                   // S = A_emb . We_ca
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
