@@ -2,7 +2,7 @@
 
 ncu's CLI source page only prints SASS; this joins it, instruction by instruction, with `nvdisasm -g` line info of
 the same kernel in the in-tree library (so the library must be the build that was profiled).
-usage: python tools/ncu_lines.py gpurun_out/clip_full.ncu-rep clip_kernelILb1 [n_top] [exec]
+usage: python tools/ncu_lines.py gpurun_out/clip_full.ncu-rep clip_kernelILb1ELb0E [n_top] [exec]
 columns: share of stall samples, share of warp instructions executed, warp instructions, source line"""
 import collections
 import csv
