@@ -19,7 +19,8 @@ DC_FLAG_CLIP = 0x10
 EXPORTS = [
     "dc_last_error", "dc_create", "dc_destroy", "dc_set_weight", "dc_finalize_weights", "dc_set_schedule",
     "dc_prepare_cond", "dc_forward", "dc_sample_step", "dc_sampler_update", "dc_sample_loop", "dc_generate_host",
-    "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step", "dc_debug_timeline",
+    "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step", "dc_debug_timeline", "dc_smooth_motion",
+    "dc_encode_music",
 ]
 
 
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
     lib.dc_kernel_launches.argtypes = [vp]
     lib.dc_set_graphs.argtypes = [vp, i32]
     lib.dc_selftest_gemm.argtypes = [i32, i32, i32, i32, i32, fp, fp, fp, fp]
+    lib.dc_encode_music.argtypes = [vp, fp, fp, fp, i32, i32, vp]
+    lib.dc_smooth_motion.argtypes = [i32, fp, fp, i32, i32, i32, i32, fp, fp, C.c_float, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("dc_last_error", "dc_destroy", "dc_kernel_launches"):

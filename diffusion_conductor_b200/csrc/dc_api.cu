@@ -16,6 +16,7 @@
 
 #include "../../include/dc_b200.h"
 #include "clip_kernel.cuh"
+#include "music_encoder.cuh"
 
 using namespace dc;
 
@@ -76,6 +77,14 @@ struct dc_handle {
     float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
     float *WlinT = nullptr, *blin = nullptr;
     float *teW0 = nullptr, *teb0 = nullptr, *teW2 = nullptr, *teb2 = nullptr, *freqs = nullptr;
+
+    // music encoder (BatchNorm folded): per 3x3 layer w [CIN][9][COUT], b [COUT]; conv2.0's 1x1 residual; conv4 + proj
+    bool has_music = false;
+    float* me_w[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* me_b[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *me_w1 = nullptr, *me_b1 = nullptr, *me_w4t = nullptr, *me_b4 = nullptr, *me_wpt = nullptr, *me_bp = nullptr;
+    float *me_buf0 = nullptr, *me_buf1 = nullptr;     // ping-pong activation planes for one chunk of clips
+    size_t me_cap = 0;                                // floats per buffer
 
     // schedule
     int S = 0;
@@ -540,6 +549,13 @@ void dc_destroy(dc_handle* h) {
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (int i = 0; i < 7; ++i) {
+        if (h->me_w[i]) cudaFree(h->me_w[i]);
+        if (h->me_b[i]) cudaFree(h->me_b[i]);
+    }
+    void* mptrs[] = {h->me_w1, h->me_b1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp, h->me_buf0, h->me_buf1};
+    for (void* p : mptrs)
+        if (p) cudaFree(p);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
 }
@@ -547,7 +563,7 @@ void dc_destroy(dc_handle* h) {
 int dc_set_weight(dc_handle* h, const char* key, const void* data, const int64_t* shape, int ndim) {
     if (!h || !key || !data || ndim < 0 || ndim > 4) return fail(h, DC_ERR_INVALID, "dc_set_weight: bad argument");
     const std::string k(key);
-    if (k.rfind("music_encoder.", 0) == 0 || k.rfind("proj.", 0) == 0) return 0;   // not on the denoise path
+    if (k.find("num_batches_tracked") != std::string::npos) return 0;              // BatchNorm bookkeeping, unused in eval mode
     HostTensor t;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) {
@@ -757,6 +773,69 @@ int dc_finalize_weights(dc_handle* h) {
             upload(h, &h->teb0, b0->v.data(), kE * 4) || upload(h, &h->teW2, W2->v.data(), W2->v.size() * 4) ||
             upload(h, &h->teb2, b2->v.data(), kE * 4) || upload(h, &h->freqs, freqs.data(), freqs.size() * 4))
             return DC_ERR_CUDA;
+    }
+    // music encoder front-end (optional: present whenever a full MotionTransformer state_dict was uploaded)
+    h->has_music = false;
+    if (h->w.count("music_encoder.conv1.0.conv2d_layer.0.weight")) {
+        const float eps = 1e-5f;       // torch BatchNorm default (reference transformer.py:298,304,327)
+        struct Spec { const char* name; int cin, cout; };
+        const Spec specs[7] = {{"conv1.0", 1, 16}, {"conv1.1", 16, 16}, {"conv1.2", 16, 16}, {"conv2.0", 16, 32},
+                               {"conv2.1", 32, 32}, {"conv3.0", 32, 32}, {"conv3.1", 32, 32}};
+        auto bn_scale = [&](const std::string& p, int n, std::vector<float>& sc, std::vector<float>& sh) -> int {
+            GET(g, p + ".weight", n);
+            GET(bt, p + ".bias", n);
+            GET(mu, p + ".running_mean", n);
+            GET(var, p + ".running_var", n);
+            sc.resize(n), sh.resize(n);
+            for (int i = 0; i < n; ++i) {
+                sc[i] = g->v[i] / std::sqrt(var->v[i] + eps);
+                sh[i] = bt->v[i] - mu->v[i] * sc[i];
+            }
+            return 0;
+        };
+        for (int li = 0; li < 7; ++li) {
+            const std::string p = std::string("music_encoder.") + specs[li].name;
+            const int ci = specs[li].cin, co = specs[li].cout;
+            GET(w, p + ".conv2d_layer.0.weight", co, ci, 3, 3);
+            GET(b, p + ".conv2d_layer.0.bias", co);
+            std::vector<float> sc, sh;
+            if (bn_scale(p + ".conv2d_layer.1", co, sc, sh)) return DC_ERR_INVALID;
+            std::vector<float> wf((size_t)ci * 9 * co), bf_(co);
+            for (int o = 0; o < co; ++o) {
+                bf_[o] = b->v[o] * sc[o] + sh[o];
+                for (int i = 0; i < ci; ++i)
+                    for (int t = 0; t < 9; ++t) wf[((size_t)i * 9 + t) * co + o] = w->v[((size_t)o * ci + i) * 9 + t] * sc[o];
+            }
+            if (upload(h, &h->me_w[li], wf.data(), wf.size() * 4) || upload(h, &h->me_b[li], bf_.data(), bf_.size() * 4)) return DC_ERR_CUDA;
+            if (ci != co && li > 0) {      // 1x1 residual convolution + BatchNorm (conv2.0)
+                GET(rw, p + ".residual.0.weight", co, ci, 1, 1);
+                GET(rb, p + ".residual.0.bias", co);
+                std::vector<float> rs, rh;
+                if (bn_scale(p + ".residual.1", co, rs, rh)) return DC_ERR_INVALID;
+                std::vector<float> w1((size_t)ci * co), b1(co);
+                for (int o = 0; o < co; ++o) {
+                    b1[o] = rb->v[o] * rs[o] + rh[o];
+                    for (int i = 0; i < ci; ++i) w1[(size_t)i * co + o] = rw->v[(size_t)o * ci + i] * rs[o];
+                }
+                if (upload(h, &h->me_w1, w1.data(), w1.size() * 4) || upload(h, &h->me_b1, b1.data(), b1.size() * 4)) return DC_ERR_CUDA;
+            }
+        }
+        GET(w4, "music_encoder.conv4.0.weight", kMusic, 512, 1);
+        GET(b4, "music_encoder.conv4.0.bias", kMusic);
+        std::vector<float> sc4, sh4;
+        if (bn_scale("music_encoder.conv4.1", kMusic, sc4, sh4)) return DC_ERR_INVALID;
+        GET(wp, "proj.weight", kMusic, kMusic);
+        GET(bp, "proj.bias", kMusic);
+        std::vector<float> w4t((size_t)512 * kMusic), b4f(kMusic), wpt((size_t)kMusic * kMusic);
+        for (int o = 0; o < kMusic; ++o) {
+            b4f[o] = b4->v[o] * sc4[o] + sh4[o];
+            for (int k = 0; k < 512; ++k) w4t[(size_t)k * kMusic + o] = w4->v[(size_t)o * 512 + k] * sc4[o];
+            for (int k = 0; k < kMusic; ++k) wpt[(size_t)k * kMusic + o] = wp->v[(size_t)o * kMusic + k];
+        }
+        if (upload(h, &h->me_w4t, w4t.data(), w4t.size() * 4) || upload(h, &h->me_b4, b4f.data(), b4f.size() * 4) ||
+            upload(h, &h->me_wpt, wpt.data(), wpt.size() * 4) || upload(h, &h->me_bp, bp->v.data(), kMusic * 4))
+            return DC_ERR_CUDA;
+        h->has_music = true;
     }
 #undef GET
     h->finalized = true;
@@ -1041,6 +1120,80 @@ int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out,
     DC_CUDA(h, cudaDeviceSynchronize());
     DC_CUDA(h, cudaMemcpy(out, h->timeline, std::min((size_t)max_launches * 512, words) * 8, cudaMemcpyDeviceToHost));
     (void)n;
+    return 0;
+}
+
+int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_out, int B, int Tm, void* stream) {
+    if (!h || !mel || !xf_proj || !xf_out || B < 1 || Tm < 1) return fail(h, DC_ERR_INVALID, "dc_encode_music: bad argument");
+    if (!h->finalized || !h->has_music) return fail(h, DC_ERR_STATE, "dc_encode_music: music_encoder.* / proj.* weights not loaded");
+    // MaxPool2d((5,5), stride (3,2), pad 2) maps Tm mel frames to (Tm - 1) / 3 + 1 motion frames; the 3x3 reflect padding
+    // needs at least 2 rows at every stage (torch raises otherwise)
+    const int T = (Tm - 1) / 3 + 1;
+    if (Tm < 2 || T < 2) return fail(h, DC_ERR_INVALID, "dc_encode_music: %d mel frames are too few for the reflect-padded convolutions", Tm);
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int kBins = 128;
+    const size_t per_clip = (size_t)16 * Tm * kBins;                  // floats of the largest activation (16 x Tm x 128 == 32 x Tm x 64)
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)1 << 28) / per_clip));   // <= 1 GiB per buffer
+    if ((size_t)chunk * per_clip > h->me_cap) {
+        if (h->me_buf0) cudaFree(h->me_buf0);
+        if (h->me_buf1) cudaFree(h->me_buf1);
+        h->me_buf0 = h->me_buf1 = nullptr, h->me_cap = 0;
+        DC_CUDA(h, cudaMalloc((void**)&h->me_buf0, (size_t)chunk * per_clip * 4));
+        DC_CUDA(h, cudaMalloc((void**)&h->me_buf1, (size_t)chunk * per_clip * 4));
+        h->me_cap = (size_t)chunk * per_clip;
+    }
+    float *p0 = h->me_buf0, *p1 = h->me_buf1;
+    auto conv_grid = [](int H, int W, int nb) { return dim3((unsigned)((W + kCvTW - 1) / kCvTW), (unsigned)((H + kCvTH - 1) / kCvTH), (unsigned)nb); };
+    auto pool = [&](const float* src, float* dst, int planes, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int& Ho, int& Wo) {
+        Ho = (H + 2 * PH - KH) / SH + 1, Wo = (W + 2 * PW - KW) / SW + 1;
+        const long n = (long)planes * Ho * Wo;
+        maxpool2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, H, W, Ho, Wo, KH, KW, SH, SW, PH, PW);
+        h->launches++;
+    };
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
+        int H = Tm, W = kBins, Ho, Wo;
+        conv3x3_bn_relu_kernel<1, 16, 0><<<conv_grid(H, W, nb), 256, 0, st>>>(m0, p0, h->me_w[0], h->me_b[0], nullptr, nullptr, H, W);
+        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[1], h->me_b[1], nullptr, nullptr, H, W);
+        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[2], h->me_b[2], nullptr, nullptr, H, W);
+        pool(p0, p1, nb * 16, H, W, 5, 5, 1, 2, 2, 2, Ho, Wo);
+        H = Ho, W = Wo;
+        conv3x3_bn_relu_kernel<16, 32, 2><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[3], h->me_b[3], h->me_w1, h->me_b1, H, W);
+        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[4], h->me_b[4], nullptr, nullptr, H, W);
+        pool(p1, p0, nb * 32, H, W, 5, 5, 3, 2, 2, 2, Ho, Wo);
+        H = Ho, W = Wo;
+        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[5], h->me_b[5], nullptr, nullptr, H, W);
+        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[6], h->me_b[6], nullptr, nullptr, H, W);
+        pool(p0, p1, nb * 32, H, W, 3, 3, 1, 2, 1, 1, Ho, Wo);
+        H = Ho, W = Wo;                                               // (nb, 32, T, 16)
+        if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
+        const long M = (long)nb * T;
+        conv4_proj_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
+                                                                                   xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, nb, T);
+        h->launches += 8;
+    }
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int dc_smooth_motion(int device, const float* motion, float* out, int B, int T, int C, int window, const float* fir, const float* edge,
+                     float scale, void* stream) {
+    if (!motion || !out || !fir || !edge || B < 1 || T < 1 || C < 1) return fail(nullptr, DC_ERR_INVALID, "dc_smooth_motion: bad argument");
+    if (window < 3 || !(window & 1) || window > kSavgolMaxWindow)
+        return fail(nullptr, DC_ERR_INVALID, "dc_smooth_motion: window must be odd, 3 <= window <= %d", kSavgolMaxWindow);
+    if (T < window) return fail(nullptr, DC_ERR_INVALID, "dc_smooth_motion: window=%d exceeds the %d frames (scipy mode='interp' requires window <= size)", window, T);
+    DC_CUDA(nullptr, cudaSetDevice(device));
+    SavgolCoef cf{};
+    cf.window = window;
+    cf.scale = scale;
+    for (int j = 0; j < window; ++j) cf.fir[j] = fir[j];
+    for (int i = 0; i < window / 2; ++i)
+        for (int j = 0; j < window; ++j) cf.edge[i][j] = edge[(size_t)i * window + j];
+    const long n = (long)B * T * C;
+    savgol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(motion, out, B, T, C, cf);
+    DC_CUDA(nullptr, cudaGetLastError());
     return 0;
 }
 

@@ -409,6 +409,39 @@ __global__ void sampler_update_kernel(const float* __restrict__ x0, size_t n, in
     x[i] = (mode & 0xF) == 1 ? ddim_rule(x[i], x0[i], cf, nz) : ddpm_rule(x[i], x0[i], cf, nz);
 }
 
+// Post-processing of generated motion (reference Diffusion_Stage/tools/visualization.py:20-26,107-126):
+// keypoints * window (pixels), then scipy.signal.savgol_filter(data, kernel, order) along time for each of the
+// C coordinates (mode='interp': the first / last kernel/2 frames are evaluated from the polynomial fitted to the
+// first / last `kernel` frames).  Both are linear maps with host-computed coefficients: an interior FIR and a
+// [kernel/2][kernel] edge matrix (the tail uses it time-reversed).
+constexpr int kSavgolMaxWindow = 31;
+struct SavgolCoef {
+    int window;                                            // odd, <= kSavgolMaxWindow
+    float scale;                                           // applied to the input (reference: motions[i] *= 600)
+    float fir[kSavgolMaxWindow];
+    float edge[kSavgolMaxWindow / 2][kSavgolMaxWindow];
+};
+
+__global__ void savgol_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int C, const __grid_constant__ SavgolCoef cf) {
+    const long n = (long)B * T * C;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int c = (int)(idx % C);
+    const int t = (int)((idx / C) % T);
+    const long base = (idx / ((long)C * T)) * (long)T * C + c;      // element (b, 0, c)
+    const int half = cf.window / 2;
+    float acc = 0.f;
+    if (t < half) {
+        for (int j = 0; j < cf.window; ++j) acc = fmaf(cf.edge[t][j], x[base + (long)j * C] * cf.scale, acc);
+    } else if (t >= T - half) {
+        const int i = T - 1 - t;
+        for (int j = 0; j < cf.window; ++j) acc = fmaf(cf.edge[i][j], x[base + (long)(T - 1 - j) * C] * cf.scale, acc);
+    } else {
+        for (int j = 0; j < cf.window; ++j) acc = fmaf(cf.fir[j], x[base + (long)(t - half + j) * C] * cf.scale, acc);
+    }
+    y[idx] = acc;
+}
+
 __global__ void set_step_kernel(int* ctr, int value, int delta) {
     pdl_trigger();
     pdl_wait();

@@ -91,3 +91,54 @@ def generate_music_motion(model, diffusion, music_mel, dim_pose: int = 26, lengt
     if len(idxs):
         return sample_fn(mel, None, noise, length)
     return sharded_sample(sample_fn, mel, mel, noise, length, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# Post-processing on device: reference tools/visualization.py:20-26 (smooth_motion) and
+# :107-126 (vis_motion: reshape to (T, 13, 2), * window pixels, Savitzky-Golay kernel 19 / order 5).
+# ------------------------------------------------------------------------------------------------
+def savgol_matrices(kernel: int, order: int):
+    """(fir [kernel], edge [kernel // 2, kernel]) of scipy.signal.savgol_filter(x, kernel, order) with its default
+    mode='interp': the interior is a symmetric FIR (least-squares polynomial evaluated at the window centre); the first
+    kernel // 2 frames are the polynomial fitted to the first `kernel` frames evaluated at frames 0 .. kernel // 2 - 1
+    (the tail is the time-reversed mirror image).  Computed in float64 with numpy only."""
+    import numpy as np
+
+    if kernel % 2 != 1 or kernel < 3:
+        raise ValueError("kernel must be an odd integer >= 3")
+    if order >= kernel:
+        raise ValueError("polyorder must be less than window_length.")       # scipy's message
+    pos = np.arange(kernel, dtype=np.float64)
+    A = np.vander(pos, order + 1, increasing=True)                            # [kernel, order + 1]
+    H = A @ np.linalg.pinv(A)                                                 # hat matrix: fitted value at pos i <- data
+    half = kernel // 2
+    return H[half].copy(), H[:half].copy()
+
+
+def smooth_motion(motion: torch.Tensor, kernel: int = 19, order: int = 5, window: float = 600.0) -> torch.Tensor:
+    """Batched, on-device version of the reference post-processing: motion (B, T, 26) or (T, 26) keypoints in [0, 1]
+    -> (B, T, 13, 2) pixel coordinates, Savitzky-Golay-smoothed along time (reference smooth_motion is called with
+    kernel=19, order=5 after `motions[i] *= 600`, visualization.py:117-120).  Runs in the CUDA library; there is no
+    CPU path."""
+    from . import _lib
+
+    squeeze = motion.dim() == 2
+    m = motion.unsqueeze(0) if squeeze else motion
+    if not m.is_cuda:
+        raise RuntimeError("smooth_motion runs on the CUDA device only (there is no CPU fallback)")
+    B, T, C_ = m.shape
+    if T < kernel:
+        raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")   # scipy's message
+    fir, edge = savgol_matrices(kernel, order)
+    import numpy as np
+
+    fir32 = np.ascontiguousarray(fir, dtype=np.float32)
+    edge32 = np.ascontiguousarray(edge, dtype=np.float32)
+    x = m.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.dc_smooth_motion(x.device.index or 0, x.data_ptr(), out.data_ptr(), B, T, C_, kernel, fir32.ctypes.data, edge32.ctypes.data,
+                              float(window), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, None)
+    out = out.view(B, T, C_ // 2, 2)
+    return out[0] if squeeze else out

@@ -255,13 +255,22 @@ class MotionTransformer(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------
     def encode_music(self, text, device):
-        with torch.no_grad():
-            x = self.music_encoder(text)
-        if self.training:      # 10 % per-frame condition dropout (reference :451-456)
+        """mel (B, 3T, 128) -> (xf_proj, xf_out), each (B, T, 64) (reference :447-459).  Eval mode runs the M2SNet CNN and
+        `proj` in the CUDA library (dc_encode_music, exact fp32).  Training mode (10 % per-frame condition dropout,
+        reference :451-456) is outside the sampling path and keeps the plain PyTorch modules."""
+        if self.training:
+            with torch.no_grad():
+                x = self.music_encoder(text)
             b, t, _ = x.shape
             mask = torch.bernoulli(torch.ones((b, t), device=device) * self.cond_mask_prob).view((b, t, 1))
             x = x * (1 - mask)
-        return self.proj(x), x
+            return self.proj(x), x
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("encode_music runs on the CUDA device only (there is no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return self.engine(dev).encode_music(torch.as_tensor(text))
 
     def generate_src_mask(self, T, length):
         ar = torch.arange(T)[None, :]
@@ -324,7 +333,7 @@ class _Engine:
         sd = dict(sd)
         sd["aux.timestep_freqs"] = timestep_frequencies(model.latent_dim)
         for key, val in sd.items():
-            if key.startswith("music_encoder.") or key.startswith("proj."):
+            if key.endswith("num_batches_tracked"):
                 continue
             t = val.detach().to(torch.float32).contiguous()
             shape = (C.c_int64 * t.dim())(*t.shape)
@@ -362,6 +371,20 @@ class _Engine:
         self._cond_key = key
         self._keepalive = (xf_proj, xf_out)
         self.B, self.T = B, T
+
+    def encode_music(self, mel: torch.Tensor):
+        """dc_encode_music: mel (B, Tm, 128) -> (xf_proj, xf_out) (B, T, 64) on this engine's device."""
+        dev = torch.device("cuda", self.device_index)
+        if mel.dim() != 3 or mel.shape[2] != 128:
+            raise ValueError(f"mel must be (B, 3T, 128), got {tuple(mel.shape)}")
+        m = self._f32(mel, dev)
+        B, Tm = int(m.shape[0]), int(m.shape[1])
+        T = (Tm - 1) // 3 + 1
+        xf_proj = torch.empty(B, T, 64, device=dev)
+        xf_out = torch.empty(B, T, 64, device=dev)
+        with torch.cuda.device(dev):
+            self._ck(self.lib.dc_encode_music(self.handle, m.data_ptr(), xf_proj.data_ptr(), xf_out.data_ptr(), B, Tm, self.stream()))
+        return xf_proj, xf_out
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         x = self._f32(x, self.device)

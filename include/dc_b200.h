@@ -61,8 +61,8 @@ int dc_create(const dc_config* cfg, dc_handle** out);
 void dc_destroy(dc_handle* h);
 
 /* load_state_dict (ddpm_trainer.py:303-319): one call per state_dict key; `data` may be a host or a
- * device pointer to fp32 (copied immediately).  Keys outside the hot path (music_encoder.*, proj.*)
- * are accepted and ignored.  "aux.timestep_freqs" [latent_dim/2] overrides the built-in frequency
+ * device pointer to fp32 (copied immediately).  music_encoder.* and proj.* feed dc_encode_music
+ * (optional: the denoising entry points work without them); *.num_batches_tracked is ignored.  "aux.timestep_freqs" [latent_dim/2] overrides the built-in frequency
  * table of timestep_embedding (transformer.py:18-20) with the host-computed one. */
 int dc_set_weight(dc_handle* h, const char* key, const void* data, const int64_t* shape, int ndim);
 /* Folds LayerNorm affines, permutes FiLM rows, converts and packs every matrix into tcgen05
@@ -115,6 +115,20 @@ int dc_profile_step(dc_handle* h, int sampler, float* x, int step, float* ms_out
 /* Debug aid: runs one denoise step with the layer kernel recording a (clock64, event id) timeline of its
  * CTA 0; out is HOST [max_launches][512] u64: per launch [0] = event count, then (cycle, id) pairs. */
 int dc_debug_timeline(dc_handle* h, float* x, int step, unsigned long long* out, int max_launches);
+
+/* MotionTransformer.encode_music in eval mode (transformer.py:447-459) = MusicEncoder.forward (transformer.py:313-340: seven
+ * reflect-padded 3x3 Conv2dResLayers with BatchNorm + ReLU, three max-pools, Conv1d 512 -> 64 + BatchNorm1d) followed by `proj`.
+ * mel: DEVICE [B][Tm][128] (Tm = 3 T mel frames at 90 Hz); xf_proj, xf_out: DEVICE [B][T][64], T = (Tm - 1) / 3 + 1.  Needs the
+ * music_encoder.* and proj.* keys of the state_dict (dc_set_weight); exact fp32 arithmetic. */
+int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_out, int B, int Tm, void* stream);
+
+/* smooth_motion + pixel scaling of vis_motion (Diffusion_Stage/tools/visualization.py:20-26, 107-126): for every clip and each of
+ * the C coordinates, out = savgol_filter(motion * scale, window, order) along time (scipy mode='interp').  motion, out: DEVICE
+ * [B][T][C] (out must not alias motion).  fir: HOST [window] interior coefficients, edge: HOST [window/2][window] rows i = value at
+ * frame i of the polynomial fitted to the first `window` frames (the tail uses the same rows time-reversed); both are computed by
+ * the host layer from (window, order).  Stateless: no handle. */
+int dc_smooth_motion(int device, const float* motion, float* out, int B, int T, int C, int window, const float* fir, const float* edge,
+                     float scale, void* stream);
 
 /* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
 int64_t dc_kernel_launches(const dc_handle* h);

@@ -84,3 +84,39 @@ def test_c1_music_encoder_and_trajectory(golden_dir):
     final, x0s, _ = O.sample_loop(sd, tb, noise, [180], torch.from_numpy(g["xf_proj"]), torch.from_numpy(g["xf_out"]))
     np.testing.assert_allclose(torch.stack(x0s).numpy(), g["ddim_x0"], rtol=0, atol=5e-5)
     np.testing.assert_allclose(final.numpy(), g["final"], rtol=0, atol=5e-5)
+
+
+def test_postprocess_oracle_reproduces_polynomials():
+    """Known answers of Savitzky-Golay smoothing (visualization.py:20-26): a polynomial of degree <= order is a fixed
+    point everywhere, edges included; white noise is attenuated."""
+    from oracle import postprocess_oracle as PO
+
+    T = 60
+    t = np.linspace(0.0, 1.0, T)
+    poly = 0.3 + 0.2 * t - 0.5 * t ** 2 + 0.1 * t ** 5
+    motion = np.tile(poly[:, None], (1, 26)).astype(np.float64)[None]
+    out = PO.vis_motion_keypoints(motion, window=600, kernel=19)
+    assert out.shape == (1, T, 13, 2)
+    assert np.allclose(out[0, :, 4, 1], 600 * poly, atol=1e-8)
+    rng = np.random.default_rng(0)
+    noise = rng.standard_normal((1, 200, 26))
+    sm = PO.vis_motion_keypoints(noise, window=1.0, kernel=19)
+    assert sm.std() < 0.75 * noise.std()
+
+
+def test_savgol_matrices_match_scipy():
+    """The host-side coefficient builder (numpy only) against scipy: interior FIR == savgol_coeffs, and the full filter
+    assembled from (fir, edge) == savgol_filter(mode='interp') on random data."""
+    from scipy.signal import savgol_coeffs, savgol_filter
+
+    from diffusion_conductor_b200.generate import savgol_matrices
+
+    for kernel, order in ((19, 5), (11, 5), (7, 2), (31, 3)):
+        fir, edge = savgol_matrices(kernel, order)
+        assert np.allclose(fir, savgol_coeffs(kernel, order)[::-1], atol=1e-12)
+        half = kernel // 2
+        x = np.random.default_rng(kernel).standard_normal(kernel + 23)
+        y = np.convolve(x, fir[::-1], mode="same")
+        y[:half] = edge @ x[:kernel]
+        y[-half:] = (edge @ x[::-1][:kernel])[::-1]
+        assert np.allclose(y, savgol_filter(x, kernel, order), atol=1e-10)
