@@ -248,6 +248,34 @@ def main():
     e2e_value = motion_seconds / (float(t.item()) / args.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- the once-per-clip conditioning: music encoder (mel -> features) and the step-invariant precompute, timed
+    # with CUDA events; and the whole generate_music_motion-equivalent call from a pinned host mel to a host motion array
+    mel, _ = synth_inputs(B, T, seed=100 + rank)
+    hmel = mel.pin_memory()
+    mel_d = mel.to(dev)
+    cond = {}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for i in range(3):
+        ev[0].record()
+        fp, fo = model.encode_music(mel_d, dev)
+        ev[1].record()
+        eng.prepare(fp, fo, [T] * B, B, T)
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        cond = {"encode_music_ms": round(ev[0].elapsed_time(ev[1]), 3), "prepare_cond_ms": round(ev[1].elapsed_time(ev[2]), 3)}
+    t0 = 0.0
+    for it in range(6):
+        if it == 1:                                                                   # iteration 0 is the warm-up
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+        fp, fo = model.encode_music(hmel.to(dev, non_blocking=True), dev)            # what generate_music_motion does per rank
+        out = diff.ddim_sample_loop(model, (B, T, 26), noise=noise_d, clip_denoised=False,
+                                    model_kwargs=dict(xf_proj=fp, xf_out=fo, length=[T] * B))
+        hout.copy_(out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    cond["e2e_from_mel_motion_s_per_s"] = round((B * T / 30.0) / ((time.perf_counter() - t0) / 5), 2)
+    cond["mel_h2d_bytes"] = hmel.numel() * 4
+
     # ---- roofline of the dominant kernel, timed live with CUDA events
     pk = peaks()
     chunked = hasattr(plan, "bounds")
@@ -316,7 +344,7 @@ def main():
                        "token_steps_per_step": B * T * S, "l2": "256 MiB buffer written between timed iterations",
                        "collective": "NCCL all_gather of the generated motion" if world > 1 else "none"},
             "e2e": {"value": round(e2e_value, 2), "unit": "motion-s/s", "h2d_bytes_per_step": n_in, "d2h_bytes_per_step": hout.numel() * 4},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "conditioning": cond,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
