@@ -80,9 +80,12 @@ struct dc_handle {
 
     // music encoder (BatchNorm folded): per 3x3 layer w [CIN][9][COUT], b [COUT]; conv2.0's 1x1 residual; conv4 + proj
     bool has_music = false;
-    float* me_w[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* me_b[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float *me_w1 = nullptr, *me_b1 = nullptr, *me_w4t = nullptr, *me_b4 = nullptr, *me_wpt = nullptr, *me_bp = nullptr;
+    // 3x3 layers: HOST copies of the per-(layer, 16-channel group) weight structs, passed by value at launch
+    ConvWeights<1, false> me_c10;
+    ConvWeights<16, false> me_c11, me_c12;
+    ConvWeights<16, true> me_c20[2];
+    ConvWeights<32, false> me_c21[2], me_c30[2], me_c31[2];
+    float *me_w4t = nullptr, *me_b4 = nullptr, *me_wpt = nullptr, *me_bp = nullptr;
     float *me_buf0 = nullptr, *me_buf1 = nullptr;     // ping-pong activation planes for one chunk of clips
     size_t me_cap = 0;                                // floats per buffer
 
@@ -549,11 +552,7 @@ void dc_destroy(dc_handle* h) {
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    for (int i = 0; i < 7; ++i) {
-        if (h->me_w[i]) cudaFree(h->me_w[i]);
-        if (h->me_b[i]) cudaFree(h->me_b[i]);
-    }
-    void* mptrs[] = {h->me_w1, h->me_b1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp, h->me_buf0, h->me_buf1};
+    void* mptrs[] = {h->me_w4t, h->me_b4, h->me_wpt, h->me_bp, h->me_buf0, h->me_buf1};
     for (void* p : mptrs)
         if (p) cudaFree(p);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -793,33 +792,40 @@ int dc_finalize_weights(dc_handle* h) {
             }
             return 0;
         };
-        for (int li = 0; li < 7; ++li) {
+        auto fill = [&](int li, int grp, float* wdst, float* bdst, float* w1dst, float* b1dst) -> int {
             const std::string p = std::string("music_encoder.") + specs[li].name;
             const int ci = specs[li].cin, co = specs[li].cout;
             GET(w, p + ".conv2d_layer.0.weight", co, ci, 3, 3);
             GET(b, p + ".conv2d_layer.0.bias", co);
             std::vector<float> sc, sh;
             if (bn_scale(p + ".conv2d_layer.1", co, sc, sh)) return DC_ERR_INVALID;
-            std::vector<float> wf((size_t)ci * 9 * co), bf_(co);
-            for (int o = 0; o < co; ++o) {
-                bf_[o] = b->v[o] * sc[o] + sh[o];
+            for (int q = 0; q < kCvCo; ++q) {
+                const int o = grp * kCvCo + q;
+                bdst[q] = b->v[o] * sc[o] + sh[o];
                 for (int i = 0; i < ci; ++i)
-                    for (int t = 0; t < 9; ++t) wf[((size_t)i * 9 + t) * co + o] = w->v[((size_t)o * ci + i) * 9 + t] * sc[o];
+                    for (int t = 0; t < 9; ++t) wdst[((size_t)i * 9 + t) * kCvCo + q] = w->v[((size_t)o * ci + i) * 9 + t] * sc[o];
             }
-            if (upload(h, &h->me_w[li], wf.data(), wf.size() * 4) || upload(h, &h->me_b[li], bf_.data(), bf_.size() * 4)) return DC_ERR_CUDA;
-            if (ci != co && li > 0) {      // 1x1 residual convolution + BatchNorm (conv2.0)
+            if (w1dst) {                   // 1x1 residual convolution + BatchNorm (conv2.0)
                 GET(rw, p + ".residual.0.weight", co, ci, 1, 1);
                 GET(rb, p + ".residual.0.bias", co);
                 std::vector<float> rs, rh;
                 if (bn_scale(p + ".residual.1", co, rs, rh)) return DC_ERR_INVALID;
-                std::vector<float> w1((size_t)ci * co), b1(co);
-                for (int o = 0; o < co; ++o) {
-                    b1[o] = rb->v[o] * rs[o] + rh[o];
-                    for (int i = 0; i < ci; ++i) w1[(size_t)i * co + o] = rw->v[(size_t)o * ci + i] * rs[o];
+                for (int q = 0; q < kCvCo; ++q) {
+                    const int o = grp * kCvCo + q;
+                    b1dst[q] = rb->v[o] * rs[o] + rh[o];
+                    for (int i = 0; i < ci; ++i) w1dst[(size_t)i * kCvCo + q] = rw->v[(size_t)o * ci + i] * rs[o];
                 }
-                if (upload(h, &h->me_w1, w1.data(), w1.size() * 4) || upload(h, &h->me_b1, b1.data(), b1.size() * 4)) return DC_ERR_CUDA;
             }
-        }
+            return 0;
+        };
+        if (fill(0, 0, h->me_c10.w, h->me_c10.b, nullptr, nullptr) || fill(1, 0, h->me_c11.w, h->me_c11.b, nullptr, nullptr) ||
+            fill(2, 0, h->me_c12.w, h->me_c12.b, nullptr, nullptr))
+            return DC_ERR_INVALID;
+        for (int g2 = 0; g2 < 2; ++g2)
+            if (fill(3, g2, h->me_c20[g2].w, h->me_c20[g2].b, h->me_c20[g2].w1, h->me_c20[g2].b1) ||
+                fill(4, g2, h->me_c21[g2].w, h->me_c21[g2].b, nullptr, nullptr) || fill(5, g2, h->me_c30[g2].w, h->me_c30[g2].b, nullptr, nullptr) ||
+                fill(6, g2, h->me_c31[g2].w, h->me_c31[g2].b, nullptr, nullptr))
+                return DC_ERR_INVALID;
         GET(w4, "music_encoder.conv4.0.weight", kMusic, 512, 1);
         GET(b4, "music_encoder.conv4.0.bias", kMusic);
         std::vector<float> sc4, sh4;
@@ -1155,24 +1161,24 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
         int H = Tm, W = kBins, Ho, Wo;
-        conv3x3_bn_relu_kernel<1, 16, 0><<<conv_grid(H, W, nb), 256, 0, st>>>(m0, p0, h->me_w[0], h->me_b[0], nullptr, nullptr, H, W);
-        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[1], h->me_b[1], nullptr, nullptr, H, W);
-        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[2], h->me_b[2], nullptr, nullptr, H, W);
+        conv3x3_bn_relu_kernel<1, 16, 0><<<conv_grid(H, W, nb), 256, 0, st>>>(m0, p0, H, W, 0, h->me_c10);
+        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, 0, h->me_c11);
+        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, 0, h->me_c12);
         pool(p0, p1, nb * 16, H, W, 5, 5, 1, 2, 2, 2, Ho, Wo);
         H = Ho, W = Wo;
-        conv3x3_bn_relu_kernel<16, 32, 2><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[3], h->me_b[3], h->me_w1, h->me_b1, H, W);
-        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[4], h->me_b[4], nullptr, nullptr, H, W);
+        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<16, 32, 2><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c20[g2]);
+        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c21[g2]);
         pool(p1, p0, nb * 32, H, W, 5, 5, 3, 2, 2, 2, Ho, Wo);
         H = Ho, W = Wo;
-        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, h->me_w[5], h->me_b[5], nullptr, nullptr, H, W);
-        conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, h->me_w[6], h->me_b[6], nullptr, nullptr, H, W);
+        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c30[g2]);
+        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c31[g2]);
         pool(p0, p1, nb * 32, H, W, 3, 3, 1, 2, 1, 1, Ho, Wo);
         H = Ho, W = Wo;                                               // (nb, 32, T, 16)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;
         conv4_proj_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
                                                                                    xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, nb, T);
-        h->launches += 8;
+        h->launches += 12;
     }
     DC_CUDA(h, cudaGetLastError());
     return 0;

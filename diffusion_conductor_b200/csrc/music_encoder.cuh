@@ -6,8 +6,8 @@
 // the weights on the host, ReLU, identity / 1x1-conv residuals, three max-pools, then a 512 -> 64 pointwise convolution
 // (+ folded BatchNorm1d) and the 64 -> 64 `proj` Linear.  Channel counts this small do not fill a tensor-core tile and
 // the features condition every denoise step, so this stays exact fp32 on the CUDA cores: direct convolution, input tile +
-// weight chunk staged in shared memory, every thread accumulates 2 pixels x all output channels in registers (64 FFMA per
-// 2 + 8 shared-memory loads).  Activations are NCHW fp32; 0.94 GMAC per 6 s clip.
+// tile staged in shared memory, weights in the constant bank (kernel parameter), every thread accumulates 4 pixels x 16 output
+// channels in registers.  Activations are NCHW fp32; 0.94 GMAC per 6 s clip.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -20,77 +20,93 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {      // torch padding
 }
 
 constexpr int kCvTH = 16, kCvTW = 32, kCvChunk = 8;             // output tile (time x bins), input-channel chunk in shared memory
+constexpr int kCvCo = 16;                                       // output channels per CTA
+
+// Folded weights of one (layer, group of 16 output channels), passed BY VALUE as a kernel parameter (<= 32 KB): they live in
+// the constant bank, every weight is warp-uniform, so the compiler feeds the FFMAs from uniform registers (ULDC) and the
+// load/store unit only serves the input pixels -- with the weights in shared memory the kernel was LSU-bound at 28 % of the
+// fp32 peak.
+template <int CIN, bool kRes>
+struct alignas(16) ConvWeights {
+    float w[CIN * 9 * kCvCo];                    // [cin][tap][co]; read as float4 (one 128-bit uniform load per 4 weights)
+    float b[kCvCo];
+    float w1[kRes ? CIN * kCvCo : 1];            // 1x1 residual convolution [cin][co] (RES == 2 only)
+    float b1[kRes ? kCvCo : 1];
+};
 
 // y = ReLU(conv3x3_reflect(x) * s + b') (+ x | + conv1x1(x) * s1 + b1')     RES: 0 none, 1 identity, 2 1x1 convolution
-// x [B][CIN][H][W], y [B][COUT][H][W]; w [CIN][9][COUT] and w1 [CIN][COUT] with the BatchNorm scale folded in.
+// x [B][CIN][H][W], y [B][COUT][H][W]; one launch per group `grp` of 16 output channels; blockIdx.z = clip.
 template <int CIN, int COUT, int RES>
-__global__ void __launch_bounds__(256) conv3x3_bn_relu_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
-                                                              const float* __restrict__ b, const float* __restrict__ w1,
-                                                              const float* __restrict__ b1, int H, int W) {
+__global__ void __launch_bounds__(256) conv3x3_bn_relu_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int grp,
+                                                              const __grid_constant__ ConvWeights<CIN, RES == 2> cw) {
     constexpr int CC = CIN < kCvChunk ? CIN : kCvChunk;
     __shared__ float s_in[CC][kCvTH + 2][kCvTW + 2];
-    __shared__ __align__(16) float s_w[CC * 9 * COUT];
     const int bi = blockIdx.z, h0 = blockIdx.y * kCvTH, w0 = blockIdx.x * kCvTW;
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;     // rows ty and ty + 8 of the tile
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;     // rows ty, ty + 8, ty + 16, ty + 24 of the tile
     const float* xb = x + (size_t)bi * CIN * H * W;
-    float acc[2][COUT];
+    constexpr int NP = kCvTH / 8;                                  // pixels per thread: every weight (a uniform-register operand) feeds NP FFMAs
+    float acc[NP][kCvCo];
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < NP; ++p)
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[p][c] = 0.f;
+        for (int c = 0; c < kCvCo; ++c) acc[p][c] = 0.f;
 
-    for (int c0 = 0; c0 < CIN; c0 += CC) {
-        __syncthreads();
-        for (int i = tid; i < CC * (kCvTH + 2) * (kCvTW + 2); i += 256) {
-            const int c = i / ((kCvTH + 2) * (kCvTW + 2)), r = (i / (kCvTW + 2)) % (kCvTH + 2), q = i % (kCvTW + 2);
-            s_in[c][r][q] = __ldg(xb + ((size_t)(c0 + c) * H + reflect_idx(h0 - 1 + r, H)) * W + reflect_idx(w0 - 1 + q, W));
-        }
-        for (int i = tid; i < CC * 9 * COUT; i += 256) s_w[i] = __ldg(w + (size_t)c0 * 9 * COUT + i);
-        __syncthreads();
-#pragma unroll 1
-        for (int c = 0; c < CC; ++c) {
+    {
+        for (int c0 = 0; c0 < CIN; c0 += CC) {
+            __syncthreads();
+            for (int i = tid; i < CC * (kCvTH + 2) * (kCvTW + 2); i += 256) {
+                const int c = i / ((kCvTH + 2) * (kCvTW + 2)), r = (i / (kCvTW + 2)) % (kCvTH + 2), q = i % (kCvTW + 2);
+                s_in[c][r][q] = __ldg(xb + ((size_t)(c0 + c) * H + reflect_idx(h0 - 1 + r, H)) * W + reflect_idx(w0 - 1 + q, W));
+            }
+            __syncthreads();
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
+            for (int c = 0; c < CC; ++c) {
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float v0 = s_in[c][ty + dy][tx + dx], v1 = s_in[c][ty + 8 + dy][tx + dx];
-                    const float4* wp = reinterpret_cast<const float4*>(s_w + (c * 9 + dy * 3 + dx) * COUT);
+                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                    for (int q = 0; q < COUT / 4; ++q) {
-                        const float4 w4 = wp[q];
-                        acc[0][4 * q] = fmaf(v0, w4.x, acc[0][4 * q]), acc[0][4 * q + 1] = fmaf(v0, w4.y, acc[0][4 * q + 1]);
-                        acc[0][4 * q + 2] = fmaf(v0, w4.z, acc[0][4 * q + 2]), acc[0][4 * q + 3] = fmaf(v0, w4.w, acc[0][4 * q + 3]);
-                        acc[1][4 * q] = fmaf(v1, w4.x, acc[1][4 * q]), acc[1][4 * q + 1] = fmaf(v1, w4.y, acc[1][4 * q + 1]);
-                        acc[1][4 * q + 2] = fmaf(v1, w4.z, acc[1][4 * q + 2]), acc[1][4 * q + 3] = fmaf(v1, w4.w, acc[1][4 * q + 3]);
+                    for (int dx = 0; dx < 3; ++dx) {
+                        float vin[NP];
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) vin[p] = s_in[c][ty + 8 * p + dy][tx + dx];
+                        const float4* wp = reinterpret_cast<const float4*>(cw.w + ((c0 + c) * 9 + dy * 3 + dx) * kCvCo);
+#pragma unroll
+                        for (int q4 = 0; q4 < kCvCo / 4; ++q4) {
+                            const float4 w4 = wp[q4];
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                acc[p][4 * q4] = fmaf(vin[p], w4.x, acc[p][4 * q4]), acc[p][4 * q4 + 1] = fmaf(vin[p], w4.y, acc[p][4 * q4 + 1]);
+                                acc[p][4 * q4 + 2] = fmaf(vin[p], w4.z, acc[p][4 * q4 + 2]), acc[p][4 * q4 + 3] = fmaf(vin[p], w4.w, acc[p][4 * q4 + 3]);
+                            }
+                        }
                     }
                 }
             }
         }
-    }
-    const int gw = w0 + tx;
+        const int gw = w0 + tx;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int gh = h0 + ty + 8 * p;
-        if (gh >= H || gw >= W) continue;
-        const size_t pix = (size_t)gh * W + gw;
+        for (int p = 0; p < NP; ++p) {
+            const int gh = h0 + ty + 8 * p;
+            if (gh >= H || gw >= W) continue;
+            const size_t pix = (size_t)gh * W + gw;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[p][c] = fmaxf(acc[p][c] + __ldg(b + c), 0.f);
-        if constexpr (RES == 1) {
+            for (int c = 0; c < kCvCo; ++c) acc[p][c] = fmaxf(acc[p][c] + cw.b[c], 0.f);
+            if constexpr (RES == 1) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[p][c] += __ldg(xb + (size_t)c * H * W + pix);
-        } else if constexpr (RES == 2) {
+                for (int c = 0; c < kCvCo; ++c) acc[p][c] += __ldg(xb + (size_t)(grp * kCvCo + c) * H * W + pix);
+            } else if constexpr (RES == 2) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[p][c] += __ldg(b1 + c);
-#pragma unroll 1
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float xv = __ldg(xb + (size_t)ci * H * W + pix);
+                for (int c = 0; c < kCvCo; ++c) acc[p][c] += cw.b1[c];
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[p][c] = fmaf(xv, __ldg(w1 + ci * COUT + c), acc[p][c]);
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float xv = __ldg(xb + (size_t)ci * H * W + pix);
+#pragma unroll
+                    for (int c = 0; c < kCvCo; ++c) acc[p][c] = fmaf(xv, cw.w1[ci * kCvCo + c], acc[p][c]);
+                }
             }
-        }
-        float* yb = y + (size_t)bi * COUT * H * W + pix;
+            float* yb = y + ((size_t)bi * COUT + grp * kCvCo) * H * W + pix;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) yb[(size_t)c * H * W] = acc[p][c];
+            for (int c = 0; c < kCvCo; ++c) yb[(size_t)c * H * W] = acc[p][c];
+        }
     }
 }
 
