@@ -1140,7 +1140,8 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int kBins = 128;
     const size_t per_clip = (size_t)16 * Tm * kBins;                  // floats of the largest activation (16 x Tm x 128 == 32 x Tm x 64)
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)1 << 28) / per_clip));   // <= 1 GiB per buffer
+    // clips per pass: <= 1 GiB per activation buffer, and 32 planes per clip must fit gridDim.z of the pooling kernels
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)B, 2047), ((size_t)1 << 28) / per_clip));
     if ((size_t)chunk * per_clip > h->me_cap) {
         if (h->me_buf0) cudaFree(h->me_buf0);
         if (h->me_buf1) cudaFree(h->me_buf1);
@@ -1151,12 +1152,7 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
     }
     float *p0 = h->me_buf0, *p1 = h->me_buf1;
     auto conv_grid = [](int H, int W, int nb) { return dim3((unsigned)((W + kCvTW - 1) / kCvTW), (unsigned)((H + kCvTH - 1) / kCvTH), (unsigned)nb); };
-    auto pool = [&](const float* src, float* dst, int planes, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int& Ho, int& Wo) {
-        Ho = (H + 2 * PH - KH) / SH + 1, Wo = (W + 2 * PW - KW) / SW + 1;
-        const long n = (long)planes * Ho * Wo;
-        maxpool2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, H, W, Ho, Wo, KH, KW, SH, SW, PH, PW);
-        h->launches++;
-    };
+    auto pool_grid = [](int Ho, int Wo, int planes) { return dim3((unsigned)((Wo + kMpTW - 1) / kMpTW), (unsigned)((Ho + kMpTH - 1) / kMpTH), (unsigned)planes); };
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
@@ -1164,21 +1160,24 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv3x3_bn_relu_kernel<1, 16, 0><<<conv_grid(H, W, nb), 256, 0, st>>>(m0, p0, H, W, 0, h->me_c10);
         conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, 0, h->me_c11);
         conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, 0, h->me_c12);
-        pool(p0, p1, nb * 16, H, W, 5, 5, 1, 2, 2, 2, Ho, Wo);
+        Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
+        maxpool2d_kernel<5, 5, 1, 2, 2, 2><<<pool_grid(Ho, Wo, nb * 16), 256, 0, st>>>(p0, p1, H, W, Ho, Wo);
         H = Ho, W = Wo;
         for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<16, 32, 2><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c20[g2]);
         for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c21[g2]);
-        pool(p1, p0, nb * 32, H, W, 5, 5, 3, 2, 2, 2, Ho, Wo);
+        Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
+        maxpool2d_kernel<5, 5, 3, 2, 2, 2><<<pool_grid(Ho, Wo, nb * 32), 256, 0, st>>>(p1, p0, H, W, Ho, Wo);
         H = Ho, W = Wo;
         for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c30[g2]);
         for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c31[g2]);
-        pool(p0, p1, nb * 32, H, W, 3, 3, 1, 2, 1, 1, Ho, Wo);
+        Ho = (H + 2 - 3) / 1 + 1, Wo = (W + 2 - 3) / 2 + 1;           // MaxPool2d((3,3), stride (1,2), padding 1)
+        maxpool2d_kernel<3, 3, 1, 2, 1, 1><<<pool_grid(Ho, Wo, nb * 32), 256, 0, st>>>(p0, p1, H, W, Ho, Wo);
         H = Ho, W = Wo;                                               // (nb, 32, T, 16)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;
         conv4_proj_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
                                                                                    xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, nb, T);
-        h->launches += 12;
+        h->launches += 15;
     }
     DC_CUDA(h, cudaGetLastError());
     return 0;

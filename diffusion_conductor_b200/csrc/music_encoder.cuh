@@ -110,24 +110,39 @@ __global__ void __launch_bounds__(256) conv3x3_bn_relu_kernel(const float* __res
     }
 }
 
-// torch.nn.MaxPool2d (implicit -inf padding): x [N][H][W] -> y [N][Ho][Wo], N = B * C planes
-__global__ void maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, long n_out, int H, int W, int Ho, int Wo, int KH, int KW,
-                                 int SH, int SW, int PH, int PW) {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_out) return;
-    const int wo = (int)(idx % Wo), ho = (int)((idx / Wo) % Ho);
-    const long plane = idx / ((long)Wo * Ho);
-    const float* xp = x + plane * (long)H * W;
-    float m = -INFINITY;
-    for (int i = 0; i < KH; ++i) {
-        const int h = ho * SH - PH + i;
-        if (h < 0 || h >= H) continue;
-        for (int j = 0; j < KW; ++j) {
-            const int w_ = wo * SW - PW + j;
-            if (w_ >= 0 && w_ < W) m = fmaxf(m, __ldg(xp + (long)h * W + w_));
-        }
+// torch.nn.MaxPool2d (implicit -inf padding): x [N][H][W] -> y [N][Ho][Wo], N = B * C planes.  One CTA per 16 x 32 tile of
+// outputs: the input window is staged once in shared memory (coalesced rows), then a separable max (along bins, then along
+// time), so every input element is read from HBM/L2 once instead of up to 25 times.
+constexpr int kMpTH = 16, kMpTW = 32;
+template <int KH, int KW, int SH, int SW, int PH, int PW>
+__global__ void __launch_bounds__(256) maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int Ho, int Wo) {
+    constexpr int IH = (kMpTH - 1) * SH + KH, IW = (kMpTW - 1) * SW + KW;
+    __shared__ float s_in[IH][IW + 1];
+    __shared__ float s_row[IH][kMpTW];
+    const int ho0 = blockIdx.y * kMpTH, wo0 = blockIdx.x * kMpTW, tid = threadIdx.x;
+    const float* xp = x + (size_t)blockIdx.z * H * W;
+    const int h_in0 = ho0 * SH - PH, w_in0 = wo0 * SW - PW;
+    for (int i = tid; i < IH * IW; i += 256) {
+        const int r = i / IW, q = i % IW, h = h_in0 + r, w_ = w_in0 + q;
+        s_in[r][q] = (h >= 0 && h < H && w_ >= 0 && w_ < W) ? __ldg(xp + (size_t)h * W + w_) : -INFINITY;
     }
-    y[idx] = m;
+    __syncthreads();
+    for (int i = tid; i < IH * kMpTW; i += 256) {
+        const int r = i / kMpTW, c = i % kMpTW;
+        float m = s_in[r][c * SW];
+#pragma unroll
+        for (int j = 1; j < KW; ++j) m = fmaxf(m, s_in[r][c * SW + j]);
+        s_row[r][c] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < kMpTH * kMpTW; i += 256) {
+        const int oh = i / kMpTW, c = i % kMpTW;
+        if (ho0 + oh >= Ho || wo0 + c >= Wo) continue;
+        float m = s_row[oh * SH][c];
+#pragma unroll
+        for (int k = 1; k < KH; ++k) m = fmaxf(m, s_row[oh * SH + k][c]);
+        y[((size_t)blockIdx.z * Ho + ho0 + oh) * Wo + wo0 + c] = m;
+    }
 }
 
 // h3 [B][32][T][16] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded BatchNorm1d)
