@@ -632,6 +632,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             rows_wait(bars, 2, ph[2]);
             tl.mark(112);
             {
+                // every row warp has published its LayerNorm output (the QKV MMAs needed all 16 arrivals), so nobody reads the
+                // parameters of layer `it` any more: fetch the next layer's block asynchronously, it lands long before it is used
+                const float4* pn4 = reinterpret_cast<const float4*>(a.prm + (size_t)(it + 1) * kPrmFloats);
+                static_assert(kPrmFloats % 4 == 0 && kPrmFloats / 4 <= 2 * kRowThreads, "parameter block layout");
+                cp_async16(reinterpret_cast<float4*>(prm) + threadIdx.x, pn4 + threadIdx.x);
+                if (threadIdx.x + kRowThreads < kPrmFloats / 4) cp_async16(reinterpret_cast<float4*>(prm) + threadIdx.x + kRowThreads, pn4 + threadIdx.x + kRowThreads);
+            }
+            {
                 // Time-axis softmax + K^T V (reference :111,:117) on the tensor cores, one clip per cluster.  Two 32 KB
                 // operand-image buffers X (xbuf), Y (ring B) are all the scratch it needs:
                 //   k (16-bit) -> X ; column maxima by a column scan of X ; E = exp(k - max) -> X ; V -> Y ;
@@ -746,7 +754,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     softmax16(qv + 16);
                     store_a16<kBf16>(awork, r, c0, qv);
                     store_a16<kBf16>(awork, r, c0 + 16, qv + 16);
-                    named_bar_sync(5, kRowThreads);                    // E image complete (all rows published)
+                    named_bar_sync(5, kRowThreads);                    // E image complete (all rows published); prm_sa is dead
+                    if (it + 2 < L && tx < 128)                         // SA biases + static key shift of layer it + 2
+                        cp_async16(reinterpret_cast<float4*>(prm_sa) + tx,
+                                   tx < 96 ? reinterpret_cast<const float4*>(a.prm + (size_t)(it + 2) * kPrmFloats) + tx
+                                           : reinterpret_cast<const float4*>(a.kshift + (size_t)(it + 2) * kD) + (tx - 96));
                     float2 s0 = make_float2(0.f, 0.f);                  // column sums from the rounded E
 #pragma unroll
                     for (int rr = 0; rr < 16; ++rr) {
@@ -784,20 +796,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
                 }
                 // ---- while the peers' partials are in flight: clear the image buffer (the merge writes only the diagonal
-                //      blocks) and fetch the next layer's parameters; all loads issued before the first store
+                //      blocks); the parameter blocks fetched with cp.async above must have landed before the barrier below
                 {
-                    const float4* pn4 = reinterpret_cast<const float4*>(a.prm + (size_t)(it + 1) * kPrmFloats);
-                    static_assert(kPrmFloats % 4 == 0 && kPrmFloats / 4 <= 2 * kRowThreads, "parameter block layout");
-                    const float4 p0 = __ldg(pn4 + tx);
-                    const float4 p1 = tx + kRowThreads < kPrmFloats / 4 ? __ldg(pn4 + tx + kRowThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 p2 = (it + 2 < L && tx < 96) ? __ldg(pn4 + kPrmFloats / 4 + tx)
-                                      : (it + 2 < L && tx < 128) ? __ldg(reinterpret_cast<const float4*>(a.kshift + (size_t)(it + 2) * kD) + (tx - 96))
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                     const uint4 z4 = make_uint4(0, 0, 0, 0);
                     for (int i = tx; i < kAworkBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(xbuf)[i] = z4;
-                    reinterpret_cast<float4*>(prm)[tx] = p0;
-                    if (tx + kRowThreads < kPrmFloats / 4) reinterpret_cast<float4*>(prm)[tx + kRowThreads] = p1;
-                    if (it + 2 < L && tx < 128) reinterpret_cast<float4*>(prm_sa)[tx] = p2;
+                    cp_async_wait_all();
                 }
                 if (nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
                 named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared

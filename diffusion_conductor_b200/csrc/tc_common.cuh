@@ -282,6 +282,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// ---------------------------------------------------------------- Ampere-style async copy global -> smem (no register staging)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- distributed shared memory (one cluster = one clip)
 // Writer: plain st.shared of the payload, CTA barrier, then ONE thread fences at cluster scope and arrives on the
 // peers' mbarriers.  Reader: one thread waits with acquire.cluster, CTA barrier, then everyone pulls with
