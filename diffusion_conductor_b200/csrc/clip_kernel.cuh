@@ -42,7 +42,7 @@ struct StepArgs {
     const float* WjT;           // [26][128] joint_embed weight, transposed
     const float* bj;            // [128]
     const float* pos;           // [num_frames][128] sequence_embedding
-    const float* WoT;           // [128][32] output head, transposed + padded
+    const uint8_t* wout_img;    // output head `out` as a [32 x 128] K-major operand image (rows >= 26 zero), 8 KB
     const float* bo;            // [32]
     uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
     const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     load(slab + a.off[kOWoCa], 2, 16384);
                     load(slab + a.off[kOW2], 1, 16384);
                     load(slab + a.off[kOWoFf], 2, 16384);
+                    if (it + 1 == L) load(a.wout_img, 1, 8192);                    // output head: both 4 KB k-blocks in one stage
                 }
                 if (it + 1 < L) load(a.wbuf + ((size_t)(it + 1) << 20) + a.off[kOWq], 2, 16384);
             }
@@ -318,6 +319,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     done(2), tl.mark(205);
                     wait_a(), gemm_b(1, 128, kColW, false, awork), done(2), tl.mark(206);  // FFN down
                     wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(207);   // h += . Wo_ffn
+                }
+                if (it + 1 == L) {
+                    // output head (reference :496): pred_x0 = h . Wout^T as one N = 32 GEMM on the 16-bit image of the final h
+                    const uint32_t idesc32 = make_idesc<kBf16>(kTileRows, 32);
+                    wait_a();
+                    const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
+                    ++itB;
+                    mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                    tc_fence_after();
+                    const uint32_t b_base = smem_u32(ringB + st * kSB);
+                    for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, b_base + k * 4096, idesc32, k > 0);
+                    umma_commit(smem_u32(&bars->emptyB[st]));
+                    done(2), tl.mark(210);
                 }
                 if (it + 1 < L) {
                     wait_a();
@@ -516,75 +530,44 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 if (it + 1 < L) tmem_st32(trow + kColH + c0, v);        // h keeps living in TMEM
             }
             if (it + 1 == L) {
-                // ---- step epilogue (reference transformer.py:496, gaussian_diffusion.py:812-830 / 605-665):
-                //      pred_x0 = h . Wout^T + b (fp32), sampler update of x.  Scratch: the operand buffers (partial dot
-                //      products) and the parameter block (output head); the rings are left alone -- the producers are
-                //      already streaming the next step's first weights.
-                float* part = reinterpret_cast<float*>(awork_p);          // [4 cq][128 rows][28] (awork | xbuf, 64 KB)
-                float* sWo = prm;                                         // [128][32] over prm | prm_sa | xchg | red
-                float* sbo = sWo + kD * 32;                               // [32]
-                static_assert(4 * kTileRows * 28 * 4 <= 2 * kAworkBytes, "partials fit awork | xbuf");
-                static_assert(kD * 32 + 32 <= kPrmFloats + 512 + 1024 + kClipRedFloats, "output head fits the parameter block");
-                const int tx = threadIdx.x;
-                const int nel = nrows * kP;
+                // ---- step epilogue (reference transformer.py:496, gaussian_diffusion.py:812-830 / 605-665): the output head runs
+                //      on the tensor core like every other Linear of the model (16-bit operands, fp32 accumulate); each of the
+                //      four threads of a row then owns 8 of the 32 accumulator columns (26 valid): bias, clamp, sampler update.
+                store_a16<kBf16>(awork, r, c0, v);
+                store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+                rows_publish<false>(a_ready_addr, lane);
                 const int smode = a.mode & 0xF;
                 const float* nzp = a.noise != nullptr ? a.noise + (size_t)si * a.noise_stride : nullptr;
-                {
-                    const float4* wo4 = reinterpret_cast<const float4*>(a.WoT);
-                    const float4 w0 = __ldg(wo4 + tx), w1 = __ldg(wo4 + tx + kRowThreads);
-                    const float tb = tx < kP ? __ldg(a.bo + tx) : 0.f;
-                    named_bar_sync(5, kRowThreads);                        // every thread has read its last bias from prm
-                    reinterpret_cast<float4*>(sWo)[tx] = w0, reinterpret_cast<float4*>(sWo)[tx + kRowThreads] = w1;
-                    if (tx < 32) sbo[tx] = tb;
+                const int p0 = (int)cq * 8, np = valid ? min(8, kP - p0) : 0;           // this thread's outputs p0 .. p0 + np - 1
+                const size_t e0 = (size_t)(row0g + r) * kP + p0;
+                float xo[8], nz[8], bo8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                                           // in flight while the head GEMM runs
+                    xo[i] = (smode != 0 && i < np) ? __ldcg(x_src + e0 + i) : 0.f;
+                    nz[i] = (smode != 0 && nzp != nullptr && i < np) ? __ldcg(nzp + e0 + i) : 0.f;
+                    bo8[i] = __ldg(a.bo + p0 + i);
                 }
-                named_bar_sync(5, kRowThreads);
-                {
-                    uint64_t acc[14];
+                const float* cf = smode != 0 ? a.coef + (size_t)tstep * 8 : nullptr;
+                float* x0p = a.x0_out + (size_t)si * a.x0_stride;
+                rows_wait(bars, 2, ph[2]);
+                float o8[8];
+                tmem_ld8(trow + kColW + p0, o8);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int p = 0; p < 14; ++p) acc[p] = 0ull;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sWo + (size_t)(c0 + i) * 32);
-                        const uint64_t hv = pk2(v[i], v[i]);
-#pragma unroll
-                        for (int q4 = 0; q4 < 7; ++q4) {
-                            const ulonglong2 wv = w2[q4];
-                            acc[2 * q4] = ffma2(hv, wv.x, acc[2 * q4]), acc[2 * q4 + 1] = ffma2(hv, wv.y, acc[2 * q4 + 1]);
-                        }
-                    }
-#pragma unroll
-                    for (int p4 = 0; p4 < 7; ++p4)
-                        *reinterpret_cast<ulonglong2*>(part + ((size_t)cq * kTileRows + r) * 28 + 4 * p4) = make_ulonglong2(acc[2 * p4], acc[2 * p4 + 1]);
-                }
-                {   // nrows x 26 outputs over 512 threads; x and noise are in flight while the partials settle
-                    float to[7], tn[7];
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const int i = tx + j * kRowThreads;
-                        to[j] = (smode != 0 && i < nel) ? __ldcg(x_src + row0g * kP + i) : 0.f;
-                        tn[j] = (smode != 0 && nzp != nullptr && i < nel) ? __ldcg(nzp + row0g * kP + i) : 0.f;
-                    }
-                    named_bar_sync(5, kRowThreads);
-                    const float* cf = smode != 0 ? a.coef + (size_t)tstep * 8 : nullptr;
-                    float* x0p = a.x0_out + (size_t)si * a.x0_stride;
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        const int i = tx + j * kRowThreads;
-                        if (i < nel) {
-                            const int rr = i / kP, p = i - rr * kP;
-                            float x0 = sbo[p] + ((part[(0 * kTileRows + rr) * 28 + p] + part[(1 * kTileRows + rr) * 28 + p]) +
-                                                 (part[(2 * kTileRows + rr) * 28 + p] + part[(3 * kTileRows + rr) * 28 + p]));
-                            if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                            x0p[row0g * kP + i] = x0;
-                            if (smode != 0) {
-                                const float xn = smode == 1 ? ddim_rule(to[j], x0, cf, tn[j]) : ddpm_rule(to[j], x0, cf, tn[j]);
-                                a.x_out[row0g * kP + i] = xn;
-                                if (a.x_trace != nullptr) a.x_trace[(size_t)si * a.M * kP + row0g * kP + i] = xn;
-                            }
+                for (int i = 0; i < 8; ++i) {
+                    if (i < np) {
+                        float x0 = o8[i] + bo8[i];
+                        if (a.mode & 0x10) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                        x0p[e0 + i] = x0;
+                        if (smode != 0) {
+                            const float xn = smode == 1 ? ddim_rule(xo[i], x0, cf, nz[i]) : ddpm_rule(xo[i], x0, cf, nz[i]);
+                            a.x_out[e0 + i] = xn;
+                            if (a.x_trace != nullptr) a.x_trace[(size_t)si * a.M * kP + e0 + i] = xn;
                         }
                     }
                 }
-                named_bar_sync(5, kRowThreads);                            // the scratch is the next step's staging area
+                tc_fence_before();
+                named_bar_sync(5, kRowThreads);                            // x of this tile is complete before the next step stages it
                 break;
             }
 
