@@ -39,7 +39,7 @@ struct StepArgs {
     int te_stride, te_step_stride;
     const float* coef;          // [S][8] update coefficients, row = timestep index; null when mode == 0
     int mode;                   // 0: model output only, 1: DDIM, 2: DDPM, | 0x10 clamp
-    const float* WjT;           // [26][128] joint_embed weight, transposed
+    const uint8_t* wj_img;      // joint_embed as a [128 x 64] K-major operand image: k 0..25 = W, k 32..57 = W again (x is fed as hi | lo)
     const float* bj;            // [128]
     const float* pos;           // [num_frames][128] sequence_embedding
     const uint8_t* wout_img;    // output head `out` as a [32 x 128] K-major operand image (rows >= 26 zero), 8 KB
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             uint32_t qf = 0;
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
+                if (it < 0) load(a.wj_img, 1, 16384);                             // joint_embed, first GEMM of the step
                 if (it >= 0) {
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
                     // ring B held the V image and then this tile's partial of the reduction that opened layer `it`:
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             const uint32_t idesc128 = make_idesc<kBf16>(kTileRows, 128);
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
+                if (it < 0) wait_a(), gemm_b(1, 128, kColH, false, awork), done(1), tl.mark(211);   // h0 = [x_hi | x_lo] . Wj2^T
                 if (it >= 0) {
                     wait_a();                                                      // merged attention image written by the row threads
                     for (int k = 0; k < 2; ++k)                                    // y = q . blockdiag(A_sa)
@@ -378,67 +380,50 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         for (int si = 0; si < a.n_steps; ++si) {
         const int tstep = a.step0 - si;                                  // timestep index of this step
         const float* x_src = si == 0 ? a.x_in : a.x_out;
-        // ---- step prologue (reference transformer.py:482,488-490): this tile's A_emb = SiLU(te + xp) image -> global
-        //      (streamed back 24 times by ring A), h0 = joint_embed(x) + sequence_embedding -> TMEM (stays there for the
-        //      whole step).  Small operands are staged through the k-image buffer (idle until the first reduction).
+        // ---- step prologue (reference transformer.py:482,488-490): h0 = joint_embed(x) + sequence_embedding -> TMEM (stays
+        //      there for the whole step).  joint_embed runs on the tensor core like every other Linear; x itself is NOT rounded:
+        //      it is fed as a (hi, lo) pair of 16-bit values in the two halves of one 64-wide k-block against [W | W], which
+        //      reproduces the fp32 input to 2^-17.  This tile's A_emb image follows after the first LayerNorm (below).
         {
-            float* sWj = reinterpret_cast<float*>(xbuf);                  // [26][128]
-            float* sbj = sWj + kP * kD;                                   // [128]
-            float* sx = sbj + kD;                                         // [128][26] x rows of this tile
-            float* ste = sx + kTileRows * kP;                             // [512] time embedding of the clip
+            float* ste = reinterpret_cast<float*>(xbuf) + kP * kD + kD + kTileRows * kP;   // [512] time embedding of the clip (read by the A_emb build)
             const int tx = threadIdx.x;
-            {   // every global load of the staging phase is issued before the first store (one L2 round trip)
-                float tw[7], tv[7];
-                const int xlim = nrows * kP;
+            const int p0 = (int)cq * 8, np = valid ? min(8, kP - p0) : 0;                  // this thread's slice of its x row
+            float xv[8];
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const int i = tx + j * kRowThreads;
-                    tw[j] = i < kP * kD ? __ldg(a.WjT + i) : 0.f;
-                    tv[j] = i < xlim ? __ldcg(x_src + row0g * kP + i) : 0.f;
-                }
-                const float tt = __ldcg(a.te + (size_t)tstep * a.te_step_stride + (size_t)clip * a.te_stride + tx);
-                const float tb = tx < kD ? __ldg(a.bj + tx) : 0.f;
-                const float4 psa = tx < 96 ? __ldg(reinterpret_cast<const float4*>(a.prm) + tx)                                      // SA biases of layer 0
-                                   : tx < 128 ? __ldg(reinterpret_cast<const float4*>(a.kshift) + (tx - 96)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) xv[i] = i < np ? __ldcg(x_src + (size_t)(row0g + r) * kP + p0 + i) : 0.f;
+            const float tt = __ldcg(a.te + (size_t)tstep * a.te_step_stride + (size_t)clip * a.te_stride + tx);
+            const float4 psa = tx < 96 ? __ldg(reinterpret_cast<const float4*>(a.prm) + tx)                                      // SA biases of layer 0
+                               : tx < 128 ? __ldg(reinterpret_cast<const float4*>(a.kshift) + (tx - 96)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hi[i] = pack2<kBf16>(xv[2 * i], xv[2 * i + 1]);
+                const float2 back = unpack2<kBf16>(hi[i]);
+                lo[i] = pack2<kBf16>(xv[2 * i] - back.x, xv[2 * i + 1] - back.y);
+            }
+            *reinterpret_cast<uint4*>(awork_p + sw128_offset(r, cq)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(awork_p + sw128_offset(r, cq + 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            ste[tx] = tt;
+            if (tx < 128) reinterpret_cast<float4*>(prm_sa)[tx] = psa;
+            rows_publish<false>(a_ready_addr, lane);
+            tl.mark(128);
+            // sequence embedding + bias of this thread's 32 features, in flight while the GEMM runs
+            float pb[32];
+            {
                 const float4* ps4 = reinterpret_cast<const float4*>(a.pos + (size_t)t * kD + c0);
+                const float4* bj4 = reinterpret_cast<const float4*>(a.bj + c0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 pv = valid ? __ldg(ps4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * i] = pv.x, v[4 * i + 1] = pv.y, v[4 * i + 2] = pv.z, v[4 * i + 3] = pv.w;
+                    const float4 bv = __ldg(bj4 + i);
+                    pb[4 * i] = pv.x + bv.x, pb[4 * i + 1] = pv.y + bv.y, pb[4 * i + 2] = pv.z + bv.z, pb[4 * i + 3] = pv.w + bv.w;
                 }
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const int i = tx + j * kRowThreads;
-                    if (i < kP * kD) sWj[i] = tw[j], sx[i] = tv[j];
-                }
-                ste[tx] = tt;
-                if (tx < kD) sbj[tx] = tb;
-                if (tx < 128) reinterpret_cast<float4*>(prm_sa)[tx] = psa;
             }
-            named_bar_sync(5, kRowThreads);
-            tl.mark(128);
-            // h0 for this thread's 32 features (v already holds the sequence embedding)
-            {
-                uint64_t hv[16];
+            rows_wait(bars, 1, ph[1]);
+            tmem_ld32(trow + kColH + c0, v);
+            tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 bv = *reinterpret_cast<const float4*>(sbj + c0 + 4 * i);
-                    hv[2 * i] = pk2(bv.x + v[4 * i], bv.y + v[4 * i + 1]), hv[2 * i + 1] = pk2(bv.z + v[4 * i + 2], bv.w + v[4 * i + 3]);
-                }
-#pragma unroll 2
-                for (int c = 0; c < kP; ++c) {
-                    const float xc = sx[r * kP + c];
-                    const uint64_t xc2 = pk2(xc, xc);
-                    const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sWj + c * kD + c0);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const ulonglong2 wv = w2[i];
-                        hv[2 * i] = ffma2(xc2, wv.x, hv[2 * i]), hv[2 * i + 1] = ffma2(xc2, wv.y, hv[2 * i + 1]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) upk2(hv[i], v[2 * i], v[2 * i + 1]);
-            }
+            for (int i = 0; i < 32; ++i) v[i] += pb[i];
             tmem_st32(trow + kColH + c0, v);
             tmem_wait_st();
             tl.mark(129);

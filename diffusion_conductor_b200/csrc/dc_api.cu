@@ -75,6 +75,7 @@ struct dc_handle {
     uint8_t* wkv = nullptr;       // [L][8][256 x 128 B] folded cross-attention K|V weights
     float* bkv = nullptr;         // [L][256]
     float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
+    uint8_t* wj_img = nullptr;    // joint_embed as a [128 x 64] operand image, k 0..25 and 32..57 both = W (x is fed as hi | lo)
     uint8_t* wout_img = nullptr;  // output head as a [32 x 128] operand image (persistent kernel: the head runs on the tensor core)
     float *WlinT = nullptr, *blin = nullptr;
     float *teW0 = nullptr, *teb0 = nullptr, *teW2 = nullptr, *teb2 = nullptr, *freqs = nullptr;
@@ -431,7 +432,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     sa.te = te, sa.te_stride = te_stride, sa.te_step_stride = te_step_stride;
     sa.coef = (mode & 0xF) ? h->coef : nullptr;
     sa.mode = mode;
-    sa.WjT = h->WjT, sa.bj = h->bj, sa.pos = h->pos, sa.wout_img = h->wout_img, sa.bo = h->bo;
+    sa.wj_img = h->wj_img, sa.bj = h->bj, sa.pos = h->pos, sa.wout_img = h->wout_img, sa.bo = h->bo;
     const uint32_t offs[12] = {kOffWeSa, kOffWoSa, kOffWeCa, kOffWqCa, kOffWoCa, kOffWeFf, kOffW1, kOffW2, kOffWoFf, kOffWq, kOffWk, kOffWv};
     for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
     sa.timeline = h->timeline_on ? h->timeline : nullptr;
@@ -549,7 +550,7 @@ void dc_destroy(dc_handle* h) {
     cudaSetDevice(h->cfg.device);
     drop_graph(h);
     free_workspace(h);
-    void* ptrs[] = {h->wbuf, h->prm, h->prm_clip, h->wfuse, h->kshift, h->wout_img, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
+    void* ptrs[] = {h->wbuf, h->prm, h->prm_clip, h->wfuse, h->kshift, h->wout_img, h->wj_img, h->wkv, h->bkv, h->WjT, h->bj, h->pos, h->WoT, h->bo, h->WlinT, h->blin,
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -756,6 +757,14 @@ int dc_finalize_weights(dc_handle* h) {
         for (int pI = 0; pI < kP; ++pI)
             for (int j = 0; j < kD; ++j) WoT[(size_t)j * 32 + pI] = Wo->v[(size_t)pI * kD + j];
         for (int pI = 0; pI < kP; ++pI) bo32[pI] = bo->v[pI];
+        {
+            std::vector<float> wj2((size_t)kD * 64, 0.f);
+            for (int n = 0; n < kD; ++n)
+                for (int k = 0; k < kP; ++k) wj2[(size_t)n * 64 + k] = wj2[(size_t)n * 64 + 32 + k] = Wj->v[(size_t)n * kP + k];
+            std::vector<uint8_t> img((size_t)kD * 128, 0);
+            pack_image(img.data(), wj2.data(), 64, 64, nullptr, nullptr, kD, 1, bf);
+            if (upload(h, &h->wj_img, img.data(), img.size())) return DC_ERR_CUDA;
+        }
         {
             std::vector<uint8_t> img(2 * 32 * 128, 0);
             int rows32[32];
