@@ -39,10 +39,10 @@ struct StepArgs {
     int te_stride, te_step_stride;
     const float* coef;          // [S][8] update coefficients, row = timestep index; null when mode == 0
     int mode;                   // 0: model output only, 1: DDIM, 2: DDPM, | 0x10 clamp
-    const uint8_t* wj_img;      // joint_embed as a [128 x 64] K-major operand image: k 0..25 = W, k 32..57 = W again (x is fed as hi | lo)
+    const uint8_t* wj_img;      // joint_embed as a [128 x 128] K-major operand image: k 0..25 = W_hi, 32..57 = W_hi, 64..89 = W_lo (x is fed as hi | lo | hi)
     const float* bj;            // [128]
     const float* pos;           // [num_frames][128] sequence_embedding
-    const uint8_t* wout_img;    // output head `out` as a [32 x 128] K-major operand image (rows >= 26 zero), 8 KB
+    const uint8_t* wout_img;    // output head `out` as a [32 x 384] K-major operand image [W_hi | W_hi | W_lo] (rows >= 26 zero), 24 KB
     const float* bo;            // [32]
     uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
     const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             uint32_t qf = 0;
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
-                if (it < 0) load(a.wj_img, 1, 16384);                             // joint_embed, first GEMM of the step
+                if (it < 0) load(a.wj_img, 2, 16384);                             // joint_embed [W_hi | W_hi], [W_lo | 0]: first GEMM of the step
                 if (it >= 0) {
                     const uint8_t* slab = a.wbuf + ((size_t)it << 20);
                     // ring B held the V image and then this tile's partial of the reduction that opened layer `it`:
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     load(slab + a.off[kOWoCa], 2, 16384);
                     load(slab + a.off[kOW2], 1, 16384);
                     load(slab + a.off[kOWoFf], 2, 16384);
-                    if (it + 1 == L) load(a.wout_img, 1, 8192);                    // output head: both 4 KB k-blocks in one stage
+                    if (it + 1 == L) load(a.wout_img, 1, 16384), load(a.wout_img + 16384, 1, 8192);   // output head [W_hi | W_hi], [W_lo]: 4 + 2 k-blocks of 4 KB
                 }
                 if (it + 1 < L) load(a.wbuf + ((size_t)(it + 1) << 20) + a.off[kOWq], 2, 16384);
             }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             const uint32_t idesc128 = make_idesc<kBf16>(kTileRows, 128);
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
-                if (it < 0) wait_a(), gemm_b(1, 128, kColH, false, awork), done(1), tl.mark(211);   // h0 = [x_hi | x_lo] . Wj2^T
+                if (it < 0) wait_a(), gemm_b(2, 128, kColH, false, awork), done(1), tl.mark(211);   // h0 = [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T
                 if (it >= 0) {
                     wait_a();                                                      // merged attention image written by the row threads
                     for (int k = 0; k < 2; ++k)                                    // y = q . blockdiag(A_sa)
@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(207);   // h += . Wo_ffn
                 }
                 if (it + 1 == L) {
-                    // output head (reference :496): pred_x0 = h . Wout^T as one N = 32 GEMM on the 16-bit image of the final h
+                    // output head (reference :496): pred_x0 = [h_hi | h_lo | h_hi] . [W_hi | W_hi | W_lo]^T, N = 32, K = 384: both the
+                    // final residual stream and the weights enter as (hi, lo) pairs of 16-bit values (fp32-equivalent to 2^-16)
                     const uint32_t idesc32 = make_idesc<kBf16>(kTileRows, 32);
                     wait_a();
                     const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
@@ -331,8 +332,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     mbar_wait(smem_u32(&bars->fullB[st]), ph);
                     tc_fence_after();
                     const uint32_t b_base = smem_u32(ringB + st * kSB);
-                    for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, b_base + k * 4096, idesc32, k > 0);
+                    for (int k = 0; k < 4; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, b_base + k * 4096, idesc32, k > 0);   // awork | xbuf
                     umma_commit(smem_u32(&bars->emptyB[st]));
+                    {   // + h_hi . W_lo (the hi image again, against the low half of the weights)
+                        const uint32_t st2 = itB % kNB, ph2 = (itB / kNB) & 1u;
+                        ++itB;
+                        mbar_wait(smem_u32(&bars->fullB[st2]), ph2);
+                        tc_fence_after();
+                        const uint32_t b2 = smem_u32(ringB + st2 * kSB);
+                        for (int k = 0; k < 2; ++k) umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, b2 + k * 4096, idesc32, true);
+                        umma_commit(smem_u32(&bars->emptyB[st2]));
+                    }
                     done(2), tl.mark(210);
                 }
                 if (it + 1 < L) {
@@ -381,9 +391,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         const int tstep = a.step0 - si;                                  // timestep index of this step
         const float* x_src = si == 0 ? a.x_in : a.x_out;
         // ---- step prologue (reference transformer.py:482,488-490): h0 = joint_embed(x) + sequence_embedding -> TMEM (stays
-        //      there for the whole step).  joint_embed runs on the tensor core like every other Linear; x itself is NOT rounded:
-        //      it is fed as a (hi, lo) pair of 16-bit values in the two halves of one 64-wide k-block against [W | W], which
-        //      reproduces the fp32 input to 2^-17.  This tile's A_emb image follows after the first LayerNorm (below).
+        //      there for the whole step).  joint_embed runs on the tensor core, but neither x nor W is rounded: both enter as
+        //      (hi, lo) pairs of 16-bit values, [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T over two 64-wide k-blocks, which is
+        //      fp32-equivalent to 2^-16.  This tile's A_emb image follows after the first LayerNorm (below).
         {
             float* ste = reinterpret_cast<float*>(xbuf) + kP * kD + kD + kTileRows * kP;   // [512] time embedding of the clip (read by the A_emb build)
             const int tx = threadIdx.x;
@@ -403,6 +413,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             }
             *reinterpret_cast<uint4*>(awork_p + sw128_offset(r, cq)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<uint4*>(awork_p + sw128_offset(r, cq + 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(awork_p + kABlockBytes + sw128_offset(r, cq)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);      // x_hi again, against W_lo
+            *reinterpret_cast<uint4*>(awork_p + kABlockBytes + sw128_offset(r, cq + 4)) = make_uint4(0, 0, 0, 0);
             ste[tx] = tt;
             if (tx < 128) reinterpret_cast<float4*>(prm_sa)[tx] = psa;
             rows_publish<false>(a_ready_addr, lane);
@@ -516,10 +528,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             }
             if (it + 1 == L) {
                 // ---- step epilogue (reference transformer.py:496, gaussian_diffusion.py:812-830 / 605-665): the output head runs
-                //      on the tensor core like every other Linear of the model (16-bit operands, fp32 accumulate); each of the
+                //      on the tensor core on the UNROUNDED final h (hi | lo split, 16-bit weights, fp32 accumulate); each of the
                 //      four threads of a row then owns 8 of the 32 accumulator columns (26 valid): bias, clamp, sampler update.
-                store_a16<kBf16>(awork, r, c0, v);
+                store_a16<kBf16>(awork, r, c0, v);                          // hi image -> awork
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {                            // lo = v - float(round16(v)) -> xbuf (contiguous with awork)
+                    const float2 back = unpack2<kBf16>(pack2<kBf16>(v[i], v[i + 1]));
+                    v[i] -= back.x, v[i + 1] -= back.y;
+                }
+                store_a16<kBf16>(smem_u32(xbuf), r, c0, v);
+                store_a16<kBf16>(smem_u32(xbuf), r, c0 + 16, v + 16);
                 rows_publish<false>(a_ready_addr, lane);
                 const int smode = a.mode & 0xF;
                 const float* nzp = a.noise != nullptr ? a.noise + (size_t)si * a.noise_stride : nullptr;

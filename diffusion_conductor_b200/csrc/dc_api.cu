@@ -75,8 +75,8 @@ struct dc_handle {
     uint8_t* wkv = nullptr;       // [L][8][256 x 128 B] folded cross-attention K|V weights
     float* bkv = nullptr;         // [L][256]
     float *WjT = nullptr, *bj = nullptr, *pos = nullptr, *WoT = nullptr, *bo = nullptr;
-    uint8_t* wj_img = nullptr;    // joint_embed as a [128 x 64] operand image, k 0..25 and 32..57 both = W (x is fed as hi | lo)
-    uint8_t* wout_img = nullptr;  // output head as a [32 x 128] operand image (persistent kernel: the head runs on the tensor core)
+    uint8_t* wj_img = nullptr;    // joint_embed as a [128 x 128] operand image [W_hi | W_hi | W_lo] (x is fed as hi | lo | hi)
+    uint8_t* wout_img = nullptr;  // output head as a [32 x 384] operand image [W_hi | W_hi | W_lo] (h is fed as hi | lo | hi)
     float *WlinT = nullptr, *blin = nullptr;
     float *teW0 = nullptr, *teb0 = nullptr, *teW2 = nullptr, *teb2 = nullptr, *freqs = nullptr;
 
@@ -757,19 +757,40 @@ int dc_finalize_weights(dc_handle* h) {
         for (int pI = 0; pI < kP; ++pI)
             for (int j = 0; j < kD; ++j) WoT[(size_t)j * 32 + pI] = Wo->v[(size_t)pI * kD + j];
         for (int pI = 0; pI < kP; ++pI) bo32[pI] = bo->v[pI];
-        {
-            std::vector<float> wj2((size_t)kD * 64, 0.f);
+        auto split16 = [&](float v, float& hi, float& lo) {                 // v = hi + lo, both exactly representable in the operand type
+            uint16_t u = to16(v, bf);
+            if (bf) {
+                __nv_bfloat16 b;
+                memcpy(&b, &u, 2);
+                hi = __bfloat162float(b);
+            } else {
+                __half hh;
+                memcpy(&hh, &u, 2);
+                hi = __half2float(hh);
+            }
+            lo = v - hi;
+        };
+        {   // joint_embed [128 x 128]: k 0..25 = W_hi, 32..57 = W_hi (against x_lo), 64..89 = W_lo (against x_hi again)
+            std::vector<float> wj2((size_t)kD * 128, 0.f);
             for (int n = 0; n < kD; ++n)
-                for (int k = 0; k < kP; ++k) wj2[(size_t)n * 64 + k] = wj2[(size_t)n * 64 + 32 + k] = Wj->v[(size_t)n * kP + k];
-            std::vector<uint8_t> img((size_t)kD * 128, 0);
-            pack_image(img.data(), wj2.data(), 64, 64, nullptr, nullptr, kD, 1, bf);
+                for (int k = 0; k < kP; ++k) {
+                    float hi, lo;
+                    split16(Wj->v[(size_t)n * kP + k], hi, lo);
+                    wj2[(size_t)n * 128 + k] = wj2[(size_t)n * 128 + 32 + k] = hi;
+                    wj2[(size_t)n * 128 + 64 + k] = lo;
+                }
+            std::vector<uint8_t> img((size_t)2 * kD * 128, 0);
+            pack_image(img.data(), wj2.data(), 128, 128, nullptr, nullptr, kD, 2, bf);
             if (upload(h, &h->wj_img, img.data(), img.size())) return DC_ERR_CUDA;
         }
-        {
-            std::vector<uint8_t> img(2 * 32 * 128, 0);
-            int rows32[32];
-            for (int i = 0; i < 32; ++i) rows32[i] = i < kP ? i : -1;
-            pack_image(img.data(), Wo->v.data(), kD, kD, rows32, nullptr, 32, 2, bf);
+        {   // output head [32 x 384]: k-blocks 0,1 = W_hi (against h_hi), 2,3 = W_hi (against h_lo), 4,5 = W_lo (against h_hi again)
+            std::vector<float> whi((size_t)32 * kD, 0.f), wlo((size_t)32 * kD, 0.f);
+            for (int pI = 0; pI < kP; ++pI)
+                for (int j = 0; j < kD; ++j) split16(Wo->v[(size_t)pI * kD + j], whi[(size_t)pI * kD + j], wlo[(size_t)pI * kD + j]);
+            std::vector<uint8_t> img(6 * 32 * 128, 0);
+            pack_image(img.data(), whi.data(), kD, kD, nullptr, nullptr, 32, 2, bf);
+            memcpy(img.data() + 2 * 32 * 128, img.data(), 2 * 32 * 128);
+            pack_image(img.data() + 4 * 32 * 128, wlo.data(), kD, kD, nullptr, nullptr, 32, 2, bf);
             if (upload(h, &h->wout_img, img.data(), img.size())) return DC_ERR_CUDA;
         }
         for (int e = 0; e < kE; ++e)
