@@ -805,13 +805,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         float2 mi[4], sj[4], r0[4], r1[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const bool on = j0 + j < nt;
-                            const uint32_t pa = mapa_u32(pbase, (uint32_t)(on ? j0 + j : rank));
-                            mi[j] = ld_dsmem_f32x2(pa + o_m);
-                            sj[j] = ld_dsmem_f32x2(pa + o_s);
-                            r0[j] = ld_dsmem_f32x2(pa + o_r0);
-                            r1[j] = ld_dsmem_f32x2(pa + o_r1);
-                            if (!on) mi[j] = make_float2(-INFINITY, -INFINITY);
+                            if (j0 + j < nt) {                             // block-uniform: no loads for absent tiles
+                                const uint32_t pa = mapa_u32(pbase, (uint32_t)(j0 + j));
+                                mi[j] = ld_dsmem_f32x2(pa + o_m);
+                                sj[j] = ld_dsmem_f32x2(pa + o_s);
+                                r0[j] = ld_dsmem_f32x2(pa + o_r0);
+                                r1[j] = ld_dsmem_f32x2(pa + o_r1);
+                            } else {
+                                mi[j] = make_float2(-INFINITY, -INFINITY);
+                                sj[j] = r0[j] = r1[j] = make_float2(0.f, 0.f);
+                            }
                         }
                         float n0 = M0, n1 = M1;
 #pragma unroll
@@ -893,12 +896,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                             *reinterpret_cast<uint16_t*>(base + sw128_offset(16 * (d >> 4) + l4 + i, (d & 63) >> 3)) = vals[i];
                     }
                 }
-                if (nt > 1) {                                              // every pull of this CTA has completed: the peers may reuse ring B
-                    named_bar_sync(5, kRowThreads);
-                    if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pull_done[seq & 1u]), (uint32_t)tx));
-                }
                 rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
                 tl.mark(126);
+                if (nt > 1) {                                              // every pull of this CTA has completed: the peers may reuse ring B
+                    named_bar_sync(5, kRowThreads);                        // (off the critical path: the q . A GEMM is already on its way)
+                    if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pull_done[seq & 1u]), (uint32_t)tx));
+                }
             }
         }
         }   // launch step si
