@@ -570,8 +570,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         }
                     }
                 }
+                // no CTA barrier: the next step's prologue re-reads exactly the x elements this thread has just written, and the
+                // operand buffers it overwrites were last read by the head GEMM every thread has just waited for
                 tc_fence_before();
-                named_bar_sync(5, kRowThreads);                            // x of this tile is complete before the next step stages it
                 break;
             }
 
@@ -660,8 +661,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         return *reinterpret_cast<uint32_t*>(&r2);
                     }
                 };
-                float kx[32];
-                tmem_ld32(trow + kColS + 128 + c0, kx);
+                float kx[32], vx[32];
+                tmem_ld32(trow + kColS + 128 + c0, kx);                   // k and v in flight together: one TMEM round trip
+                tmem_ld32(trow + kColW + c0, vx);
                 tmem_wait_ld();
 
                 add_bias32(kx, prm_sa + kPrmSaBk + c0);
@@ -677,12 +679,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 // LayerNorm output, ||n|| <= sqrt(128)) by a small constant, that bound replaces the running column max --
                 // no 16-bit k image, no column scan, three CTA barriers less.  Otherwise: exact tile-local column max.
                 const bool static_shift = (a.static_mask >> (it + 1)) & 1u;
-                float vx[32];
                 if (!static_shift) {
                     store_a16<kBf16>(eimg, r, c0, kx);
                     store_a16<kBf16>(eimg, r, c0 + 16, kx + 16);
-                    tmem_ld32(trow + kColW + c0, vx);
-                    tmem_wait_ld();
                     add_bias32(vx, prm_sa + kPrmSaBv + c0);
                     named_bar_sync(5, kRowThreads);
                     {   // column maxima: this thread scans 16 rows of a column PAIR (packed 16-bit max)
@@ -700,8 +699,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     }
                     named_bar_sync(5, kRowThreads);
                 } else {
-                    tmem_ld32(trow + kColW + c0, vx);
-                    tmem_wait_ld();
                     add_bias32(vx, prm_sa + kPrmSaBv + c0);
                     if (tx < 128) msm[tx] = 0.f;                       // every tile reports the same (virtual) max: the merge just adds
                 }
