@@ -551,7 +551,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     nz[i] = (smode != 0 && nzp != nullptr && i < np) ? __ldcg(nzp + e0 + i) : 0.f;
                     bo8[i] = __ldg(a.bo + p0 + i);
                 }
-                const float* cf = smode != 0 ? a.coef + (size_t)tstep * 8 : nullptr;
+                float cf[8];                                                            // this step's coefficient row, fetched before the wait
+                {
+                    const float4* cf4 = reinterpret_cast<const float4*>(a.coef + (size_t)(smode != 0 ? tstep : 0) * 8);
+                    const float4 ca = smode != 0 ? __ldg(cf4) : make_float4(0.f, 0.f, 0.f, 0.f), cb = smode != 0 ? __ldg(cf4 + 1) : ca;
+                    cf[0] = ca.x, cf[1] = ca.y, cf[2] = ca.z, cf[3] = ca.w, cf[4] = cb.x, cf[5] = cb.y, cf[6] = cb.z, cf[7] = cb.w;
+                }
                 float* x0p = a.x0_out + (size_t)si * a.x0_stride;
                 rows_wait(bars, 2, ph[2]);
                 float o8[8];
