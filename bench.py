@@ -111,6 +111,31 @@ def cpu_reference_rate(B, T, S, n_steps_sample, batch_sample=None):
     return rate, cores, dt, f"{n_steps_sample} denoise steps of a {Bs}x{T}-frame batch after 1 warm-up step, x{S} extrapolated"
 
 
+def eager_gpu_rate(B, T, S, dev, n_calls=3):
+    """the reference algorithm in PyTorch eager fp32 ON THE SAME GPU (the oracle restatement of
+    MotionTransformer.forward with every tensor on the device; the sampler update is negligible next to it) -- the
+    "existing GPU kernels" bar.  Times n_calls forward passes after one warm-up and extrapolates to the S-step loop."""
+    import torch
+
+    from diffusion_conductor_b200.synth import synth_features, synth_inputs, synth_state_dict
+    from oracle import motion_oracle as O
+
+    sd = {k: v.to(dev) for k, v in synth_state_dict(0, num_layers=8).items()}
+    xf_proj, xf_out = (t.to(dev) for t in synth_features(B, T, seed=1))
+    x = synth_inputs(B, T, seed=1)[1].to(dev)
+    t = torch.full((B,), S - 1, dtype=torch.long, device=dev)
+    with torch.no_grad():
+        O.motion_transformer_forward(sd, x, t, [T] * B, xf_proj, xf_out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_calls):
+            O.motion_transformer_forward(sd, x, t, [T] * B, xf_proj, xf_out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    dt = e0.elapsed_time(e1) / 1e3 / n_calls
+    return (B * T / 30.0) / (dt * S), f"{n_calls} eager forward passes of a {B}x{T}-frame batch after 1 warm-up, x{S} extrapolated"
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -330,10 +355,15 @@ def main():
                 "whole_loop_frac_of_peak": round(B * T * S * FLOP_PER_TOKEN_STEP / (ms_per_step / 1e3) / 1e12 / pk["bf16_tflops"], 4)}
 
     if rank == 0:
-        cpu = None
+        cpu, eager = None, None
         if not args.no_cpu_baseline and world == 1:
             rate, cores, dt, sample = cpu_reference_rate(B, T, S, 3)
             cpu = {"value": round(rate, 3), "unit": "motion-s/s", "cores": cores, "kind": "port", "sample": sample}
+            try:
+                grate, gsample = eager_gpu_rate(B, T, S, dev)
+                eager = {"value": round(grate, 2), "unit": "motion-s/s", "kind": "port, PyTorch eager fp32 on the same B200", "sample": gsample}
+            except Exception as exc:                      # a baseline leg must never take the product line down
+                eager = {"unavailable": repr(exc)[:200]}
         n_in = (hp.numel() + ho.numel() + hn.numel()) * 4
         line = {
             "metric": "motion-seconds generated/sec (50-step DDIM)", "value": round(value, 2), "unit": "motion-s/s",
@@ -344,7 +374,7 @@ def main():
                        "token_steps_per_step": B * T * S, "l2": "256 MiB buffer written between timed iterations",
                        "collective": "NCCL all_gather of the generated motion" if world > 1 else "none"},
             "e2e": {"value": round(e2e_value, 2), "unit": "motion-s/s", "h2d_bytes_per_step": n_in, "d2h_bytes_per_step": hout.numel() * 4},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "conditioning": cond,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "torch_eager_gpu_baseline": eager, "clocks": clk, "conditioning": cond,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

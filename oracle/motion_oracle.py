@@ -87,7 +87,7 @@ def gather(arr: np.ndarray, t: Tensor, ndim: int) -> Tensor:
 def timestep_embedding(t: Tensor, dim: int, max_period: int = 10000) -> Tensor:
     """transformer.py:8-25 -- [cos | sin], fp32 frequencies."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)   # CPU exp, then moved (:19-20)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -175,7 +175,7 @@ def motion_transformer_forward(sd: StateDict, x: Tensor, timesteps: Tensor, leng
     if x.dim() == 4:
         x = torch.flatten(x, start_dim=2, end_dim=3)
     h = _lin(sd, "joint_embed", x.to(dtype)) + sd["sequence_embedding"].to(dtype)[None, :T, :]
-    mask = src_mask_from_length(T, length).to(dtype).unsqueeze(-1)
+    mask = src_mask_from_length(T, length).to(device=x.device, dtype=dtype).unsqueeze(-1)
     for i in range(num_layers_of(sd)):
         p = f"temporal_decoder_blocks.{i}"
         h = linear_self_attention(sd, p + ".sa_block", h, emb, mask, num_heads)
