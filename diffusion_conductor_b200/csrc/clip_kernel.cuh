@@ -449,10 +449,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 tmem_wait_ld();
                 row_stats32(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(102);                                   // S = A_emb . We_sa
-                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0);
-                tc_fence_before();                                           // S consumed: the next FiLM projection may start
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_free_addr);
+                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0, s_free_addr, lane);   // releases S as soon as it has been read
                 rows_publish<false>(a_ready_addr, lane); tl.mark(151);                                          // -> h += A . Wo_sa
 
                 // ================= cross-attention
@@ -486,10 +483,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 if (lane == 0) mbar_arrive(smem_u32(&bars->w_free));
                 row_stats32(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(106);                                   // S = A_emb . We_ca
-                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0);
-                tc_fence_before();                                           // S consumed: the next FiLM projection may start
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_free_addr);
+                film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0, s_free_addr, lane);   // releases S as soon as it has been read
                 rows_publish<false>(a_ready_addr, lane); tl.mark(154);                                          // -> h += A . Wo_ca
 
                 // ================= FFN (no pre-norm, reference transformer.py:170-173): W[0:64] = h . W1 was issued together

@@ -430,9 +430,11 @@ __device__ __forceinline__ void normalize32(float* v, float mean, float rstd) {
 // A operand <- SiLU( LN(y) * (1 + scale) + shift ) for this thread's 32 features [c0, c0+32)
 // (reference transformer.py:77-80).  The scale|shift accumulator in TMEM columns kColS is laid out
 //   [scale 0..63 | shift 0..63 | scale 64..127 | shift 64..127]; st = stylization params in smem.
+// s_free_addr != 0: arrive on that mbarrier (one lane per warp) as soon as this warp's LAST scale|shift values have left
+// TMEM -- before the second half of the math -- so that the next FiLM projection can start that much earlier.
 template <bool kBf16>
 __device__ __forceinline__ void film_to_a(uint32_t trow, const float* y, float mean, float rstd, const float* st, uint32_t awork,
-                                          uint32_t r, uint32_t c0) {
+                                          uint32_t r, uint32_t c0, uint32_t s_free_addr = 0, int lane = 0) {
     const uint32_t sbase = trow + kColS + (c0 >> 6) * 128 + (c0 & 63);     // scale column of feature c0
     const float* be = st + kStBe + (c0 >> 6) * 128 + (c0 & 63);
     const uint64_t r2 = pk2(rstd, rstd), nm = pk2(-mean * rstd, -mean * rstd), half2 = pk2(0.5f, 0.5f);
@@ -442,6 +444,11 @@ __device__ __forceinline__ void film_to_a(uint32_t trow, const float* y, float m
         tmem_ld16(sbase + 16 * hf, sc);
         tmem_ld16(sbase + 64 + 16 * hf, sh);
         tmem_wait_ld();
+        if (hf == 1 && s_free_addr != 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free_addr);
+        }
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
             const float4 g4 = *reinterpret_cast<const float4*>(st + kStG + c0 + 16 * hf + 4 * i4);
