@@ -11,11 +11,11 @@ echo "=== bench reference"; timeout 900 python bench.py --impl reference --steps
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "=== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conditioning > gpurun_out/ncu_launch_run.log 2>&1
 tail -3 gpurun_out/ncu_launch_run.log
 echo "=== ncu full (layer kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(clip_kernel|layer_kernel)" -s 3 -c 1 -f -o gpurun_out/clip_full \
-   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conditioning > gpurun_out/ncu_full_run.log 2>&1
 tail -3 gpurun_out/ncu_full_run.log
 ls -la gpurun_out | head -30
 fi
