@@ -265,7 +265,7 @@ class GaussianDiffusion:
 
     def _loop(self, sampler, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
               eta, idxs, match_rng_stream):
-        """Whole-loop entry: one C call that replays the captured per-step CUDA graph S times."""
+        """Whole-loop entry: one C call = one launch of the persistent kernel for all S steps (dc_sample_loop)."""
         self._require_fast_path(model, denoised_fn, cond_fn)
         img, device = self._initial(model, shape, noise, device)
         eng = self._bind(model, img, model_kwargs, eta)

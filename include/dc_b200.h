@@ -94,8 +94,9 @@ int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0,
                       void* stream);
 
 /* GaussianDiffusion.ddim_sample_loop / p_sample_loop (gaussian_diffusion.py:871-965 / 667-781):
- * runs steps S-1 .. 0 from x (initial noise, updated in place to the final sample), replaying a
- * captured CUDA graph.  step_noise: DEVICE [S][B][T][26] in loop order or NULL.  trace_x0 / trace_x:
+ * runs steps S-1 .. 0 from x (initial noise, updated in place to the final sample) as ONE launch of the
+ * persistent cluster-per-clip kernel (clips of up to 2048 frames; longer clips: a captured CUDA graph of
+ * per-layer launches).  step_noise: DEVICE [S][B][T][26] in loop order or NULL.  trace_x0 / trace_x:
  * DEVICE [S][B][T][26] receiving pred_xstart / sample of every step, or NULL. */
 int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise, float* trace_x0, float* trace_x,
                    void* stream);
@@ -132,7 +133,8 @@ int dc_smooth_motion(int device, const float* motion, float* out, int B, int T, 
 
 /* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
 int64_t dc_kernel_launches(const dc_handle* h);
-/* 1 = replay captured CUDA graphs in dc_sample_loop (default), 0 = plain launches (profiling). */
+/* Per-layer launch path only (clips longer than 2048 frames, DC_PERSIST=0): 1 = replay captured CUDA graphs in
+ * dc_sample_loop (default), 0 = plain launches (profiling). */
 int dc_set_graphs(dc_handle* h, int enabled);
 
 /* Stand-alone check of the tcgen05 GEMM building block: out[M][N] = A[M][K] . W[N][K]^T + bias with
