@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 rows_wait(bars, 2, ph[2]); tl.mark(101);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
-                row_stats32(rs, v, mean, rstd);
+                row_stats32<false>(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(102);                                   // S = A_emb . We_sa
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0, s_free_addr, lane);   // releases S as soon as it has been read
                 rows_publish<false>(a_ready_addr, lane); tl.mark(151);                                          // -> h += A . Wo_sa
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 tmem_st32(trow + kColH + c0, v);
                 store_a16<kBf16>(smem_u32(xbuf), r, c0, v);                  // 16-bit image of h for the fused FFN up-projection
                 store_a16<kBf16>(smem_u32(xbuf), r, c0 + 16, v + 16);
-                row_stats32(rs, v, mean, rstd);
+                row_stats32<false>(rs, v, mean, rstd);
                 normalize32(v, mean, rstd);                                  // LN affine folded into Wq_ca
                 store_a16<kBf16>(awork, r, c0, v);
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 tc_fence_before();                                           // y_ca is in registers: W may take h16 . W1 now
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->w_free));
-                row_stats32(rs, v, mean, rstd);
+                row_stats32<false>(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(106);                                   // S = A_emb . We_ca
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStCa, awork, r, c0, s_free_addr, lane);   // releases S as soon as it has been read
                 rows_publish<false>(a_ready_addr, lane); tl.mark(154);                                          // -> h += A . Wo_ca
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
                 add_bias32(v, prm + kPrmFfB2 + c0);
-                row_stats32(rs, v, mean, rstd);
+                row_stats32<false>(rs, v, mean, rstd);
                 rows_wait(bars, 0, ph[0]); tl.mark(110);                                   // S = A_emb . We_ffn
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStFf, awork, r, c0);
                 rows_publish<false>(a_ready_addr, lane); tl.mark(157);                                          // -> h += A . Wo_ffn
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             }
 
             // ================= self-attention head of layer it+1: LN -> q | k | v, then the time-axis reduction
-            row_stats32(rs, v, mean, rstd);
+            row_stats32<false>(rs, v, mean, rstd);
             normalize32(v, mean, rstd);                                  // LN affine folded into Wq/Wk/Wv
             store_a16<kBf16>(awork, r, c0, v);
             store_a16<kBf16>(awork, r, c0 + 16, v + 16);

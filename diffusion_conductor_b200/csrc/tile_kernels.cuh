@@ -388,6 +388,10 @@ struct RowStats {
     uint32_t flip;
 };
 
+// kGuardReuse: second barrier that keeps a fast warp's NEXT call from overwriting the exchange buffer before everyone has read
+// it.  The persistent kernel passes false: between two calls every warp publishes an A operand and waits for the MMA that needed
+// all 16 publications, which orders every read of call k before any write of call k + 1.
+template <bool kGuardReuse = true>
 __device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float& mean, float& rstd) {
     uint64_t s2a = pk2(0.f, 0.f), s2b = s2a;
 #pragma unroll
@@ -413,7 +417,7 @@ __device__ __forceinline__ void row_stats32(RowStats& rs, const float* v, float&
     buf[rs.cq * 128 + rs.r] = make_float2(lm, m2);
     named_bar_sync(rs.bar_id, 128);
     const float2 p0 = buf[rs.r], p1 = buf[128 + rs.r], p2 = buf[256 + rs.r], p3 = buf[384 + rs.r];
-    named_bar_sync(rs.bar_id, 128);       // single exchange buffer: everyone has read before the next call writes
+    if constexpr (kGuardReuse) named_bar_sync(rs.bar_id, 128);       // single exchange buffer: everyone has read before the next call writes
     mean = 0.25f * ((p0.x + p1.x) + (p2.x + p3.x));
     const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
     const float M2 = (p0.y + p1.y) + (p2.y + p3.y) + 32.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
