@@ -774,10 +774,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 named_bar_sync(5, kRowThreads);                            // partial complete
                 tl.mark(124);
                 // ---- publish to the peers: release at cluster scope, one remote arrive per peer
-                if (nt > 1 && tx < nt && tx != rank) {
-                    fence_acq_rel_cluster();
-                    mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
-                }
+                // (no separate fence: the arrive is a release at cluster scope, and release is cumulative over the writes of the
+                //  other row threads that were ordered before it by the CTA barrier above)
+                if (nt > 1 && tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
                 // ---- while the peers' partials are in flight: clear the image buffer (the merge writes only the diagonal
                 //      blocks); the parameter blocks fetched with cp.async above must have landed before the barrier below
                 {
@@ -874,10 +873,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         }
                     }
                     named_bar_sync(5, kRowThreads);
-                    if (tx < nt && tx != rank) {
-                        fence_acq_rel_cluster();
-                        mbar_arrive_cluster(mapa_u32(smem_u32(&bars->slice_ready[seq & 1u]), (uint32_t)tx));
-                    }
+                    if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->slice_ready[seq & 1u]), (uint32_t)tx));
                     if (tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->slice_ready[seq & 1u]), (seq >> 1) & 1u);
                     named_bar_sync(5, kRowThreads);
                     {

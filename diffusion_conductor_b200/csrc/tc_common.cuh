@@ -302,9 +302,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // ---------------------------------------------------------------- distributed shared memory (one cluster = one clip)
-// Writer: plain st.shared of the payload, CTA barrier, then ONE thread fences at cluster scope and arrives on the
-// peers' mbarriers.  Reader: one thread waits with acquire.cluster, CTA barrier, then everyone pulls with
-// ld.shared::cluster.  (Cluster-scope fences flush L1, so they are kept to one per exchange.)
+// Writer: plain st.shared of the payload, CTA barrier, then one thread per peer arrives on the peer's mbarrier with
+// release.cluster (cumulative over the barrier: no separate fence.acq_rel.cluster, which costs an L1 flush).  Reader: one
+// thread waits with acquire.cluster, CTA barrier, then everyone pulls with ld.shared::cluster.
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
