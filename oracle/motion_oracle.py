@@ -1,9 +1,9 @@
 """CPU oracle for the Diffusion-Conductor denoising hot path.
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file; only
-`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
-legs may call it, and there only as the checker (or the timed CPU baseline), never as
-the thing shipped.
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s baseline legs (cpu_baseline,
+torch_eager_gpu_baseline, `--impl reference`) may call it, and there only as the checker
+(or the timed baseline), never as the thing shipped.
 
 It is a functional restatement (plain torch-CPU tensor ops over a `state_dict`, no
 nn.Module graph) of the reference algorithm.  Each function cites the reference lines
