@@ -527,11 +527,19 @@ int dc_create(const dc_config* cfg, dc_handle** out) {
     h->cfg = *cfg;
     h->bf16 = cfg->operand != DC_OPERAND_FP16;
     h->num_sms = prop.multiProcessorCount;
-    DC_CUDA(h, cudaSetDevice(cfg->device));
-    if (int rc = init_kernel_attrs(h)) return rc;
-    DC_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
-    DC_CUDA(h, cudaMalloc((void**)&h->step_ctr, 4));
-    DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
+    // any failure below: the message is already in g_last_error (dc_last_error(NULL)); release what was created
+    auto init = [&]() -> int {
+        DC_CUDA(h, cudaSetDevice(cfg->device));
+        if (int rc = init_kernel_attrs(h)) return rc;
+        DC_CUDA(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        DC_CUDA(h, cudaMalloc((void**)&h->step_ctr, 4));
+        DC_CUDA(h, cudaMemset(h->step_ctr, 0, 4));
+        return 0;
+    };
+    if (int rc = init()) {
+        dc_destroy(h);
+        return rc;
+    }
     const char* mi = getenv("DC_MASK_INVERT");
     if (mi && mi[0] == '1') h->mask_invert = 1;
     if (mi && mi[0] == '3') h->mask_invert = 3;
@@ -582,6 +590,8 @@ int dc_set_weight(dc_handle* h, const char* key, const void* data, const int64_t
 int dc_finalize_weights(dc_handle* h) {
     if (!h) return fail(h, DC_ERR_INVALID, "null handle");
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    // a sampling loop may still be running on a (non-blocking) user stream: nothing below may race with it
+    DC_CUDA(h, cudaDeviceSynchronize());
     const int L = h->cfg.num_layers;
     const bool bf = h->bf16;
 #define GET(var, key, ...)                          \
@@ -897,6 +907,7 @@ int dc_set_schedule(dc_handle* h, int num_steps, const float* coef) {
     if (!h || num_steps < 1 || !coef) return fail(h, DC_ERR_INVALID, "dc_set_schedule: bad argument");
     if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_set_schedule: call dc_finalize_weights first");
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    DC_CUDA(h, cudaDeviceSynchronize());       // coef / te_table may still be read by a loop on a non-blocking user stream
     drop_graph(h);
     if (upload(h, &h->coef, coef, (size_t)num_steps * 8 * 4)) return DC_ERR_CUDA;
     if (h->te_table) cudaFree(h->te_table);
@@ -941,8 +952,12 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
             const cudaError_t qe = h->bf16 ? cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<true, false>, &cfg)
                                            : cudaOccupancyMaxActiveClusters(&nclusters, clip_kernel<false, false>, &cfg);
             if (qe != cudaSuccess || nclusters < 1) {
+                // never drop to the (1.4x slower) per-layer path silently: the caller asks for it with DC_PERSIST=0
                 cudaGetLastError();
-                persist = false;
+                return fail(h, DC_ERR_UNSUPPORTED,
+                            "dc_prepare_cond: this device cannot co-schedule a cluster of %d CTAs (one per 128-frame tile of a %d-frame clip): "
+                            "cudaOccupancyMaxActiveClusters -> %s, %d clusters.  Set DC_PERSIST=0 to run the per-layer launch path instead.",
+                            nt, T, cudaGetErrorString(qe), nclusters);
             } else {
                 h->clip_nt_checked = nt;
             }
@@ -1032,9 +1047,12 @@ int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0,
     return 0;
 }
 
-int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise, float* trace_x0, float* trace_x, void* stream) {
+int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x, void* stream) {
     if (int rc = check_sampling(h, sampler, "dc_sample_loop")) return rc;
     if (!x) return fail(h, DC_ERR_INVALID, "dc_sample_loop: null x");
+    if (num_steps != h->S)
+        return fail(h, DC_ERR_STATE, "dc_sample_loop: caller expects %d steps but the schedule set with dc_set_schedule has %d "
+                    "(the noise / trace buffers are sized by the caller)", num_steps, h->S);
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->M * kP;
@@ -1101,6 +1119,7 @@ int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const floa
                      float* motion_out, int B, int T, void* stream) {
     if (!h || !xf_proj || !xf_out || !noise || !motion_out || B < 1 || T < 1) return fail(h, DC_ERR_INVALID, "dc_generate_host: bad argument");
     if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_generate_host: weights not finalized");
+    if (h->S < 1) return fail(h, DC_ERR_STATE, "dc_generate_host: call dc_set_schedule first");
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = ensure_workspace(h, B, T)) return rc;
@@ -1113,7 +1132,7 @@ int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const floa
     DC_CUDA(h, cudaMemcpyAsync(xdev, noise, M * kP * 4, cudaMemcpyHostToDevice, st));
     // dc_sample_loop copies x -> xwork first, so aliasing x0work as the in/out buffer is safe: the
     // final copy back happens after the last step has written its pred_xstart.
-    if (int rc = dc_sample_loop(h, sampler, xdev, nullptr, nullptr, nullptr, stream)) return rc;
+    if (int rc = dc_sample_loop(h, sampler, h->S, xdev, nullptr, nullptr, nullptr, stream)) return rc;
     DC_CUDA(h, cudaMemcpyAsync(motion_out, xdev, M * kP * 4, cudaMemcpyDeviceToHost, st));
     DC_CUDA(h, cudaStreamSynchronize(st));
     return 0;
@@ -1237,6 +1256,33 @@ int dc_smooth_motion(int device, const float* motion, float* out, int B, int T, 
     const long n = (long)B * T * C;
     savgol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(motion, out, B, T, C, cf);
     DC_CUDA(nullptr, cudaGetLastError());
+    return 0;
+}
+
+int dc_time_embedding(dc_handle* h, const int64_t* timesteps, int n, float* out, void* stream) {
+    if (!h || !timesteps || !out || n < 1) return fail(h, DC_ERR_INVALID, "dc_time_embedding: bad argument");
+    if (!h->finalized) return fail(h, DC_ERR_STATE, "dc_time_embedding: weights not finalized");
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    time_embed_kernel<<<n, kE, 0, (cudaStream_t)stream>>>((const long long*)timesteps, 0, h->freqs, h->teW0, h->teb0, h->teW2, h->teb2, out);
+    h->launches++;
+    DC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+int dc_cluster_occupancy(dc_handle* h, int tiles_per_clip, int* max_clusters) {
+    if (!h || !max_clusters || tiles_per_clip < 1 || tiles_per_clip > kMaxClipTiles)
+        return fail(h, DC_ERR_INVALID, "dc_cluster_occupancy: need 1 <= tiles_per_clip <= %d", kMaxClipTiles);
+    DC_CUDA(h, cudaSetDevice(h->cfg.device));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)tiles_per_clip), cfg.blockDim = dim3(kTileThreads), cfg.dynamicSmemBytes = kClipSmemBytes;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)tiles_per_clip, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cfg.attrs = &at, cfg.numAttrs = 1;
+    int n = 0;
+    DC_CUDA(h, h->bf16 ? cudaOccupancyMaxActiveClusters(&n, clip_kernel<true, false>, &cfg)
+                       : cudaOccupancyMaxActiveClusters(&n, clip_kernel<false, false>, &cfg));
+    *max_clusters = n;
     return 0;
 }
 

@@ -24,6 +24,25 @@ from . import _lib
 from .transformer import MotionTransformer
 
 
+def _advance_rng_like_randn(x: th.Tensor, draws: int) -> None:
+    """Leave torch's generator for x.device exactly where `draws` consecutive `th.randn_like(x)` calls would leave it,
+    without materialising the (unused) samples: the reference draws one randn_like per step in ddim_sample even when
+    eta == 0 (gaussian_diffusion.py:822), so a drop-in must consume the same stream.  A CUDA generator advances its
+    Philox offset by a fixed amount per call of a given size: one real draw measures it, set_offset does the rest."""
+    if draws <= 0:
+        return
+    if x.is_cuda:
+        gen = th.cuda.default_generators[x.device.index if x.device.index is not None else th.cuda.current_device()]
+        if hasattr(gen, "get_offset") and hasattr(gen, "set_offset"):
+            before = gen.get_offset()
+            th.randn_like(x)
+            step = gen.get_offset() - before
+            gen.set_offset(before + step * draws)
+            return
+    for _ in range(draws):
+        th.randn_like(x)
+
+
 def get_named_beta_schedule(schedule_name, num_diffusion_timesteps):
     if schedule_name == "linear":
         scale = 1000 / num_diffusion_timesteps
@@ -163,7 +182,7 @@ class GaussianDiffusion:
             xf_proj, xf_out = model.encode_music(text, x.device)
         eng = model.engine_for(x.device, B, T)
         eng.prepare(xf_proj, xf_out, length, B, T)
-        eng.set_schedule((id(self), float(eta)), self.step_coefficients(eta))
+        eng.set_schedule(self.step_coefficients(eta))
         return eng
 
     @staticmethod
@@ -209,7 +228,9 @@ class GaussianDiffusion:
                                  self._as_state(noise, x.device) if eta != 0.0 else None)
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
-                         model_kwargs=None, device=None, progress=False, eta=0.0, idxs=[], match_rng_stream=False):
+                         model_kwargs=None, device=None, progress=False, eta=0.0, idxs=[], match_rng_stream=True):
+        """match_rng_stream (extension, default on): consume torch's generator like the reference does -- one randn_like
+        per step even at eta == 0 (:822) -- so that whatever the caller draws next matches a run of the reference."""
         return self._loop(_lib.DC_SAMPLER_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
                           device, progress, eta, idxs, match_rng_stream)
 
@@ -274,17 +295,19 @@ class GaussianDiffusion:
         stochastic = sampler == _lib.DC_SAMPLER_DDPM or eta != 0.0
         step_noise = None
         if stochastic:
-            # same generator draws, in the same order, as the reference's per-step randn_like
-            step_noise = th.stack([th.randn_like(x) for _ in range(S)])
+            # same generator draws, in the same order, as the reference's per-step randn_like; one [S, ...] buffer filled
+            # slice by slice (normal_ on a contiguous slice consumes the generator exactly like randn_like of that shape)
+            step_noise = th.empty((S,) + tuple(x.shape), device=x.device, dtype=th.float32)
+            for i in range(S):
+                step_noise[i].normal_()
         elif match_rng_stream:
-            for _ in range(S):
-                th.randn_like(x)
+            _advance_rng_like_randn(x, S)
         trace = th.empty((S,) + tuple(x.shape), device=x.device, dtype=th.float32) if len(idxs) else None
         flags = sampler | (_lib.DC_FLAG_CLIP if clip_denoised else 0)
         if progress:
             from tqdm.auto import tqdm
             bar = tqdm(total=S)
-        eng.sample_loop(flags, x, step_noise=step_noise, trace_x=trace)
+        eng.sample_loop(flags, x, step_noise=step_noise, trace_x=trace, num_steps=S)
         if progress:
             bar.update(S)
             bar.close()

@@ -30,11 +30,16 @@ def gather_shards(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor
         return local
     sizes = [shard_range(n_items, r, world) for r in range(world)]
     cap = max(b - a for a, b in sizes)
+    if all(b - a == cap for a, b in sizes):
+        # equal shards (the usual case): ONE collective straight into the (n_items, ...) result, no staging copies
+        out = local.new_empty((n_items,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = local.new_zeros((cap,) + tuple(local.shape[1:]))
     pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([bufs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+    buf = local.new_empty((world * cap,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return torch.cat([buf[r * cap: r * cap + (b - a)] for r, (a, b) in enumerate(sizes)], dim=0)
 
 
 def sharded_sample(sample_fn: Callable[[torch.Tensor, torch.Tensor, torch.Tensor, List[int]], torch.Tensor],
@@ -70,10 +75,19 @@ def generate_music_motion(model, diffusion, music_mel, dim_pose: int = 26, lengt
     if mel.dim() == 2:
         mel = mel.unsqueeze(0)
     mel = mel.to(device=device, dtype=torch.float32)
-    B, T = mel.shape[0], mel.shape[1] // 3
-    length = [T] * B if length is None else [int(v) for v in length]
+    # motion frames = music-feature frames: the reference takes T from xf_proj.shape[1] (ddpm_trainer.py:187-188); the
+    # encoder's stride-3 max-pool (kernel 5, padding 2) yields (Tm - 1) // 3 + 1 frames for Tm mel frames
+    B, T = mel.shape[0], (mel.shape[1] - 1) // 3 + 1
+    if length is None:
+        length = [T] * B
+    else:
+        length = [int(v) for v in (length.tolist() if isinstance(length, torch.Tensor) else length)]
+        if len(length) != B:
+            raise ValueError(f"len(length)={len(length)} must equal the number of clips {B}")
     if noise is None:
         noise = torch.randn(B, T, dim_pose, device=device)
+    elif tuple(noise.shape) != (B, T, dim_pose):
+        raise ValueError(f"noise must be {(B, T, dim_pose)} for {mel.shape[1]} mel frames, got {tuple(noise.shape)}")
     if len(idxs) and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         raise NotImplementedError("idxs (intermediate samples) is single-process only")
 

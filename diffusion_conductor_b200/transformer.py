@@ -5,8 +5,9 @@ same 396-entry `state_dict` as reference Diffusion_Stage/models/transformer.py:3
 reference checkpoint (`checkpoint['encoder']`, ddpm_trainer.py:303-319) loads unchanged.  The nn
 sub-modules below only *hold* parameters under the reference's names; the arithmetic of the
 decoder runs in the sm_100a library through the C ABI (include/dc_b200.h).  The music-encoder CNN
-(reference :289-357) is the once-per-clip front-end outside the step loop and stays in PyTorch
-(SURVEY.md §8(f) N1).
+(reference :289-357), the once-per-clip front-end outside the step loop, runs there too in eval mode
+(dc_encode_music); the `MusicEncoder` module below holds its parameters and is only
+executed by PyTorch in training mode (condition dropout), which is outside the sampling path.
 
 Unsupported on purpose (raise, never fall back): `no_eff=True` (quadratic attention variant),
 autograd through `forward`, CPU tensors.
@@ -40,6 +41,14 @@ def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 1000
 def timestep_frequencies(dim: int, max_period: int = 10000) -> torch.Tensor:
     half = dim // 2
     return torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+
+
+def _as_int_list(length) -> list:
+    """`length` as the reference callers pass it: a python list, or a (CUDA) LongTensor (ddpm_trainer.py:198) -- one
+    device->host copy instead of one per element."""
+    if isinstance(length, torch.Tensor):
+        return [int(v) for v in length.detach().reshape(-1).tolist()]
+    return [int(v) for v in length]
 
 
 def _zero_(module: nn.Module) -> nn.Module:
@@ -191,7 +200,6 @@ class MotionTransformer(nn.Module):
         self.proj = nn.Linear(64, 64)
 
         self._engine: Optional[_Engine] = None
-        self._chunk_engines = []            # extra handles for clip chunks of large batches (see engine_for)
         self._weights_dirty = True
 
     # ---- weight bookkeeping -------------------------------------------------------------------
@@ -218,40 +226,15 @@ class MotionTransformer(nn.Module):
             self._weights_dirty = True
         if self._weights_dirty:
             self._engine.upload(self)
-            for e in self._chunk_engines:
-                e.upload(self)
             self._weights_dirty = False
         return self._engine
 
     def engine_for(self, device: torch.device, B: int, T: int):
-        """Engine for a (B, T) batch.  Clips of up to 2048 frames run on the cluster-per-clip kernel (one handle, any
-        batch).  Beyond that: the older grid-resident persistent kernel needs every 128-token tile of the batch on
-        its own SM; clips are independent, so a larger batch is cut into equal chunks of clips that fit, each
-        chunk with its own handle (workspace + captured graph) run back to back.  Short clips (T < 128) and single
-        clips longer than the GPU use one handle and the per-layer launch path."""
-        base = self.engine(device)
-        if T <= 16 * 128 and os.environ.get("DC_CLUSTER", "1") != "0" and os.environ.get("DC_PERSIST", "1") != "0":
-            return base         # cluster-per-clip kernel: clips are scheduled by the hardware, any batch size in one launch
-        sms = torch.cuda.get_device_properties(base.device).multi_processor_count
-        tiles = -(-B * T // 128)
-        per_chunk = (sms * 128) // T if T >= 128 else 0
-        # measured (r01, B200): with more than ~2 SM-fulls of tiles the per-layer launch path (3+ full waves) is as
-        # fast as running the persistent kernel chunk after chunk (C3: 75.7 ms vs 79.0 ms), so chunk only up to 2x
-        max_fulls = float(os.environ.get("DC_CHUNK_MAX", "2"))
-        if tiles <= sms or tiles > max_fulls * sms or per_chunk < 1 or B <= per_chunk:
-            return base
-        n_chunks = -(-B // per_chunk)
-        while len(self._chunk_engines) < n_chunks - 1:
-            e = _Engine(self, base.device_index)
-            e.upload(self)
-            self._chunk_engines.append(e)
-        size, extra = divmod(B, n_chunks)
-        bounds, a = [], 0
-        for i in range(n_chunks):
-            b = a + size + (1 if i < extra else 0)
-            bounds.append((a, b))
-            a = b
-        return _ChunkedEngine([base] + self._chunk_engines[: n_chunks - 1], bounds)
+        """Engine for a (B, T) batch: one handle serves any batch size.  Clips of up to 2048 frames run on the
+        cluster-per-clip persistent kernel (clusters are scheduled by the hardware as SMs free up); longer clips --
+        possible only when the model was built with num_frames > 2048 -- use the per-layer launch path of the same
+        handle (a captured CUDA graph per 5 steps)."""
+        return self.engine(device)
 
     # ---- reference API ------------------------------------------------------------------------
     def encode_music(self, text, device):
@@ -274,7 +257,7 @@ class MotionTransformer(nn.Module):
 
     def generate_src_mask(self, T, length):
         ar = torch.arange(T)[None, :]
-        return (ar < torch.as_tensor([int(v) for v in length])[:, None]).float()
+        return (ar < torch.as_tensor(_as_int_list(length))[:, None]).float()
 
     def forward(self, x, timesteps, length=None, text=None, xf_proj=None, xf_out=None):
         """x: (B,T,26) or (B,T,13,2); timesteps: (B,) integer; returns predicted x0 (B,T,26)."""
@@ -312,7 +295,7 @@ class _Engine:
         self.handle = handle
         self._cond_key = None
         self._schedule_key = None
-        self.B = self.T = 0
+        self.B = self.T = self.S = 0
 
     def __del__(self):
         try:
@@ -341,13 +324,18 @@ class _Engine:
         self._ck(self.lib.dc_finalize_weights(self.handle))
         self._cond_key = None
 
-    def set_schedule(self, key, coef: torch.Tensor):
-        if key == self._schedule_key:
-            return
+    def set_schedule(self, coef: torch.Tensor):
+        """Upload the [S, 8] coefficient table unless it is, value for value, the one already in the library.  The cache
+        is keyed on the table CONTENT: object ids are reused by CPython, and a stale table with another S would make the
+        library index noise / trace buffers that Python sized for the new S."""
         coef = coef.detach().to("cpu", torch.float32).contiguous()
         assert coef.dim() == 2 and coef.shape[1] == 8
+        key = (int(coef.shape[0]), coef.numpy().tobytes())
+        if key == self._schedule_key:
+            return
         self._ck(self.lib.dc_set_schedule(self.handle, coef.shape[0], C.c_void_p(coef.data_ptr())))
         self._schedule_key = key
+        self.S = int(coef.shape[0])
 
     @staticmethod
     def _f32(t: torch.Tensor, device) -> torch.Tensor:
@@ -359,7 +347,7 @@ class _Engine:
         if tuple(xf_proj.shape) != (B, T, 64) or tuple(xf_out.shape) != (B, T, 64):
             raise ValueError(f"xf_proj/xf_out must be (B,T,64)=({B},{T},64); music frames must equal motion frames "
                              f"(got {tuple(xf_proj.shape)}, {tuple(xf_out.shape)})")
-        length = [int(v) for v in length]
+        length = _as_int_list(length)
         if len(length) != B:
             raise ValueError("len(length) must equal the batch size")
         key = (xf_proj.data_ptr(), xf_proj._version, xf_out.data_ptr(), xf_out._version, B, T, tuple(length))
@@ -404,9 +392,29 @@ class _Engine:
                                          self.stream()))
         return x0
 
-    def sample_loop(self, sampler: int, x: torch.Tensor, step_noise=None, trace_x0=None, trace_x=None):
+    def sample_loop(self, sampler: int, x: torch.Tensor, step_noise=None, trace_x0=None, trace_x=None, num_steps=None):
+        """num_steps: the S the caller sized step_noise / traces for (defaults to their leading dimension, else the
+        schedule last uploaded through this engine); the library refuses a mismatch with its own schedule."""
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
-        self._ck(self.lib.dc_sample_loop(self.handle, sampler, p(x), p(step_noise), p(trace_x0), p(trace_x), self.stream()))
+        if num_steps is None:
+            sized = [t for t in (step_noise, trace_x0, trace_x) if t is not None]
+            num_steps = int(sized[0].shape[0]) if sized else self.S
+        for t in (step_noise, trace_x0, trace_x):
+            if t is not None and (int(t.shape[0]) != num_steps or t.numel() != num_steps * x.numel()):
+                raise ValueError(f"per-step buffers must be [{num_steps}, *x.shape]; got {tuple(t.shape)}")
+        self._ck(self.lib.dc_sample_loop(self.handle, sampler, int(num_steps), p(x), p(step_noise), p(trace_x0), p(trace_x), self.stream()))
+
+    def time_embedding(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """time_embed(timestep_embedding(t, latent_dim)) -> (n, 512) (reference transformer.py:8-25, 410-414, 482)."""
+        t = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(t.numel(), 512, device=self.device)
+        self._ck(self.lib.dc_time_embedding(self.handle, C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(out.data_ptr()), self.stream()))
+        return out
+
+    def cluster_occupancy(self, tiles_per_clip: int) -> int:
+        n = C.c_int(0)
+        self._ck(self.lib.dc_cluster_occupancy(self.handle, int(tiles_per_clip), C.byref(n)))
+        return int(n.value)
 
     def sampler_update(self, sampler: int, x: torch.Tensor, x0: torch.Tensor, step: int, noise=None):
         nz = C.c_void_p(noise.data_ptr()) if noise is not None else None
@@ -414,7 +422,7 @@ class _Engine:
                                             x.numel(), self.stream()))
 
     def generate_host(self, sampler, xf_proj, xf_out, length, noise, out, B, T):
-        arr = (C.c_int64 * B)(*[int(v) for v in length]) if length is not None else None
+        arr = (C.c_int64 * B)(*_as_int_list(length)) if length is not None else None
         self._ck(self.lib.dc_generate_host(self.handle, sampler, C.c_void_p(xf_proj.data_ptr()), C.c_void_p(xf_out.data_ptr()),
                                            arr, C.c_void_p(noise.data_ptr()), C.c_void_p(out.data_ptr()), B, T, self.stream()))
         self._cond_key = None
@@ -433,61 +441,3 @@ class _Engine:
 
     def set_graphs(self, enabled: bool):
         self._ck(self.lib.dc_set_graphs(self.handle, 1 if enabled else 0))
-
-
-class _ChunkedEngine:
-    """Same interface as _Engine over a batch cut into contiguous chunks of clips, one handle per chunk."""
-
-    def __init__(self, engines, bounds):
-        self.engines, self.bounds = engines, bounds
-        self.device = engines[0].device
-        self.device_index = engines[0].device_index
-        self.B = self.T = 0
-
-    def _each(self):
-        return zip(self.engines, self.bounds)
-
-    def set_schedule(self, key, coef):
-        for e in self.engines:
-            e.set_schedule(key, coef)
-
-    def prepare(self, xf_proj, xf_out, length, B, T):
-        xf_proj = _Engine._f32(xf_proj, self.device)
-        xf_out = _Engine._f32(xf_out, self.device)
-        length = [int(v) for v in length]
-        if len(length) != B:
-            raise ValueError("len(length) must equal the batch size")
-        for e, (a, b) in self._each():
-            e.prepare(xf_proj[a:b], xf_out[a:b], length[a:b], b - a, T)
-        self._keepalive = (xf_proj, xf_out)
-        self.B, self.T = B, T
-
-    def forward(self, x, timesteps):
-        x = _Engine._f32(x, self.device)
-        out = torch.empty_like(x)
-        for e, (a, b) in self._each():
-            out[a:b] = e.forward(x[a:b], timesteps[a:b])
-        return out
-
-    def sample_step(self, sampler, x, step, noise):
-        x0 = torch.empty_like(x)
-        for e, (a, b) in self._each():
-            x0[a:b] = e.sample_step(sampler, x[a:b], step, None if noise is None else noise[a:b])
-        return x0
-
-    def sample_loop(self, sampler, x, step_noise=None, trace_x0=None, trace_x=None):
-        for e, (a, b) in self._each():
-            sn = None if step_noise is None else step_noise[:, a:b].contiguous()
-            t0 = None if trace_x0 is None else torch.empty_like(trace_x0[:, a:b].contiguous())
-            t1 = None if trace_x is None else torch.empty_like(trace_x[:, a:b].contiguous())
-            e.sample_loop(sampler, x[a:b], step_noise=sn, trace_x0=t0, trace_x=t1)
-            if t0 is not None:
-                trace_x0[:, a:b] = t0
-            if t1 is not None:
-                trace_x[:, a:b] = t1
-
-    def sampler_update(self, sampler, x, x0, step, noise=None):
-        self.engines[0].sampler_update(sampler, x, x0, step, noise)
-
-    def kernel_launches(self) -> int:
-        return sum(e.kernel_launches() for e in self.engines)

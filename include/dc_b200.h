@@ -97,8 +97,9 @@ int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0,
  * runs steps S-1 .. 0 from x (initial noise, updated in place to the final sample) as ONE launch of the
  * persistent cluster-per-clip kernel (clips of up to 2048 frames; longer clips: a captured CUDA graph of
  * per-layer launches).  step_noise: DEVICE [S][B][T][26] in loop order or NULL.  trace_x0 / trace_x:
- * DEVICE [S][B][T][26] receiving pred_xstart / sample of every step, or NULL. */
-int dc_sample_loop(dc_handle* h, int sampler, float* x, const float* step_noise, float* trace_x0, float* trace_x,
+ * DEVICE [S][B][T][26] receiving pred_xstart / sample of every step, or NULL.  num_steps is the S the caller sized those
+ * buffers for (GaussianDiffusion.num_timesteps): the call fails with DC_ERR_STATE when it is not the S of dc_set_schedule. */
+int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x,
                    void* stream);
 
 /* generate_music_motion (ddpm_trainer.py:183-201) with HOST buffers: uploads the encode_music
@@ -130,6 +131,15 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
  * the host layer from (window, order).  Stateless: no handle. */
 int dc_smooth_motion(int device, const float* motion, float* out, int B, int T, int C, int window, const float* fir, const float* edge,
                      float scale, void* stream);
+
+/* timestep_embedding + time_embed (transformer.py:8-25, 410-414, 482): out[i] = time_embed(timestep_embedding(timesteps[i], 128)),
+ * timesteps DEVICE int64 [n], out DEVICE [n][512].  The same kernel tabulates the schedule in dc_set_schedule. */
+int dc_time_embedding(dc_handle* h, const int64_t* timesteps, int n, float* out, void* stream);
+
+/* How many clusters of `tiles_per_clip` CTAs (one clip of up to 128 * tiles_per_clip frames each) of the persistent sampling
+ * kernel this device can run concurrently (cudaOccupancyMaxActiveClusters).  dc_prepare_cond fails with DC_ERR_UNSUPPORTED when
+ * this is 0 for the clip length it is given (unless DC_PERSIST=0 selects the per-layer launch path). */
+int dc_cluster_occupancy(dc_handle* h, int tiles_per_clip, int* max_clusters);
 
 /* Number of this library's kernels launched so far (graph replays count their kernel nodes). */
 int64_t dc_kernel_launches(const dc_handle* h);

@@ -22,9 +22,10 @@ def main():
     def sample_fn(xp, xo, nz, ln):      # CPU stand-in for the CUDA sampler: the oracle
         return O.sample_loop(sd, tb, nz, ln, xp, xo, max_steps=2)[0]
 
-    gathered = sharded_sample(sample_fn, xf_proj, xf_out, noise, length)
+    gathered = sharded_sample(sample_fn, xf_proj, xf_out, noise, length)        # 5 clips over 2 ranks: unequal shards (padded gather)
     single = sample_fn(xf_proj, xf_out, noise, length)
-    torch.save({"gathered": gathered, "single": single}, f"{sys.argv[1]}.{dist.get_rank()}")
+    even = sharded_sample(sample_fn, xf_proj[:4], xf_out[:4], noise[:4], length[:4])   # equal shards: one all_gather_into_tensor
+    torch.save({"gathered": gathered, "single": single, "even": even}, f"{sys.argv[1]}.{dist.get_rank()}")
     dist.destroy_process_group()
 
 

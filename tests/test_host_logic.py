@@ -152,3 +152,4 @@ def test_sharded_sampling_world_size_2_gloo(tmp_path):
     b = torch.load(str(out) + ".1")
     assert torch.equal(a["gathered"], b["gathered"])
     assert torch.equal(a["gathered"], a["single"])
+    assert torch.equal(a["even"], b["even"]) and torch.equal(a["even"], a["single"][:4])

@@ -120,3 +120,50 @@ def test_savgol_matrices_match_scipy():
         y[:half] = edge @ x[:kernel]
         y[-half:] = (edge @ x[::-1][:kernel])[::-1]
         assert np.allclose(y, savgol_filter(x, kernel, order), atol=1e-10)
+
+
+# ---- round-2 fixtures: the BASELINE.json configs pinned by the unmodified reference (oracle/make_golden.py pinned_configs)
+def _pin(x0s, S, steps):
+    return torch.stack([x0s[S - 1 - int(t)] for t in steps]).numpy()
+
+
+def test_c3_full_clip_vs_reference(golden_dir):
+    """north_star target: one 60 s clip (T = 1800, mel 5400 x 128), music encoder + 50-step DDIM."""
+    g = np.load(os.path.join(golden_dir, "c3_clip.npz"))
+    sd = synth_state_dict(0, num_layers=8)
+    mel, noise = synth_inputs(1, 1800, seed=3)
+    with torch.no_grad():
+        xp, xo = O.encode_music(sd, mel)
+    np.testing.assert_allclose(xo.numpy()[:, ::8], g["xf_out_rows8"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(xp.numpy()[:, ::8], g["xf_proj_rows8"], rtol=0, atol=2e-5)
+    final, x0s, _ = O.sample_loop(sd, O.Tables(O.linear_betas(50)), noise, [1800], xp, xo)
+    np.testing.assert_allclose(_pin(x0s, 50, g["steps"]), g["ddim_x0"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(final.numpy(), g["final"], rtol=0, atol=1e-4)
+
+
+def test_c2_schedule_pair_vs_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "c2_pair.npz"))
+    sd = synth_state_dict(0, num_layers=8)
+    xf_proj, xf_out = synth_features(2, 180, seed=21)
+    _, noise = synth_inputs(2, 180, seed=21)
+    final, x0s, _ = O.sample_loop(sd, O.Tables(O.linear_betas(50)), noise, [180, 180], xf_proj, xf_out)
+    np.testing.assert_allclose(_pin(x0s, 50, g["steps"]), g["ddim_x0"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(final.numpy(), g["final"], rtol=0, atol=5e-5)
+
+
+def ddpm_noise_stream(seed, S, shape):
+    """The per-step noise the reference draws (gaussian_diffusion.py:656: one randn_like per step from torch's global CPU
+    generator), regenerated from the seed stored in the fixture."""
+    torch.manual_seed(int(seed))
+    return torch.stack([torch.randn(*shape) for _ in range(S)])
+
+
+def test_ddpm_1000_steps_vs_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ddpm1000.npz"))
+    sd = synth_state_dict(0, num_layers=8)
+    xf_proj, xf_out = synth_features(1, 180, seed=22)
+    _, noise = synth_inputs(1, 180, seed=22)
+    nz = ddpm_noise_stream(g["seed"], 1000, (1, 180, 26))
+    _, x0s, smp = O.sample_loop(sd, O.Tables(O.linear_betas(1000)), noise, [180], xf_proj, xf_out, kind="ddpm", step_noise=nz)
+    got = torch.stack([smp[999 - int(t)] for t in g["steps"]]).numpy()
+    np.testing.assert_allclose(got, g["ddpm_sample"], rtol=0, atol=2e-4)
