@@ -20,7 +20,7 @@ EXPORTS = [
     "dc_last_error", "dc_create", "dc_destroy", "dc_set_weight", "dc_finalize_weights", "dc_set_schedule",
     "dc_prepare_cond", "dc_forward", "dc_sample_step", "dc_sampler_update", "dc_sample_loop", "dc_generate_host",
     "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step", "dc_debug_timeline", "dc_smooth_motion",
-    "dc_encode_music", "dc_time_embedding", "dc_cluster_occupancy",
+    "dc_encode_music", "dc_time_embedding", "dc_cluster_occupancy", "dc_sample_range",
 ]
 
 
@@ -57,6 +57,7 @@ def load() -> C.CDLL:
     lib.dc_sample_step.argtypes = [vp, i32, fp, fp, i32, fp, vp]
     lib.dc_sampler_update.argtypes = [vp, i32, fp, fp, i32, fp, i64, vp]
     lib.dc_sample_loop.argtypes = [vp, i32, i32, fp, fp, fp, fp, vp]
+    lib.dc_sample_range.argtypes = [vp, i32, i32, i32, fp, fp, fp, fp, vp]
     lib.dc_generate_host.argtypes = [vp, i32, fp, fp, C.POINTER(i64), fp, fp, i32, i32, vp]
     lib.dc_profile_step.argtypes = [vp, i32, fp, i32, C.POINTER(C.c_float), C.POINTER(i32), vp]
     lib.dc_debug_timeline.argtypes = [vp, fp, i32, C.POINTER(C.c_uint64), i32]

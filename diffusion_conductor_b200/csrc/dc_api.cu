@@ -1047,35 +1047,33 @@ int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0,
     return 0;
 }
 
-int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x, void* stream) {
-    if (int rc = check_sampling(h, sampler, "dc_sample_loop")) return rc;
-    if (!x) return fail(h, DC_ERR_INVALID, "dc_sample_loop: null x");
-    if (num_steps != h->S)
-        return fail(h, DC_ERR_STATE, "dc_sample_loop: caller expects %d steps but the schedule set with dc_set_schedule has %d "
-                    "(the noise / trace buffers are sized by the caller)", num_steps, h->S);
+int dc_sample_range(dc_handle* h, int sampler, int step0, int n_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x,
+                    void* stream) {
+    if (int rc = check_sampling(h, sampler, "dc_sample_range")) return rc;
+    if (!x) return fail(h, DC_ERR_INVALID, "dc_sample_range: null x");
+    if (step0 < 0 || step0 >= h->S || n_steps < 1 || n_steps > step0 + 1)
+        return fail(h, DC_ERR_INVALID, "dc_sample_range: steps %d .. %d are outside the schedule of %d steps", step0, step0 - n_steps + 1, h->S);
     DC_CUDA(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)h->M * kP;
-    const int S = h->S;
     const bool traced = trace_x0 || trace_x || step_noise;
+    const bool whole = step0 == h->S - 1 && n_steps == h->S;
 
-    // The loop body reads its step index from device memory, so one captured step serves all S
-    // replays; per-step noise / trace slices are addressed by plain pointer arithmetic on the host,
-    // which forces the un-captured path when they are requested.
     DC_CUDA(h, cudaMemcpyAsync(h->xwork, x, n * 4, cudaMemcpyDeviceToDevice, st));
-    set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, S - 1, 0);
+    set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, step0, 0);
     h->launches++;
     const int64_t per_step = (h->fuse_kv ? 1 : 2) * (int64_t)h->cfg.num_layers + 4;
     if (h->persist) {
-        // the whole sampling loop is ONE launch of the persistent kernel (noise / trace slices are strides inside it)
+        // the whole block of steps is ONE launch of the persistent kernel (noise / trace slices are strides inside it)
         if (int rc = enqueue_persistent(h, h->xwork, h->te_table, 0, kE, sampler, h->xwork, trace_x0 ? trace_x0 : h->x0work, trace_x0 ? n : 0,
-                                        trace_x, step_noise, step_noise ? n : 0, S - 1, S, st))
+                                        trace_x, step_noise, step_noise ? n : 0, step0, n_steps, st))
             return rc;
-    } else if (h->use_graphs && !traced) {
+    } else if (h->use_graphs && !traced && whole) {
+        // per-layer path: the loop body reads its step index from device memory, so one captured 5-step graph is replayed S/5
+        // times; per-step noise / trace slices are host pointer arithmetic, which forces the un-captured path below
         GraphKey key;
         key.sampler = sampler;
-        // per-layer path: the step index lives in device memory and a 5-step graph is replayed S/5 times
-        key.steps = (S % 5 == 0) ? 5 : 1;
+        key.steps = (n_steps % 5 == 0) ? 5 : 1;
         if (!h->gexec || !(h->gkey == key)) {
             drop_graph(h);
             cudaGraph_t graph = nullptr;
@@ -1098,13 +1096,13 @@ int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const flo
             DC_CUDA(h, ce);
             h->gkey = key;
         }
-        for (int i = 0; i < S / key.steps; ++i) DC_CUDA(h, cudaGraphLaunch(h->gexec, st));
-        h->launches += (int64_t)S * per_step;
+        for (int i = 0; i < n_steps / key.steps; ++i) DC_CUDA(h, cudaGraphLaunch(h->gexec, st));
+        h->launches += (int64_t)n_steps * per_step;
     } else {
-        for (int i = 0; i < S; ++i) {
+        for (int i = 0; i < n_steps; ++i) {
             const float* nz = step_noise ? step_noise + (size_t)i * n : nullptr;
             float* x0dst = trace_x0 ? trace_x0 + (size_t)i * n : h->x0work;
-            if (int rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, x0dst, nz, S - 1 - i, st)) return rc;
+            if (int rc = enqueue_step(h, h->xwork, h->te_table, 0, true, sampler, h->xwork, x0dst, nz, step0 - i, st)) return rc;
             if (trace_x) DC_CUDA(h, cudaMemcpyAsync(trace_x + (size_t)i * n, h->xwork, n * 4, cudaMemcpyDeviceToDevice, st));
             set_step_kernel<<<1, 1, 0, st>>>(h->step_ctr, 0, -1);
             h->launches++;
@@ -1113,6 +1111,14 @@ int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const flo
     DC_CUDA(h, cudaMemcpyAsync(x, h->xwork, n * 4, cudaMemcpyDeviceToDevice, st));
     DC_CUDA(h, cudaGetLastError());
     return 0;
+}
+
+int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x, void* stream) {
+    if (int rc = check_sampling(h, sampler, "dc_sample_loop")) return rc;
+    if (num_steps != h->S)
+        return fail(h, DC_ERR_STATE, "dc_sample_loop: caller expects %d steps but the schedule set with dc_set_schedule has %d "
+                    "(the noise / trace buffers are sized by the caller)", num_steps, h->S);
+    return dc_sample_range(h, sampler, h->S - 1, h->S, x, step_noise, trace_x0, trace_x, stream);
 }
 
 int dc_generate_host(dc_handle* h, int sampler, const float* xf_proj, const float* xf_out, const int64_t* length, const float* noise,

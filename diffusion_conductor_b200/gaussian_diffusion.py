@@ -88,6 +88,8 @@ def _extract_into_tensor(arr, timesteps, broadcast_shape):
 
 
 class GaussianDiffusion:
+    NOISE_BLOCK_BYTES = 1 << 30      # pre-drawn step noise of stochastic loops is generated in blocks of at most this size
+
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False):
         self.model_mean_type = model_mean_type
         self.model_var_type = model_var_type
@@ -293,23 +295,34 @@ class GaussianDiffusion:
         x = self._as_state(img, eng.device).clone()
         S = self.num_timesteps
         stochastic = sampler == _lib.DC_SAMPLER_DDPM or eta != 0.0
-        step_noise = None
-        if stochastic:
-            # same generator draws, in the same order, as the reference's per-step randn_like; one [S, ...] buffer filled
-            # slice by slice (normal_ on a contiguous slice consumes the generator exactly like randn_like of that shape)
-            step_noise = th.empty((S,) + tuple(x.shape), device=x.device, dtype=th.float32)
-            for i in range(S):
-                step_noise[i].normal_()
-        elif match_rng_stream:
-            _advance_rng_like_randn(x, S)
         trace = th.empty((S,) + tuple(x.shape), device=x.device, dtype=th.float32) if len(idxs) else None
         flags = sampler | (_lib.DC_FLAG_CLIP if clip_denoised else 0)
         if progress:
             from tqdm.auto import tqdm
             bar = tqdm(total=S)
-        eng.sample_loop(flags, x, step_noise=step_noise, trace_x=trace, num_steps=S)
+        if stochastic:
+            # The reference draws one randn_like per step from torch's generator; here the same draws, in the same order
+            # (normal_ on a contiguous slice consumes the generator exactly like randn_like of that shape), land in a noise
+            # buffer that is bounded to NOISE_BLOCK_BYTES: the loop runs as ceil(S / block) launches of `block` steps each.
+            block = max(1, min(S, self.NOISE_BLOCK_BYTES // max(1, x.numel() * 4)))
+            buf = th.empty((block,) + tuple(x.shape), device=x.device, dtype=th.float32)
+            done = 0
+            while done < S:
+                n = min(block, S - done)
+                for i in range(n):
+                    buf[i].normal_()
+                eng.sample_range(flags, x, S - 1 - done, n, step_noise=buf[:n],
+                                 trace_x=None if trace is None else trace[done:done + n])
+                done += n
+                if progress:
+                    bar.update(n)
+        else:
+            if match_rng_stream:
+                _advance_rng_like_randn(x, S)
+            eng.sample_loop(flags, x, trace_x=trace, num_steps=S)
+            if progress:
+                bar.update(S)
         if progress:
-            bar.update(S)
             bar.close()
         final = x.view(img.shape)
         if len(idxs) == 0:

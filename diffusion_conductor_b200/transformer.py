@@ -404,6 +404,15 @@ class _Engine:
                 raise ValueError(f"per-step buffers must be [{num_steps}, *x.shape]; got {tuple(t.shape)}")
         self._ck(self.lib.dc_sample_loop(self.handle, sampler, int(num_steps), p(x), p(step_noise), p(trace_x0), p(trace_x), self.stream()))
 
+    def sample_range(self, sampler: int, x: torch.Tensor, step0: int, n_steps: int, step_noise=None, trace_x0=None, trace_x=None):
+        """Steps step0, step0 - 1, ... (n_steps of them) in one launch; per-step buffers are [n_steps, *x.shape]."""
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        for t in (step_noise, trace_x0, trace_x):
+            if t is not None and t.numel() != n_steps * x.numel():
+                raise ValueError(f"per-step buffers must be [{n_steps}, *x.shape]; got {tuple(t.shape)}")
+        self._ck(self.lib.dc_sample_range(self.handle, sampler, int(step0), int(n_steps), p(x), p(step_noise), p(trace_x0), p(trace_x),
+                                          self.stream()))
+
     def time_embedding(self, timesteps: torch.Tensor) -> torch.Tensor:
         """time_embed(timestep_embedding(t, latent_dim)) -> (n, 512) (reference transformer.py:8-25, 410-414, 482)."""
         t = timesteps.detach().to(device=self.device, dtype=torch.int64).contiguous()

@@ -102,6 +102,12 @@ int dc_sampler_update(dc_handle* h, int sampler, float* x, const float* pred_x0,
 int dc_sample_loop(dc_handle* h, int sampler, int num_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x,
                    void* stream);
 
+/* A block of the same loop: the n_steps consecutive steps step0, step0 - 1, ... (one launch of the persistent kernel).  Buffers are
+ * [n_steps][B][T][26].  Lets a stochastic loop (DDPM, DDIM with eta > 0) bound its noise buffer: 1000 steps of a 32 x 1800-frame batch
+ * would otherwise need 6 GB of pre-drawn noise. */
+int dc_sample_range(dc_handle* h, int sampler, int step0, int n_steps, float* x, const float* step_noise, float* trace_x0, float* trace_x,
+                    void* stream);
+
 /* generate_music_motion (ddpm_trainer.py:183-201) with HOST buffers: uploads the encode_music
  * features and the initial noise, runs dc_prepare_cond + dc_sample_loop, downloads the motion and
  * synchronises the stream.  Host buffers should be pinned for asynchronous copies. */

@@ -430,6 +430,12 @@ def test_ddpm_1000_steps_small():
     b = d.p_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False,
                         model_kwargs=dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B))
     assert torch.equal(a, b) and not torch.equal(a, xs)
+    # bounded noise buffer: the same loop as 16 launches of <= 64 steps (dc_sample_range) is bit-identical
+    d.NOISE_BLOCK_BYTES = 64 * x.numel() * 4
+    torch.manual_seed(5)
+    c = d.p_sample_loop(m, x.shape, noise=x.cuda(), clip_denoised=False,
+                        model_kwargs=dict(xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda(), length=[T] * B), idxs=[10, 999])
+    assert torch.equal(c[1000], a) and sorted(c) == [10, 999, 1000] and torch.equal(c[999], a)
 
 
 def test_smooth_motion_on_device():
