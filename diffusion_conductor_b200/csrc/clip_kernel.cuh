@@ -54,6 +54,15 @@ struct StepArgs {
     int nt, rows_per;           // tiles (= cluster size) per clip, frames per tile
     const float* kshift;        // [L][128] static softmax shift of the self-attention keys (upper bound of |k|, see dc_api.cu)
     uint32_t static_mask;       // bit l set: layer l uses the static shift (no column-max pass)
+    // Exchange of the per-clip partials through GLOBAL memory instead of distributed shared memory (gx = 1; launched with
+    // cluster size 1).  Clusters of 9..16 CTAs fit only once per GPC (7 x 15 = 105 of the 148 SMs busy on a 1800-frame batch);
+    // without the cluster constraint every SM takes a tile.  Reduce-scatter + all-gather as in the large-cluster path; every
+    // 8-byte word carries its own flag (value | tag, tag = gx_tag0 + reduction sequence number + 1, unique per reduction and
+    // launch), so a reader simply re-reads until the tag is there: no fence, no separate flag, one L2 round trip per phase.
+    int gx;
+    uint2* gx_part;             // [B][2][nt][kKvPartFloats] (value, tag) partials, double-buffered by reduction parity
+    uint2* gx_slice;            // [B][2][128][8] (two 16-bit merged attention values, tag)
+    uint32_t gx_tag0;
 };
 enum { kOWeSa = 0, kOWoSa, kOWeCa, kOWqCa, kOWoCa, kOWeFf, kOW1, kOW2, kOWoFf, kOWq, kOWk, kOWv };
 
@@ -96,9 +105,95 @@ struct ClipBarriers : LayerBarriers {
     uint64_t w_free;                    // row threads -> MMA issuer: y_ca has been read out of W, h16 . W1 may start (16 warp arrivals)
 };
 
+// Merge of the per-clip partials through L2 (StepArgs::gx; only the kGx instantiation of the kernel contains it, so that the
+// cluster variant keeps its register allocation).
+template <bool kBf16>
+__device__ __forceinline__ void gx_merge(const uint2* pbase, uint2* slices, float4* comb /* [G <= 8][per] (M, sum, acc0, acc1) */, uint8_t* xbuf, int nt,
+                                         int rank, int tx, uint32_t gtag, bool static_shift) {
+    // reduce-scatter + all-gather through L2.  CTA `rank` merges key features [rank fs, rank fs + fs) of all nt partials:
+    // thread (g, dl, l2) takes the tiles j = g, g + G, ... (at most 3) of feature rank fs + dl, value columns 2 l2, 2 l2 + 1;
+    // the G groups combine through shared memory (ring B is idle here); the merged rows go out as (two 16-bit values, tag)
+    // words; then everyone gathers the 128 x 16 merged matrix.
+    const int fs = (kD + nt - 1) / nt;
+    const int per = fs * 8;                                      // threads per tile group
+    const int G = min(8, kRowThreads / per);                     // nt <= 16 -> ceil(nt / G) <= 3: one round trip
+    const int g = tx / per, idx = tx - g * per, dl = idx >> 3, l2 = idx & 7, d = rank * fs + dl;
+    const bool act = g < G && d < kD;
+    float Mx = -INFINITY, ss = 0.f, a0 = 0.f, a1 = 0.f;
+    if (act) {
+        // three tiles per round trip (registers), online-softmax accumulation across round trips
+        for (int k0 = 0; k0 < 3; k0 += 3) {
+            if (g + k0 * G >= nt) break;
+            uint4 pw[3];
+            uint2 sw[3], mw[3];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int j = g + (k0 + k) * G;
+                    if (j < nt) {
+                        const uint2* pp = pbase + (size_t)j * kKvPartFloats;
+                        pw[k] = ld_volatile_v4(reinterpret_cast<const uint4*>(pp + 256 + d * 16 + 2 * l2));
+                        sw[k] = ld_volatile_v2(pp + 128 + d);
+                        mw[k] = static_shift ? make_uint2(0u, gtag) : ld_volatile_v2(pp + d);
+                        ok = ok && pw[k].y == gtag && pw[k].w == gtag && sw[k].y == gtag && mw[k].y == gtag;
+                    }
+                }
+            } while (!ok);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (g + (k0 + k) * G < nt) {
+                    if (static_shift) {
+                        Mx = 0.f;
+                        ss += __uint_as_float(sw[k].x), a0 += __uint_as_float(pw[k].x), a1 += __uint_as_float(pw[k].z);
+                    } else {
+                        const float m = __uint_as_float(mw[k].x), nm = fmaxf(Mx, m);
+                        const float cs = __expf(Mx - nm), w = __expf(m - nm);          // exp(-inf) = 0 on the first tile
+                        ss = fmaf(__uint_as_float(sw[k].x), w, ss * cs);
+                        a0 = fmaf(__uint_as_float(pw[k].x), w, a0 * cs), a1 = fmaf(__uint_as_float(pw[k].z), w, a1 * cs);
+                        Mx = nm;
+                    }
+                }
+        }
+        if (G > 1) comb[g * per + idx] = make_float4(Mx, ss, a0, a1);
+    }
+    if (G > 1) {
+        named_bar_sync(5, kRowThreads);
+        if (act && g == 0) {
+            for (int k = 1; k < G; ++k) {
+                const float4 c = comb[k * per + idx];
+                if (static_shift) {
+                    ss += c.y, a0 += c.z, a1 += c.w;
+                } else {
+                    const float nm = fmaxf(Mx, c.x);
+                    const float cs = __expf(Mx - nm), w = __expf(c.x - nm);
+                    ss = fmaf(c.y, w, ss * cs), a0 = fmaf(c.z, w, a0 * cs), a1 = fmaf(c.w, w, a1 * cs);
+                    Mx = nm;
+                }
+            }
+        }
+    }
+    if (act && g == 0) {
+        const float inv = ss > 0.f ? 1.f / ss : 0.f;
+        st_global_v2(slices + d * 8 + l2, make_uint2(pack2<kBf16>(a0 * inv, a1 * inv), gtag));
+    }
+    {
+        const int dd = tx >> 2, q4 = tx & 3;
+        uint4 w;
+        do w = ld_volatile_v4(reinterpret_cast<const uint4*>(slices + dd * 8 + 2 * q4));
+        while (w.y != gtag || w.w != gtag);
+        const uint16_t vals[4] = {(uint16_t)(w.x & 0xFFFFu), (uint16_t)(w.x >> 16), (uint16_t)(w.z & 0xFFFFu), (uint16_t)(w.z >> 16)};
+        uint8_t* base = xbuf + (size_t)(dd >> 6) * kABlockBytes + (dd & 7) * 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint16_t*>(base + sw128_offset(16 * (dd >> 4) + 4 * q4 + i, (dd & 63) >> 3)) = vals[i];
+    }
+}
+
 // kTl: instrumented build for dc_debug_timeline (the marks cost ~5 % of the instruction stream, so the production
 // instantiation compiles them out)
-template <bool kBf16, bool kTl = false>
+template <bool kBf16, bool kTl = false, bool kGx = false>
 __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_constant__ StepArgs a) {
     constexpr int kNA = kPRingAStages, kSA = kStageBytes, kNB = kRingBStages, kSB = kRingBStageBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -210,7 +305,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     // ring B held the V image and then this tile's partial of the reduction that opened layer `it`:
                     // refill only when the local q . blockdiag(A_sa) has been issued AND every peer has pulled the partial
                     mbar_wait(smem_u32(&bars->q_full), qf++ & 1u);
-                    if (nt > 1) {
+                    if (!kGx && nt > 1) {
                         const uint32_t seq = (uint32_t)(si * L + it);
                         mbar_wait(smem_u32(&bars->pull_done[seq & 1u]), (seq >> 1) & 1u);
                     }
@@ -637,11 +732,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 float* pm = reinterpret_cast<float*>(xchg);            // [8 rg][128] exchange (max, then sums); xchg is idle here
                 float* msm = red;                                      // [128] maxima
                 float* ssm = msm + 128;                                // [128] sums
-                float* mypart = reinterpret_cast<float*>(ringB);       // [kKvPartFloats]
                 uint8_t* Xp = xbuf;
                 const uint32_t eimg = smem_u32(xbuf), vimg = smem_u32(ringB);
                 const int tx = threadIdx.x;
                 const uint32_t seq = (uint32_t)(si * L + it + 1);            // reductions completed so far in this launch
+                float* mypart = reinterpret_cast<float*>(ringB);             // [kKvPartFloats] (distributed-shared-memory exchange)
                 const int col = tx & 127;
                 // column pair (2 cp, 2 cp + 1), rows [16 rg, 16 rg + 16) of a [128 x 128] 16-bit operand image
                 const int cp = tx & 63, rg = tx >> 6;
@@ -759,24 +854,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 }
                 rows_wait(bars, 2, ph[2]);                                // E^T V complete: the E and V images are dead
                 tl.mark(123);
+                const uint32_t gtag = a.gx_tag0 + seq + 1u;
                 if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
                     float pr[32];
                     tmem_ld32(trow + kColW + 32 * lq, pr);
                     tmem_wait_ld();
-                    float4* dst = reinterpret_cast<float4*>(mypart + 256 + (r >> 4) * 256 + (r & 15) * 16);
                     const int o = (lane & 16);
+                    if constexpr (kGx) {
+                        uint2* gp = a.gx_part + (((size_t)clip * 2 + (seq & 1u)) * nt + rank) * kKvPartFloats;
+                        uint4* dst = reinterpret_cast<uint4*>(gp + 256 + r * 16);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
-                                   : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
-                    mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
+                        for (int i = 0; i < 8; ++i)
+                            st_global_v4(dst + i, make_uint4(__float_as_uint(o ? pr[16 + 2 * i] : pr[2 * i]), gtag,
+                                                             __float_as_uint(o ? pr[17 + 2 * i] : pr[2 * i + 1]), gtag));
+                        st_global_v2(gp + 128 + tx, make_uint2(__float_as_uint(ssm[tx]), gtag));
+                        if (!static_shift) st_global_v2(gp + tx, make_uint2(__float_as_uint(msm[tx]), gtag));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(mypart + 256 + (r >> 4) * 256 + (r & 15) * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
+                                       : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
+                        mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
+                    }
                 }
-                named_bar_sync(5, kRowThreads);                            // partial complete
+                if (!kGx) named_bar_sync(5, kRowThreads);                  // partial complete (global exchange: every word carries its own flag)
                 tl.mark(124);
                 // ---- publish to the peers: release at cluster scope, one remote arrive per peer
                 // (no separate fence: the arrive is a release at cluster scope, and release is cumulative over the writes of the
                 //  other row threads that were ordered before it by the CTA barrier above)
-                if (nt > 1 && tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
+                if (!kGx && nt > 1 && tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
                 // ---- while the peers' partials are in flight: clear the image buffer (the merge writes only the diagonal
                 //      blocks); the parameter blocks fetched with cp.async above must have landed before the barrier below
                 {
@@ -784,12 +891,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     for (int i = tx; i < kAworkBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(xbuf)[i] = z4;
                     cp_async_wait_all();
                 }
-                if (nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
+                if (!kGx && nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
                 named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared
                 tl.mark(125);
                 // ---- merge the nt partials (online-softmax rescaling, four tiles per round trip) into the block-diagonal
                 //      B-operand image.
-                if (nt <= kDirectMergeTiles) {
+                if constexpr (kGx) {
+                    gx_merge<kBf16>(a.gx_part + ((size_t)clip * 2 + (seq & 1u)) * nt * kKvPartFloats,
+                                    a.gx_slice + ((size_t)clip * 2 + (seq & 1u)) * (kD * 8), reinterpret_cast<float4*>(ringB), xbuf, nt, rank, tx,
+                                    gtag, static_shift);
+                } else if (nt <= kDirectMergeTiles) {
                     // small clusters: every CTA pulls every partial.  Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
                     const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
                     const uint32_t pbase = smem_u32(mypart);
@@ -890,7 +1001,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 }
                 rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
                 tl.mark(126);
-                if (nt > 1) {                                              // every pull of this CTA has completed: the peers may reuse ring B
+                if (!kGx && nt > 1) {                                      // every pull of this CTA has completed: the peers may reuse ring B
                     named_bar_sync(5, kRowThreads);                        // (off the critical path: the q . A GEMM is already on its way)
                     if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pull_done[seq & 1u]), (uint32_t)tx));
                 }

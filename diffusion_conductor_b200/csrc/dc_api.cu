@@ -117,6 +117,11 @@ struct dc_handle {
     bool persist = false;         // persistent sampling-loop kernel: one thread-block cluster per clip (T <= 16 tiles, any batch)
     int clip_nt = 1;              // tiles (= cluster size) per clip
     int clip_nt_checked = 0;      // last cluster size validated with cudaOccupancyMaxActiveClusters
+    bool clip_gx = false;         // per-clip exchange through global memory (cluster size 1) instead of distributed shared memory
+    uint2* gx_part = nullptr;     // [B][2][nt][kKvPartFloats] (value, tag)
+    uint2* gx_slice = nullptr;    // [B][2][128][8] (two 16-bit values, tag)
+    uint32_t gx_tag = 0;          // tags handed out so far (every reduction of every launch gets its own)
+    size_t gx_cap = 0, gx_cap_b = 0;   // B * nt and B the three buffers were sized for
     int num_sms = 0;
     unsigned long long* timeline = nullptr;   // debug: [launch][512] u64 (dc_debug_timeline)
     bool timeline_on = false;
@@ -243,6 +248,9 @@ void free_workspace(dc_handle* h) {
     if (h->kv_part) cudaFree(h->kv_part);
     if (h->clip_cnt) cudaFree(h->clip_cnt);
     h->kv_part = nullptr, h->clip_cnt = nullptr;
+    if (h->gx_part) cudaFree(h->gx_part);
+    if (h->gx_slice) cudaFree(h->gx_slice);
+    h->gx_part = nullptr, h->gx_slice = nullptr, h->gx_cap = 0, h->gx_cap_b = 0;
     void* ptrs[] = {h->xp, h->zimg, h->aemb, h->hbuf, h->q_img, h->kv, h->bd_sa, h->bd_ca, h->length,
                     h->te_b, h->xwork, h->x0work, h->in_proj, h->in_out};
     for (void* p : ptrs)
@@ -306,7 +314,9 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
-    void (*clip_variants[4])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>};
+    void (*clip_variants[8])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>,
+                                          clip_kernel<true, false, true>, clip_kernel<false, false, true>, clip_kernel<true, true, true>,
+                                          clip_kernel<false, true, true>};
     for (auto k : clip_variants) {
         DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
         DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
@@ -437,12 +447,27 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     for (int i = 0; i < 12; ++i) sa.off[i] = offs[i];
     sa.timeline = h->timeline_on ? h->timeline : nullptr;
     if (const char* dbg = getenv("DC_DBG")) sa.dbg = atoi(dbg);
-    // one cluster of clip_nt CTAs per clip; the kernel keeps no global exchange state
+    // clip_nt CTAs per clip: one cluster (exchange through distributed shared memory, no global state), or -- long clips --
+    // independent CTAs that exchange through L2 (flags zeroed per launch; relies on CTAs being dispatched in blockIdx order, so
+    // that the lowest-numbered unfinished clip always has all of its CTAs resident)
     sa.nt = h->clip_nt;
     sa.rows_per = (h->T + h->clip_nt - 1) / h->clip_nt;
-    void (*kern)(StepArgs) = h->timeline_on ? (h->bf16 ? clip_kernel<true, true> : clip_kernel<false, true>)
-                                            : (h->bf16 ? clip_kernel<true, false> : clip_kernel<false, false>);
-    DC_CUDA(h, launch_kc(h->use_pdl, h->clip_nt, kern, dim3((unsigned)(h->B * h->clip_nt)), dim3(kTileThreads), kClipSmemBytes, st, sa));
+    sa.gx = h->clip_gx ? 1 : 0;
+    if (h->clip_gx) {
+        const uint32_t need = (uint32_t)n_steps * (uint32_t)L + 1u;          // tags gx_tag + 1 .. gx_tag + need - 1 are used by this launch
+        if (h->gx_tag > 0xFFFFFFFFu - need - 1u) {                           // wrap-around: start over on cleared buffers
+            DC_CUDA(h, cudaMemsetAsync(h->gx_part, 0, h->gx_cap * 2 * kKvPartFloats * sizeof(uint2), st));
+            DC_CUDA(h, cudaMemsetAsync(h->gx_slice, 0, h->gx_cap_b * 2 * kD * 8 * sizeof(uint2), st));
+            h->gx_tag = 0;
+        }
+        sa.gx_part = h->gx_part, sa.gx_slice = h->gx_slice, sa.gx_tag0 = h->gx_tag;
+        h->gx_tag += need;
+    }
+    void (*kern)(StepArgs) = h->clip_gx ? (h->timeline_on ? (h->bf16 ? clip_kernel<true, true, true> : clip_kernel<false, true, true>)
+                                                          : (h->bf16 ? clip_kernel<true, false, true> : clip_kernel<false, false, true>))
+                                        : (h->timeline_on ? (h->bf16 ? clip_kernel<true, true> : clip_kernel<false, true>)
+                                                          : (h->bf16 ? clip_kernel<true, false> : clip_kernel<false, false>));
+    DC_CUDA(h, launch_kc(h->use_pdl, h->clip_gx ? 1 : h->clip_nt, kern, dim3((unsigned)(h->B * h->clip_nt)), dim3(kTileThreads), kClipSmemBytes, st, sa));
     h->launches++;
     DC_CUDA(h, cudaGetLastError());
     return 0;
@@ -941,7 +966,24 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         const char* pe = getenv("DC_PERSIST");
         const int nt = (T + kTileRows - 1) / kTileRows;
         bool persist = nt <= kMaxClipTiles && !h->use_pair && !(pe && pe[0] == '0');
-        if (persist && nt > 1 && nt != h->clip_nt_checked) {
+        // Clusters of more than 4 CTAs leave SMs idle (measured: 15 resident clusters of 8, 7 of 15 or 16 -- 120 / 105 of 148
+        // SMs): those clips run as independent CTAs that exchange their partials through L2.  DC_GX=0 / 1 forces the choice.
+        const char* gxe = getenv("DC_GX");
+        const bool gx = persist && nt > 1 && (gxe ? gxe[0] == '1' : nt > kDirectMergeTiles);
+        if (gx && ((size_t)B * nt > h->gx_cap || (size_t)B > h->gx_cap_b)) {
+            if (h->gx_part) cudaFree(h->gx_part);
+            if (h->gx_slice) cudaFree(h->gx_slice);
+            h->gx_part = nullptr, h->gx_slice = nullptr, h->gx_cap = 0, h->gx_cap_b = 0;
+            DC_CUDA(h, cudaMalloc((void**)&h->gx_part, (size_t)B * 2 * nt * kKvPartFloats * sizeof(uint2)));
+            DC_CUDA(h, cudaMalloc((void**)&h->gx_slice, (size_t)B * 2 * kD * 8 * sizeof(uint2)));
+            // tag 0 is never handed out: cleared buffers hold no valid word (the layout depends on nt, so a resize starts over too)
+            DC_CUDA(h, cudaMemsetAsync(h->gx_part, 0, (size_t)B * 2 * nt * kKvPartFloats * sizeof(uint2), st));
+            DC_CUDA(h, cudaMemsetAsync(h->gx_slice, 0, (size_t)B * 2 * kD * 8 * sizeof(uint2), st));
+            h->gx_tag = 0;
+            h->gx_cap = (size_t)B * nt, h->gx_cap_b = (size_t)B;
+        }
+        h->clip_gx = gx;
+        if (persist && nt > 1 && !gx && nt != h->clip_nt_checked) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)nt), cfg.blockDim = dim3(kTileThreads), cfg.dynamicSmemBytes = kClipSmemBytes;
             cudaLaunchAttribute at{};

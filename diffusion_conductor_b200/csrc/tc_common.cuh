@@ -328,6 +328,26 @@ __device__ __forceinline__ float2 ld_dsmem_f32x2(uint32_t cluster_addr) {
     return v;
 }
 
+// ---------------------------------------------------------------- flag-in-data exchange through global memory (L2)
+// Every 8-byte word is (value, tag): a naturally aligned 8-byte store is performed as one access, so a reader that sees the
+// expected tag also sees the value -- no fence, no separate flag.  Volatile accesses bypass L1.
+__device__ __forceinline__ void st_global_v2(uint2* p, uint2 v) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(uint4* p, uint4 v) {          // two (value, tag) words
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // The barriers the MMA issuer waits on are local to the leader CTA; the peer arrives on them with
 // release.cluster after fencing its own shared-memory writes for the async proxy.  Those writes are read by the
 // peer SM's own tensor-core datapath, so the ordinary CTA-scope probe is what is needed here (cluster-scope
