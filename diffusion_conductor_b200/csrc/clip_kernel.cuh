@@ -134,7 +134,7 @@ __device__ __forceinline__ void gx_merge(const uint2* pbase, uint2* slices, floa
                     const int j = g + (k0 + k) * G;
                     if (j < nt) {
                         const uint2* pp = pbase + (size_t)j * kKvPartFloats;
-                        pw[k] = ld_volatile_v4(reinterpret_cast<const uint4*>(pp + 256 + d * 16 + 2 * l2));
+                        pw[k] = ld_volatile_v4(reinterpret_cast<const uint4*>(pp + 256 + l2 * 256 + d * 2));
                         sw[k] = ld_volatile_v2(pp + 128 + d);
                         mw[k] = static_shift ? make_uint2(0u, gtag) : ld_volatile_v2(pp + d);
                         ok = ok && pw[k].y == gtag && pw[k].w == gtag && sw[k].y == gtag && mw[k].y == gtag;
@@ -855,28 +855,34 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 rows_wait(bars, 2, ph[2]);                                // E^T V complete: the E and V images are dead
                 tl.mark(123);
                 const uint32_t gtag = a.gx_tag0 + seq + 1u;
-                if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
+                if constexpr (kGx) {
+                    // TMEM lane = key feature r; the diagonal block of its head is 16 value columns: warp cq takes 4 of them, so all 16
+                    // row warps share the write.  Words are laid out [column pair][feature]: a warp's store is 512 contiguous bytes.
+                    float p0[4], p1[4];
+                    tmem_ld4(trow + kColW + 32 * lq + 4 * cq, p0);
+                    tmem_ld4(trow + kColW + 32 * lq + 16 + 4 * cq, p1);
+                    tmem_wait_ld();
+                    const bool hi = (lane & 16) != 0;
+                    uint2* gp = a.gx_part + (((size_t)clip * 2 + (seq & 1u)) * nt + rank) * kKvPartFloats;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        st_global_v4(reinterpret_cast<uint4*>(gp + 256 + (2 * cq + i) * 256 + r * 2),
+                                     make_uint4(__float_as_uint(hi ? p1[2 * i] : p0[2 * i]), gtag, __float_as_uint(hi ? p1[2 * i + 1] : p0[2 * i + 1]), gtag));
+                    if (cq == 0) {
+                        st_global_v2(gp + 128 + tx, make_uint2(__float_as_uint(ssm[tx]), gtag));
+                        if (!static_shift) st_global_v2(gp + tx, make_uint2(__float_as_uint(msm[tx]), gtag));
+                    }
+                } else if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
                     float pr[32];
                     tmem_ld32(trow + kColW + 32 * lq, pr);
                     tmem_wait_ld();
                     const int o = (lane & 16);
-                    if constexpr (kGx) {
-                        uint2* gp = a.gx_part + (((size_t)clip * 2 + (seq & 1u)) * nt + rank) * kKvPartFloats;
-                        uint4* dst = reinterpret_cast<uint4*>(gp + 256 + r * 16);
+                    float4* dst = reinterpret_cast<float4*>(mypart + 256 + (r >> 4) * 256 + (r & 15) * 16);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            st_global_v4(dst + i, make_uint4(__float_as_uint(o ? pr[16 + 2 * i] : pr[2 * i]), gtag,
-                                                             __float_as_uint(o ? pr[17 + 2 * i] : pr[2 * i + 1]), gtag));
-                        st_global_v2(gp + 128 + tx, make_uint2(__float_as_uint(ssm[tx]), gtag));
-                        if (!static_shift) st_global_v2(gp + tx, make_uint2(__float_as_uint(msm[tx]), gtag));
-                    } else {
-                        float4* dst = reinterpret_cast<float4*>(mypart + 256 + (r >> 4) * 256 + (r & 15) * 16);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
-                                       : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
-                        mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
+                                   : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
+                    mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];     // cq == 0 <=> tx < 128: this thread's own column max / sum
                 }
                 if (!kGx) named_bar_sync(5, kRowThreads);                  // partial complete (global exchange: every word carries its own flag)
                 tl.mark(124);

@@ -128,6 +128,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 4 consecutive columns
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 // 32 lanes x 8 consecutive columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     uint32_t r[8];
