@@ -21,6 +21,8 @@ EXPORTS = [
     "dc_prepare_cond", "dc_forward", "dc_sample_step", "dc_sampler_update", "dc_sample_loop", "dc_generate_host",
     "dc_kernel_launches", "dc_set_graphs", "dc_selftest_gemm", "dc_profile_step", "dc_debug_timeline", "dc_smooth_motion",
     "dc_encode_music", "dc_time_embedding", "dc_cluster_occupancy", "dc_sample_range",
+    "dc_eval_create", "dc_eval_destroy", "dc_eval_set_weight", "dc_eval_finalize", "dc_eval_motion_features", "dc_eval_feature_stats",
+    "dc_eval_feature_l1", "dc_eval_motion_beats", "dc_eval_beat_alignment",
 ]
 
 
@@ -69,6 +71,16 @@ def load() -> C.CDLL:
     lib.dc_time_embedding.argtypes = [vp, fp, i32, fp, vp]
     lib.dc_cluster_occupancy.argtypes = [vp, i32, C.POINTER(i32)]
     lib.dc_smooth_motion.argtypes = [i32, fp, fp, i32, i32, i32, i32, fp, fp, C.c_float, vp]
+    lib.dc_eval_create.argtypes = [i32, C.POINTER(vp)]
+    lib.dc_eval_destroy.argtypes = [vp]
+    lib.dc_eval_destroy.restype = None
+    lib.dc_eval_set_weight.argtypes = [vp, C.c_char_p, fp, i64]
+    lib.dc_eval_finalize.argtypes = [vp]
+    lib.dc_eval_motion_features.argtypes = [vp, fp, fp, i32, i32, vp]
+    lib.dc_eval_feature_stats.argtypes = [i32, fp, i64, fp, fp, vp]
+    lib.dc_eval_feature_l1.argtypes = [i32, fp, fp, i64, fp, vp]
+    lib.dc_eval_motion_beats.argtypes = [i32, fp, fp, fp, i32, i32, i32, vp]
+    lib.dc_eval_beat_alignment.argtypes = [i32, fp, i32, fp, i32, i32, C.c_float, fp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("dc_last_error", "dc_destroy", "dc_kernel_launches"):

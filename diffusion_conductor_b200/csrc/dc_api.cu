@@ -17,6 +17,7 @@
 #include "../../include/dc_b200.h"
 #include "clip_kernel.cuh"
 #include "music_encoder.cuh"
+#include "eval_kernels.cuh"
 
 using namespace dc;
 
@@ -1382,6 +1383,227 @@ int dc_selftest_gemm(int device, int operand, int M, int N, int K, const float* 
     DC_CUDA(nullptr, cudaMemcpy(out, dout, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
     cudaFree(da), cudaFree(dw), cudaFree(dout);
     if (db) cudaFree(db);
+    return 0;
+}
+
+// =============================================================================================
+// Evaluation features: ST-GCN motion encoder + metric reductions, see eval_kernels.cuh
+// =============================================================================================
+struct dc_eval {
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> w;          // host copies by state_dict key
+    float* pool = nullptr;                                // one device allocation for all folded parameters
+    dc::StgcnLayer layer[dc::kEvLayers];
+    const float* dbn = nullptr;                           // [2][26]
+    const float* wfc = nullptr;                           // [416][64]
+    const float* bfc = nullptr;                           // [64]
+    float* act[2] = {nullptr, nullptr};                   // [N * T][13][32] ping-pong
+    size_t act_rows = 0;
+};
+
+static int efail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define EV_CUDA(expr)                                                                                            \
+    do {                                                                                                         \
+        cudaError_t e_ = (expr);                                                                                 \
+        if (e_ != cudaSuccess) return efail(DC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));               \
+    } while (0)
+
+int dc_eval_create(int device, dc_eval** out) {
+    if (!out) return efail(DC_ERR_INVALID, "dc_eval_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return efail(DC_ERR_CUDA, "dc_eval_create: CUDA device %d unavailable; there is no CPU fallback", device);
+    EV_CUDA(cudaSetDevice(device));
+    EV_CUDA(cudaFuncSetAttribute(dc::stgcn_layer_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::stgcn_smem_bytes(32)));
+    EV_CUDA(cudaFuncSetAttribute(dc::stgcn_layer_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dc::stgcn_smem_bytes(2)));
+    dc_eval* e = new dc_eval();
+    e->device = device;
+    *out = e;
+    return 0;
+}
+
+void dc_eval_destroy(dc_eval* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->pool) cudaFree(e->pool);
+    if (e->act[0]) cudaFree(e->act[0]);
+    if (e->act[1]) cudaFree(e->act[1]);
+    delete e;
+}
+
+int dc_eval_set_weight(dc_eval* e, const char* key, const float* data, int64_t count) {
+    if (!e || !key || !data || count < 0) return efail(DC_ERR_INVALID, "dc_eval_set_weight: bad argument");
+    std::vector<float> v((size_t)count);
+    EV_CUDA(cudaSetDevice(e->device));
+    EV_CUDA(cudaMemcpy(v.data(), data, (size_t)count * 4, cudaMemcpyDefault));
+    e->w[key] = std::move(v);
+    e->finalized = false;
+    return 0;
+}
+
+int dc_eval_finalize(dc_eval* e) {
+    if (!e) return efail(DC_ERR_INVALID, "dc_eval_finalize: null handle");
+    using namespace dc;
+    auto get = [&](const std::string& k, size_t n) -> const float* {
+        auto it = e->w.find(k);
+        if (it == e->w.end()) {
+            efail(DC_ERR_INVALID, "dc_eval_finalize: missing weight %s", k.c_str());
+            return nullptr;
+        }
+        if (it->second.size() != n) {
+            efail(DC_ERR_INVALID, "dc_eval_finalize: weight %s has %zu elements, expected %zu", k.c_str(), it->second.size(), n);
+            return nullptr;
+        }
+        return it->second.data();
+    };
+    // eval-mode BatchNorm -> (scale, shift) in fp64 (torch: (x - mean) / sqrt(var + 1e-5) * weight + bias)
+    auto bn = [&](const std::string& p, int c, std::vector<double>& sc, std::vector<double>& sh) -> bool {
+        const float *g = get(p + ".weight", c), *b = get(p + ".bias", c), *m = get(p + ".running_mean", c), *v = get(p + ".running_var", c);
+        if (!g || !b || !m || !v) return false;
+        sc.resize(c), sh.resize(c);
+        for (int i = 0; i < c; ++i) {
+            sc[i] = (double)g[i] / std::sqrt((double)v[i] + 1e-5);
+            sh[i] = (double)b[i] - (double)m[i] * sc[i];
+        }
+        return true;
+    };
+    std::vector<float> pool;
+    auto push = [&](const std::vector<double>& v) -> size_t {
+        const size_t off = pool.size();
+        for (double x : v) pool.push_back((float)x);
+        while (pool.size() % 4) pool.push_back(0.f);
+        return off;
+    };
+    const float* A = get("st_gcn.A", kEvV * kEvV);
+    if (!A) return DC_ERR_INVALID;
+    size_t off[kEvLayers][5];
+    std::vector<double> sc, sh;
+    if (!bn("st_gcn.data_bn", 2 * kEvV, sc, sh)) return DC_ERR_INVALID;
+    std::vector<double> dbn(4 * kEvV);
+    for (int i = 0; i < 2 * kEvV; ++i) dbn[i] = sc[i], dbn[2 * kEvV + i] = sh[i];      // channel index = joint * 2 + coordinate
+    const size_t off_dbn = push(dbn);
+    for (int l = 0; l < kEvLayers; ++l) {
+        const int cin = l == 0 ? 2 : kEvC;
+        const std::string p = "st_gcn.st_gcn_networks." + std::to_string(l);
+        const float *wg = get(p + ".gcn.conv.weight", (size_t)kEvC * cin), *bg = get(p + ".gcn.conv.bias", kEvC);
+        const float *wt = get(p + ".tcn.2.weight", (size_t)kEvC * kEvC * 3), *bt = get(p + ".tcn.2.bias", kEvC);
+        const float* imp = get("st_gcn.edge_importance." + std::to_string(l), kEvV * kEvV);
+        std::vector<double> s1, h1, s2, h2;
+        if (!wg || !bg || !wt || !bt || !imp || !bn(p + ".tcn.0", kEvC, s1, h1) || !bn(p + ".tcn.3", kEvC, s2, h2)) return DC_ERR_INVALID;
+        std::vector<double> fwg((size_t)cin * kEvC), ae(kEvV * kEvV), cg(kEvV * kEvC), fwt(3 * kEvC * kEvC), ct(kEvC);
+        for (int c = 0; c < kEvC; ++c)
+            for (int ci = 0; ci < cin; ++ci) fwg[(size_t)ci * kEvC + c] = s1[c] * (double)wg[c * cin + ci];
+        for (int i = 0; i < kEvV * kEvV; ++i) ae[i] = (double)((float)A[i] * (float)imp[i]);          // fp32 product, as self.A * importance
+        for (int w = 0; w < kEvV; ++w) {
+            double cs = 0.0;
+            for (int v = 0; v < kEvV; ++v) cs += ae[v * kEvV + w];
+            for (int c = 0; c < kEvC; ++c) cg[w * kEvC + c] = s1[c] * (double)bg[c] * cs + h1[c];
+        }
+        for (int co = 0; co < kEvC; ++co) {
+            for (int ci = 0; ci < kEvC; ++ci)
+                for (int dt = 0; dt < 3; ++dt) fwt[((size_t)dt * kEvC + ci) * kEvC + co] = s2[co] * (double)wt[(co * kEvC + ci) * 3 + dt];
+            ct[co] = s2[co] * (double)bt[co] + h2[co];
+        }
+        off[l][0] = push(fwg), off[l][1] = push(ae), off[l][2] = push(cg), off[l][3] = push(fwt), off[l][4] = push(ct);
+    }
+    const float *wf = get("fc.0.weight", (size_t)kEvLat * kEvV * kEvC), *bf_ = get("fc.0.bias", kEvLat);
+    if (!wf || !bf_ || !bn("fc.1", kEvLat, sc, sh)) return DC_ERR_INVALID;
+    std::vector<double> fw((size_t)kEvV * kEvC * kEvLat), fb(kEvLat);
+    for (int o = 0; o < kEvLat; ++o) {
+        for (int c = 0; c < kEvC; ++c)
+            for (int v = 0; v < kEvV; ++v) fw[((size_t)v * kEvC + c) * kEvLat + o] = sc[o] * (double)wf[o * (kEvV * kEvC) + c * kEvV + v];   // flatten order: c * 13 + v
+        fb[o] = sc[o] * (double)bf_[o] + sh[o];
+    }
+    const size_t off_fw = push(fw), off_fb = push(fb);
+    EV_CUDA(cudaSetDevice(e->device));
+    EV_CUDA(cudaDeviceSynchronize());
+    if (e->pool) cudaFree(e->pool);
+    e->pool = nullptr;
+    EV_CUDA(cudaMalloc((void**)&e->pool, pool.size() * 4));
+    EV_CUDA(cudaMemcpy(e->pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice));
+    e->dbn = e->pool + off_dbn, e->wfc = e->pool + off_fw, e->bfc = e->pool + off_fb;
+    for (int l = 0; l < kEvLayers; ++l)
+        e->layer[l] = StgcnLayer{e->pool + off[l][0], e->pool + off[l][1], e->pool + off[l][2], e->pool + off[l][3], e->pool + off[l][4]};
+    e->finalized = true;
+    return 0;
+}
+
+int dc_eval_motion_features(dc_eval* e, const float* motion, float* feat, int N, int T, void* stream) {
+    if (!e || !motion || !feat || N < 1 || T < 1) return efail(DC_ERR_INVALID, "dc_eval_motion_features: bad argument");
+    if (!e->finalized) return efail(DC_ERR_STATE, "dc_eval_motion_features: call dc_eval_finalize first");
+    using namespace dc;
+    EV_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rows = (size_t)N * T;
+    if (rows > e->act_rows) {
+        if (e->act[0]) cudaFree(e->act[0]);
+        if (e->act[1]) cudaFree(e->act[1]);
+        e->act[0] = e->act[1] = nullptr, e->act_rows = 0;
+        EV_CUDA(cudaMalloc((void**)&e->act[0], rows * kEvV * kEvC * 4));
+        EV_CUDA(cudaMalloc((void**)&e->act[1], rows * kEvV * kEvC * 4));
+        e->act_rows = rows;
+    }
+    const dim3 grid((unsigned)((T + kEvTT - 1) / kEvTT), (unsigned)N);
+    stgcn_layer_kernel<2><<<grid, 256, stgcn_smem_bytes(2), st>>>(motion, e->act[0], T, e->layer[0], e->dbn, 0);
+    for (int l = 1; l < kEvLayers; ++l)
+        stgcn_layer_kernel<32><<<grid, 256, stgcn_smem_bytes(32), st>>>(e->act[(l - 1) & 1], e->act[l & 1], T, e->layer[l], nullptr, 1);
+    stgcn_fc_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(e->act[(kEvLayers - 1) & 1], e->wfc, e->bfc, feat, (long)rows);
+    EV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dc_eval_feature_stats(int device, const float* feat, int64_t rows, double* sum, double* m2, void* stream) {
+    if (!feat || !sum || !m2 || rows < 1) return efail(DC_ERR_INVALID, "dc_eval_feature_stats: bad argument");
+    EV_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    EV_CUDA(cudaMemsetAsync(sum, 0, dc::kEvLat * 8, st));
+    EV_CUDA(cudaMemsetAsync(m2, 0, dc::kEvLat * dc::kEvLat * 8, st));
+    const unsigned blocks = (unsigned)std::min<int64_t>(296, (rows + 31) / 32);
+    dc::feat_colsum_kernel<<<blocks, 256, 0, st>>>(feat, (long)rows, sum);
+    dc::feat_cov_kernel<<<blocks, 256, 0, st>>>(feat, (long)rows, sum, m2);
+    EV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dc_eval_feature_l1(int device, const float* a, const float* b, int64_t rows, double* out, void* stream) {
+    if (!a || !b || !out || rows < 1) return efail(DC_ERR_INVALID, "dc_eval_feature_l1: bad argument");
+    EV_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    EV_CUDA(cudaMemsetAsync(out, 0, 8, st));
+    const int64_t n = rows * dc::kEvLat;
+    dc::feat_l1_kernel<<<(unsigned)std::min<int64_t>(592, (n + 255) / 256), 256, 0, st>>>(a, b, (long)n, out);
+    EV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dc_eval_motion_beats(int device, const float* motion, float* envelope, uint8_t* beats, int N, int T, int order, void* stream) {
+    if (!motion || !envelope || !beats || N < 1 || T < 1 || order < 1) return efail(DC_ERR_INVALID, "dc_eval_motion_beats: bad argument");
+    EV_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)(((long)N * T + 255) / 256);
+    dc::motion_envelope_kernel<<<blocks, 256, 0, st>>>(motion, envelope, N, T);
+    dc::local_minima_kernel<<<blocks, 256, 0, st>>>(envelope, beats, N, T, order);
+    EV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dc_eval_beat_alignment(int device, const uint8_t* music_beats, int Tm, const uint8_t* motion_beats, int T, int N, float sigma, float* scores,
+                           void* stream) {
+    if (!music_beats || !motion_beats || !scores || N < 1 || T < 1 || Tm < 1 || !(sigma > 0.f))
+        return efail(DC_ERR_INVALID, "dc_eval_beat_alignment: bad argument");
+    EV_CUDA(cudaSetDevice(device));
+    dc::beat_alignment_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(music_beats, Tm, motion_beats, T, sigma, scores);
+    EV_CUDA(cudaGetLastError());
     return 0;
 }
 

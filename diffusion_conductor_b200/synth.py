@@ -124,3 +124,78 @@ def synth_features(B: int, T: int, seed: int = 0):
     xf_out = torch.randn(B, T, 64, generator=_gen(seed, "xf_out"), dtype=torch.float32)
     xf_proj = torch.randn(B, T, 64, generator=_gen(seed, "xf_proj"), dtype=torch.float32)
     return xf_proj, xf_out
+
+
+def stgcn_shapes() -> Dict[str, Tuple[int, ...]]:
+    """state_dict layout of the reference's MotionEncoder_STGCN (tools/eval_new_metrics.py:38-49: ST_GCN(in 2, out 32, mode
+    'M2S', edge importance) + fc = Conv1d(416, 64, 1) + BatchNorm1d(64)), key -> shape."""
+    s: Dict[str, Tuple[int, ...]] = {"st_gcn.A": (1, 13, 13)}
+
+    def bn(p, c):
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            s[p + "." + n] = (c,)
+        s[p + ".num_batches_tracked"] = ()
+
+    bn("st_gcn.data_bn", 26)
+    for i in range(10):
+        cin = 2 if i == 0 else 32
+        p = f"st_gcn.st_gcn_networks.{i}"
+        s[p + ".gcn.conv.weight"] = (32, cin, 1, 1)
+        s[p + ".gcn.conv.bias"] = (32,)
+        bn(p + ".tcn.0", 32)
+        s[p + ".tcn.2.weight"] = (32, 32, 3, 1)
+        s[p + ".tcn.2.bias"] = (32,)
+        bn(p + ".tcn.3", 32)
+    for i in range(10):
+        s[f"st_gcn.edge_importance.{i}"] = (1, 13, 13)
+    s["st_gcn.fcn.weight"] = (32, 256, 1, 1)
+    s["st_gcn.fcn.bias"] = (32,)
+    s["fc.0.weight"] = (64, 416, 1)
+    s["fc.0.bias"] = (64,)
+    bn("fc.1", 64)
+    return s
+
+
+def synth_stgcn_state_dict(seed: int = 0, A=None) -> Dict[str, torch.Tensor]:
+    """Random weights for the ST-GCN motion encoder (same recipe as synth_state_dict); `A` (1, 13, 13) is the graph buffer
+    (defaults to the ConductorMotionX uniform-strategy adjacency), edge importances ~ 1 + 0.2 N(0, 1)."""
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape in stgcn_shapes().items():
+        g = _gen(seed, "stgcn." + key)
+        leaf = key.rsplit(".", 1)[-1]
+        if key == "st_gcn.A":
+            if A is None:
+                from .evaluation import conductor_graph
+                A = conductor_graph()
+            sd[key] = torch.as_tensor(A, dtype=torch.float32).reshape(shape).clone()
+        elif key.startswith("st_gcn.edge_importance"):
+            sd[key] = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif leaf == "num_batches_tracked":
+            sd[key] = torch.tensor(0, dtype=torch.int64)
+        elif leaf == "running_mean":
+            sd[key] = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "running_var":
+            sd[key] = 0.5 + torch.rand(shape, generator=g)
+        elif len(shape) == 1 and leaf == "weight":
+            sd[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[key] = 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            sd[key] = _uniform(shape, fan_in ** -0.5, g)
+    return sd
+
+
+def synth_motion(N: int, T: int, seed: int = 0) -> torch.Tensor:
+    """Smooth keypoint tracks in [0, 1] (N, T, 13, 2): a few sinusoids per coordinate plus a little noise, so that the joint-speed
+    envelope has genuine local minima."""
+    g = _gen(seed, "motion")
+    t = torch.arange(T, dtype=torch.float32)[None, :, None, None]
+    f = 0.02 + 0.08 * torch.rand(N, 1, 13, 2, generator=g)
+    ph = 6.2831853 * torch.rand(N, 1, 13, 2, generator=g)
+    f2 = 0.2 + 0.3 * torch.rand(N, 1, 13, 2, generator=g)
+    base = torch.rand(N, 1, 13, 2, generator=g)
+    x = base + 0.15 * torch.sin(6.2831853 * f * t + ph) + 0.03 * torch.sin(6.2831853 * f2 * t) + 0.002 * torch.randn(N, T, 13, 2, generator=g)
+    return x.clamp(0, 1)

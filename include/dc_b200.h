@@ -158,6 +158,46 @@ int dc_set_graphs(dc_handle* h, int enabled);
 int dc_selftest_gemm(int device, int operand, int M, int N, int K, const float* A, const float* W, const float* bias,
                      float* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation features computed right after the sampling path.  Reference: the Evaluator of
+ * Diffusion_Stage/tools/eval_new_metrics.py (pure Python / numpy there).  Errors: dc_last_error(NULL).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dc_eval dc_eval;
+
+/* MotionEncoder_STGCN (eval_new_metrics.py:38-49: ST_GCN(in 2, out 32, mode 'M2S', edge importance weighting) + fc): create,
+ * upload every float tensor of its state_dict by key (HOST or DEVICE pointer, `count` floats; st_gcn.A, st_gcn.data_bn.*,
+ * st_gcn.st_gcn_networks.{0..9}.{gcn.conv, tcn.0, tcn.2, tcn.3}.*, st_gcn.edge_importance.{0..9}, fc.0.*, fc.1.*; st_gcn.fcn.* is
+ * unused by features()), then finalize (eval-mode BatchNorms are folded on the host in fp64). */
+int dc_eval_create(int device, dc_eval** out);
+void dc_eval_destroy(dc_eval* e);
+int dc_eval_set_weight(dc_eval* e, const char* key, const float* data, int64_t count);
+int dc_eval_finalize(dc_eval* e);
+
+/* MotionEncoder_STGCN.features(motion)[-1] (eval_new_metrics.py:62-74; ST_GCN.py:86-113, 217-228; tgcn.py:61-73): the 64-d latent
+ * of every frame.  motion: DEVICE [N][T][26] keypoints (13 joints x 2), feat: DEVICE [N][T][64]. */
+int dc_eval_motion_features(dc_eval* e, const float* motion, float* feat, int N, int T, void* stream);
+
+/* Sufficient statistics of np.mean / np.cov(rowvar=False) over `rows` latents (get_scores, eval_new_metrics.py:159-168), fp64:
+ * sum[64] and the centred second moments m2[64][64] = sum_r (f_r - mean)(f_r - mean)^T  (cov = m2 / (rows - 1)).  feat: DEVICE
+ * [rows][64]; sum, m2: DEVICE.  The 64 x 64 matrix square root of the Frechet distance is finished on the host. */
+int dc_eval_feature_stats(int device, const float* feat, int64_t rows, double* sum, double* m2, void* stream);
+
+/* sum over rows of sum_c |a - b| in fp64 (np.mean(np.sum(np.absolute(a - b), axis=-1)) * rows): diversity
+ * (eval_new_metrics.py:148-156) and the latent-space MAE (:179-185).  a, b: DEVICE [rows][64]; out: DEVICE double[1]. */
+int dc_eval_feature_l1(int device, const float* a, const float* b, int64_t rows, double* out, void* stream);
+
+/* motion_peak_onehot (eval_new_metrics.py:277-303): envelope[n][t] = sum over joints of |x_t - x_{t-1}|_2, beats[n][t] = 1 at the
+ * strict local minima within +-order frames (scipy argrelextrema(np.less, order, mode='clip'); the reference uses order = 10).
+ * motion: DEVICE [N][T][26]; envelope: DEVICE float [N][T]; beats: DEVICE uint8 [N][T]. */
+int dc_eval_motion_beats(int device, const float* motion, float* envelope, uint8_t* beats, int N, int T, int order, void* stream);
+
+/* alignment_score, the beat-consistency variant (eval_new_metrics.py:243-267): per clip the mean over the music beats of
+ * exp(-d^2 / (2 sigma^2)), d = index distance to the nearest motion beat (0 when the clip has no motion beat).  music_beats:
+ * DEVICE uint8 [N][Tm] (librosa's beat tracker in the reference -- third party, stays on the host); motion_beats: DEVICE uint8
+ * [N][T]; scores: DEVICE float [N]. */
+int dc_eval_beat_alignment(int device, const uint8_t* music_beats, int Tm, const uint8_t* motion_beats, int T, int N, float sigma,
+                           float* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 
     python oracle/make_golden.py            # everything
     python oracle/make_golden.py pinned     # only c3_clip / c2_pair / ddpm1000 (round 2)
+    python oracle/make_golden.py eval       # only eval_features / stgcn_state_dict_layout (round 2)
 
 The reference cannot travel to the GPU box, so the fixtures are committed together with
 this script.  TEST INFRASTRUCTURE ONLY (see oracle/motion_oracle.py header).
@@ -111,9 +112,91 @@ def pinned_configs():
 DDPM_SEED = 2024
 
 
+def eval_features():
+    """tests/golden/eval_features.npz: the UNMODIFIED reference ST_GCN module (models/ST_GCN/ST_GCN.py) wrapped
+    exactly as MotionEncoder_STGCN does (tools/eval_new_metrics.py:38-74 -- that file itself imports mmcv / librosa at module
+    level, which are absent, so the 10-line wrapper class is restated here), and the reference's OWN source of
+    motion_peak_onehot / alignment_score / calculate_frechet_distance, extracted from the file with ast and executed."""
+    import ast
+    import json
+    import textwrap
+
+    import scipy.signal as scisignal
+    from scipy import linalg
+    from torch import nn
+
+    from models.ST_GCN.ST_GCN import ST_GCN  # noqa: E402  (the reference)
+
+    from diffusion_conductor_b200.synth import synth_motion, synth_stgcn_state_dict
+
+    class MotionEncoder_STGCN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.st_gcn = ST_GCN(in_channels=2, out_channels=32, graph_args={}, edge_importance_weighting=True, mode="M2S")
+            self.fc = nn.Sequential(nn.Conv1d(32 * 13, 64, kernel_size=1), nn.BatchNorm1d(64))
+
+        def features(self, input):
+            input = input.transpose(1, 2).transpose(1, 3).unsqueeze(4)
+            output = self.st_gcn(input).transpose(1, 2)
+            output = torch.flatten(output, start_dim=2)
+            output = self.fc(output.transpose(1, 2)).transpose(1, 2)
+            features = self.st_gcn.extract_feature(input)
+            features.append(output.transpose(1, 2))
+            return features
+
+    enc = MotionEncoder_STGCN()
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in enc.state_dict().items()},
+              open(os.path.join(OUT, "stgcn_state_dict_layout.json"), "w"), indent=0)
+    graph_A = enc.st_gcn.A.numpy().copy()
+    sd = synth_stgcn_state_dict(5, A=graph_A)
+    enc.load_state_dict(sd, strict=True)
+    enc.eval()
+    motion = synth_motion(3, 200, seed=9)
+    with torch.no_grad():
+        feats = enc.features(motion)
+    latent = feats[-1].transpose(1, 2).numpy() if feats[-1].shape[1] == 64 else feats[-1].numpy()     # (N, T, 64)
+    layer3 = feats[4].numpy()                                                                              # after st_gcn layer 3: (N, T, 416)
+
+    src = open("/root/reference/Diffusion_Stage/tools/eval_new_metrics.py").read()
+    tree = ast.parse(src)
+    want = {"alignment_score", "normalize", "motion_peak_onehot", "calculate_frechet_distance"}
+    class _Linalg:                     # this scipy dropped sqrtm's `disp` argument (disp=False returned (sqrtm, error estimate))
+        @staticmethod
+        def sqrtm(a, disp=True):
+            r = linalg.sqrtm(a)
+            return r if disp else (r, 0.0)
+
+    ns = {"np": np, "scisignal": scisignal, "linalg": _Linalg}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "Evaluator":
+            body = [n for n in node.body if isinstance(n, ast.FunctionDef) and n.name in want]
+            cls = ast.ClassDef(name="RefEvaluator", bases=[], keywords=[], body=body, decorator_list=[])
+            mod = ast.Module(body=[cls], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, "eval_new_metrics.py (extract)", "exec"), ns)
+    ev = ns["RefEvaluator"]()
+    beats = np.stack([ev.motion_peak_onehot(motion[i].numpy(), "generated") for i in range(motion.shape[0])])
+    rng = np.random.RandomState(3)
+    music = np.zeros((motion.shape[0], 600), dtype=np.float32)
+    for i in range(motion.shape[0]):
+        music[i, np.sort(rng.choice(600, 40, replace=False))] = 1.0
+    scores = np.array([ev.alignment_score(music[i], beats[i], "generated", sigma=3) for i in range(motion.shape[0])], dtype=np.float64)
+    a, b = latent[:2].reshape(-1, 64), latent[1:].reshape(-1, 64)
+    mu_a, cov_a, mu_b, cov_b = np.mean(a, axis=0), np.cov(a, rowvar=False), np.mean(b, axis=0), np.cov(b, rowvar=False)
+    fgd = ev.calculate_frechet_distance(mu_a, cov_a, mu_b, cov_b)
+    l1 = np.mean(np.sum(np.absolute(a - b), axis=-1))
+    np.savez_compressed(os.path.join(OUT, "eval_features.npz"), graph_A=graph_A, latent=latent, layer3=layer3, beats=beats, music_beats=music,
+                        beat_scores=scores, mu_a=mu_a, cov_a=cov_a, fgd=np.array(fgd), l1=np.array(l1))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":        # only the N4 fixtures
+        eval_features()
+        for f in sorted(os.listdir(OUT)):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "pinned":      # only the round-2 fixtures (the round-1 ones stay byte-identical)
         pinned_configs()
         for f in sorted(os.listdir(OUT)):
@@ -169,6 +252,7 @@ def main():
                         final=smp[-1])
     write_state_dict_layout()
     pinned_configs()
+    eval_features()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -662,3 +662,63 @@ def test_generate_music_motion_under_nccl(tmp_path):
     for key in ("odd", "even"):
         assert torch.equal(a[key], b[key]), key                 # every rank holds the full gathered batch
         assert torch.equal(a[key], a[key + "_single"]), key      # == one process generating all clips (clip-aligned tiles)
+
+
+# ------------------------------------------------------------------------------------------------
+# on-device evaluation features (diffusion_conductor_b200/evaluation.py, dc_eval_*)
+# ------------------------------------------------------------------------------------------------
+def test_evaluation_features_on_device(golden_dir):
+    """ST-GCN motion encoder latents, Frechet statistics, latent L1, motion beats and beat consistency against the reference
+    golden (tests/golden/eval_features.npz) and the CPU oracle at a second shape (ragged tile, single frame)."""
+    from diffusion_conductor_b200 import evaluation as EV
+    from diffusion_conductor_b200.synth import synth_motion, synth_stgcn_state_dict
+    from oracle import eval_oracle as E
+
+    g = np.load(os.path.join(golden_dir, "eval_features.npz"))
+    enc = EV.MotionEncoder_STGCN()
+    sd = synth_stgcn_state_dict(5)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval()
+    motion = synth_motion(3, 200, seed=9)
+    lat = enc(motion.cuda())
+    scale = max(1.0, float(np.abs(g["latent"]).max()))
+    err = float(np.abs(lat.cpu().numpy() - g["latent"]).max())
+    REPORT.append({"what": "ST-GCN latents vs reference golden", "operand": "fp32", "rel_rms": None, "max_abs": err, "ref_rms": scale})
+    assert err < 5e-5 * scale
+    assert torch.equal(enc.features(motion.cuda())[-1], lat)
+    with pytest.raises(RuntimeError):
+        enc(motion)                                                 # CPU tensor: no fallback
+    # a second shape vs the oracle: 5 clips x 37 frames (3 time tiles, ragged last tile), and a single frame
+    for (N, T) in [(5, 37), (1, 1), (2, 16)]:
+        mo = synth_motion(N, T, seed=N * 100 + T)
+        ref = E.motion_features(sd, mo).numpy()
+        assert np.abs(enc(mo.cuda()).cpu().numpy() - ref).max() < 5e-5 * max(1.0, float(np.abs(ref).max())), (N, T)
+    # new weights are picked up (the engine reloads when the state_dict changes)
+    sd2 = synth_stgcn_state_dict(6)
+    enc.load_state_dict(sd2, strict=True)
+    ref2 = E.motion_features(sd2, motion).numpy()
+    assert np.abs(enc(motion.cuda()).cpu().numpy() - ref2).max() < 5e-5 * max(1.0, float(np.abs(ref2).max()))
+    # ---- statistics, FGD, L1 on the golden latents
+    a = torch.from_numpy(g["latent"][:2]).cuda()
+    b = torch.from_numpy(g["latent"][1:]).cuda()
+    mu, cov = EV.feature_statistics(a)
+    assert np.abs(mu - g["mu_a"]).max() < 1e-6 and np.abs(cov - g["cov_a"]).max() < 1e-6 * max(1.0, float(np.abs(g["cov_a"]).max()))
+    fgd = EV.frechet_gesture_distance(a, b)
+    assert abs(fgd - float(g["fgd"])) < 1e-5 * max(1.0, abs(float(g["fgd"])))
+    assert abs(EV.latent_l1(a, b) - float(g["l1"])) < 1e-5 * float(g["l1"])
+    div = EV.diversity_score([a[0], a[1], b[1]], perm=torch.tensor([2, 0, 1]))
+    ref_div = E.feature_l1(np.concatenate([g["latent"][0], g["latent"][1], g["latent"][2]]), np.concatenate([g["latent"][2], g["latent"][0], g["latent"][1]]))
+    assert abs(div - ref_div) < 1e-5 * ref_div
+    # ---- beats
+    env, beats = EV.motion_beats(motion.cuda())
+    assert np.array_equal(beats.cpu().numpy(), g["beats"])
+    ref_env = np.stack([E.motion_peak_onehot(motion[i].numpy())[0] for i in range(3)])
+    assert np.abs(env.cpu().numpy() - ref_env).max() < 1e-5
+    scores = EV.beat_consistency(torch.from_numpy(g["music_beats"]).cuda(), beats)
+    assert np.abs(scores.cpu().numpy() - g["beat_scores"]).max() < 1e-5
+    none = EV.beat_consistency(torch.from_numpy(g["music_beats"]).cuda(), torch.zeros_like(beats))
+    assert float(none.abs().max()) == 0.0
+    # order as an argument; a short clip (T < order) has no interior minimum test beyond the clipped neighbours
+    env2, beats2 = EV.motion_beats(motion[:, :7].cuda(), order=3)
+    for i in range(3):
+        assert np.array_equal(beats2[i].cpu().numpy(), E.motion_peak_onehot(motion[i, :7].numpy(), order=3)[1])

@@ -167,3 +167,41 @@ def test_ddpm_1000_steps_vs_reference(golden_dir):
     _, x0s, smp = O.sample_loop(sd, O.Tables(O.linear_betas(1000)), noise, [180], xf_proj, xf_out, kind="ddpm", step_noise=nz)
     got = torch.stack([smp[999 - int(t)] for t in g["steps"]]).numpy()
     np.testing.assert_allclose(got, g["ddpm_sample"], rtol=0, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation features (oracle/eval_oracle.py) against what the unmodified reference ST_GCN module and the
+# reference's own metric source produced (oracle/make_golden.py eval -> tests/golden/eval_features.npz)
+# ------------------------------------------------------------------------------------------------
+def test_eval_oracle_vs_reference_golden(golden_dir):
+    import json
+
+    from diffusion_conductor_b200.evaluation import MotionEncoder_STGCN, conductor_graph
+    from diffusion_conductor_b200.synth import stgcn_shapes, synth_motion, synth_stgcn_state_dict
+    from oracle import eval_oracle as E
+
+    g = np.load(os.path.join(golden_dir, "eval_features.npz"))
+    # the graph of the reference's Graph('ConductorMotionX', 'uniform') (restated twice: oracle and product constructor)
+    assert np.array_equal(E.conductor_graph().astype(np.float32), g["graph_A"])
+    assert np.array_equal(conductor_graph().astype(np.float32), g["graph_A"])
+    # checkpoint contract: same keys, shapes, dtypes as the reference's MotionEncoder_STGCN
+    layout = json.load(open(os.path.join(golden_dir, "stgcn_state_dict_layout.json")))
+    ours = MotionEncoder_STGCN().state_dict()
+    assert list(ours.keys()) == list(layout.keys())
+    for k, (shape, dtype) in layout.items():
+        assert list(ours[k].shape) == shape and str(ours[k].dtype) == dtype, k
+    assert {k: list(v) for k, v in stgcn_shapes().items()} == {k: v[0] for k, v in layout.items()}
+    sd = synth_stgcn_state_dict(5)
+    motion = synth_motion(3, 200, seed=9)
+    lat = E.motion_features(sd, motion).numpy()
+    assert np.abs(lat - g["latent"]).max() < 2e-5 * max(1.0, np.abs(g["latent"]).max())
+    for i in range(3):
+        env, beats = E.motion_peak_onehot(motion[i].numpy())
+        assert np.array_equal(beats, g["beats"][i]) and beats.sum() > 0
+        assert abs(E.alignment_score(g["music_beats"][i], beats) - g["beat_scores"][i]) < 1e-6
+    assert E.alignment_score(g["music_beats"][0], np.zeros(200, dtype=bool)) == 0.0
+    a, b = g["latent"][:2].reshape(-1, 64), g["latent"][1:].reshape(-1, 64)
+    mu, cov = E.feature_stats(a)
+    assert np.array_equal(mu, g["mu_a"]) and np.array_equal(cov, g["cov_a"])
+    assert abs(E.frechet_distance(mu, cov, *E.feature_stats(b)) - float(g["fgd"])) < 1e-9
+    assert abs(E.feature_l1(a, b) - float(g["l1"])) < 1e-6
