@@ -16,7 +16,7 @@
 
 #include "../../include/dc_b200.h"
 #include "clip_kernel.cuh"
-#include "music_encoder.cuh"
+#include "music_encoder_tc.cuh"
 #include "eval_kernels.cuh"
 
 using namespace dc;
@@ -83,11 +83,11 @@ struct dc_handle {
 
     // music encoder (BatchNorm folded): per 3x3 layer w [CIN][9][COUT], b [COUT]; conv2.0's 1x1 residual; conv4 + proj
     bool has_music = false;
-    // 3x3 layers: HOST copies of the per-(layer, 16-channel group) weight structs, passed by value at launch
-    ConvWeights<1, false> me_c10;
-    ConvWeights<16, false> me_c11, me_c12;
-    ConvWeights<16, true> me_c20[2];
-    ConvWeights<32, false> me_c21[2], me_c30[2], me_c31[2];
+    Conv10Weights me_c10;          // conv1.0 (1 -> 16 channels): HOST copy, passed by value at launch (CUDA cores)
+    uint8_t* me_wimg = nullptr;    // the six tensor-core layers: (hi, lo)-split B-operand blocks, see music_encoder_tc.cuh
+    float* me_bias = nullptr;      // [6][64]: folded bias [COUT] (+ [COUT] of conv2.0's 1x1 residual)
+    size_t me_woff[6] = {0, 0, 0, 0, 0, 0};
+    int me_occ[4] = {1, 1, 1, 1};  // resident CTAs per SM of the four conv_tc_kernel instances (conv1.x, conv2.0, conv2.1, conv3.x)
     float *me_w4t = nullptr, *me_b4 = nullptr, *me_wpt = nullptr, *me_bp = nullptr;
     float *me_buf0 = nullptr, *me_buf1 = nullptr;     // ping-pong activation planes for one chunk of clips
     size_t me_cap = 0;                                // floats per buffer
@@ -315,6 +315,22 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
+    {   // music-encoder convolutions: opt in to their shared memory; resident CTAs per SM = min over shared memory (227 KB, 1 KB
+        // reserved per CTA), registers and 4 x 128 TMEM columns -- the persistent grids are sized to exactly that
+        const void* fn[4] = {(const void*)conv_tc_kernel<16, 16, 1, 128, kMeR128>, (const void*)conv_tc_kernel<16, 32, 2, 64, kMeR64>,
+                             (const void*)conv_tc_kernel<32, 32, 1, 64, kMeR64>, (const void*)conv_tc_kernel<32, 32, 1, 32, kMeR32>};
+        const int sm[4] = {me_smem_bytes<16, 16, 1, 128, kMeR128>(), me_smem_bytes<16, 32, 2, 64, kMeR64>(), me_smem_bytes<32, 32, 1, 64, kMeR64>(),
+                           me_smem_bytes<32, 32, 1, 32, kMeR32>()};
+        for (int i = 0; i < 4; ++i) {
+            DC_CUDA(h, cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, sm[i]));
+            cudaFuncAttributes fa{};
+            DC_CUDA(h, cudaFuncGetAttributes(&fa, fn[i]));
+            const int by_smem = (227 * 1024) / (sm[i] + (int)fa.sharedSizeBytes + 1024);
+            const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * ((kMeThreads + 31) & ~31));
+            h->me_occ[i] = std::max(1, std::min(std::min(by_smem, by_regs), 4));
+            if (getenv("DC_VERBOSE")) fprintf(stderr, "[dc_b200] conv_tc variant %d: %d regs, %d B smem -> %d CTAs/SM\n", i, fa.numRegs, sm[i], h->me_occ[i]);
+        }
+    }
     void (*clip_variants[8])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>,
                                           clip_kernel<true, false, true>, clip_kernel<false, false, true>, clip_kernel<true, true, true>,
                                           clip_kernel<false, true, true>};
@@ -588,7 +604,7 @@ void dc_destroy(dc_handle* h) {
                     h->teW0, h->teb0, h->teW2, h->teb2, h->freqs, h->coef, h->te_table, h->step_ctr, h->timeline};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    void* mptrs[] = {h->me_w4t, h->me_b4, h->me_wpt, h->me_bp, h->me_buf0, h->me_buf1};
+    void* mptrs[] = {h->me_w4t, h->me_b4, h->me_wpt, h->me_bp, h->me_buf0, h->me_buf1, h->me_wimg, h->me_bias};
     for (void* p : mptrs)
         if (p) cudaFree(p);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -866,40 +882,76 @@ int dc_finalize_weights(dc_handle* h) {
             }
             return 0;
         };
-        auto fill = [&](int li, int grp, float* wdst, float* bdst, float* w1dst, float* b1dst) -> int {
+        // BatchNorm-folded weights of layer li as fp32 [co][ci][9] (+ 1x1 residual [co][ci]) and biases
+        auto folded = [&](int li, std::vector<float>& wf, std::vector<float>& bf_, std::vector<float>* w1f, std::vector<float>* b1f) -> int {
             const std::string p = std::string("music_encoder.") + specs[li].name;
             const int ci = specs[li].cin, co = specs[li].cout;
             GET(w, p + ".conv2d_layer.0.weight", co, ci, 3, 3);
             GET(b, p + ".conv2d_layer.0.bias", co);
             std::vector<float> sc, sh;
             if (bn_scale(p + ".conv2d_layer.1", co, sc, sh)) return DC_ERR_INVALID;
-            for (int q = 0; q < kCvCo; ++q) {
-                const int o = grp * kCvCo + q;
-                bdst[q] = b->v[o] * sc[o] + sh[o];
-                for (int i = 0; i < ci; ++i)
-                    for (int t = 0; t < 9; ++t) wdst[((size_t)i * 9 + t) * kCvCo + q] = w->v[((size_t)o * ci + i) * 9 + t] * sc[o];
+            wf.resize((size_t)co * ci * 9), bf_.resize(co);
+            for (int o = 0; o < co; ++o) {
+                bf_[o] = b->v[o] * sc[o] + sh[o];
+                for (int i = 0; i < ci * 9; ++i) wf[(size_t)o * ci * 9 + i] = w->v[(size_t)o * ci * 9 + i] * sc[o];
             }
-            if (w1dst) {                   // 1x1 residual convolution + BatchNorm (conv2.0)
+            if (w1f) {                     // 1x1 residual convolution + BatchNorm (conv2.0)
                 GET(rw, p + ".residual.0.weight", co, ci, 1, 1);
                 GET(rb, p + ".residual.0.bias", co);
                 std::vector<float> rs, rh;
                 if (bn_scale(p + ".residual.1", co, rs, rh)) return DC_ERR_INVALID;
-                for (int q = 0; q < kCvCo; ++q) {
-                    const int o = grp * kCvCo + q;
-                    b1dst[q] = rb->v[o] * rs[o] + rh[o];
-                    for (int i = 0; i < ci; ++i) w1dst[(size_t)i * kCvCo + q] = rw->v[(size_t)o * ci + i] * rs[o];
+                w1f->resize((size_t)co * ci), b1f->resize(co);
+                for (int o = 0; o < co; ++o) {
+                    (*b1f)[o] = rb->v[o] * rs[o] + rh[o];
+                    for (int i = 0; i < ci; ++i) (*w1f)[(size_t)o * ci + i] = rw->v[(size_t)o * ci + i] * rs[o];
                 }
             }
             return 0;
         };
-        if (fill(0, 0, h->me_c10.w, h->me_c10.b, nullptr, nullptr) || fill(1, 0, h->me_c11.w, h->me_c11.b, nullptr, nullptr) ||
-            fill(2, 0, h->me_c12.w, h->me_c12.b, nullptr, nullptr))
-            return DC_ERR_INVALID;
-        for (int g2 = 0; g2 < 2; ++g2)
-            if (fill(3, g2, h->me_c20[g2].w, h->me_c20[g2].b, h->me_c20[g2].w1, h->me_c20[g2].b1) ||
-                fill(4, g2, h->me_c21[g2].w, h->me_c21[g2].b, nullptr, nullptr) || fill(5, g2, h->me_c30[g2].w, h->me_c30[g2].b, nullptr, nullptr) ||
-                fill(6, g2, h->me_c31[g2].w, h->me_c31[g2].b, nullptr, nullptr))
-                return DC_ERR_INVALID;
+        {
+            std::vector<float> wf, bf_;
+            if (folded(0, wf, bf_, nullptr, nullptr)) return DC_ERR_INVALID;
+            for (int t = 0; t < 9; ++t)
+                for (int q = 0; q < 16; ++q) h->me_c10.w[t * 16 + q] = wf[(size_t)q * 9 + t];
+            for (int q = 0; q < 16; ++q) h->me_c10.b[q] = bf_[q];
+        }
+        // tensor-core layers: per tap one [COUT x 64] B block of (hi, lo)-split weights, row = [w_hi | w_lo] (A rows: [a_hi | a_lo])
+        auto hi_of = [](float v) {
+            const uint16_t u = to16(v, true);
+            uint32_t w32 = (uint32_t)u << 16;
+            float f;
+            memcpy(&f, &w32, 4);
+            return f;
+        };
+        std::vector<uint8_t> wimg;
+        std::vector<float> biases(6 * 64, 0.f);
+        for (int li = 1; li < 7; ++li) {
+            const int ci = specs[li].cin, co = specs[li].cout;
+            const bool res = li == 3;
+            std::vector<float> wf, bf_, w1f, b1f;
+            if (folded(li, wf, bf_, res ? &w1f : nullptr, res ? &b1f : nullptr)) return DC_ERR_INVALID;
+            h->me_woff[li - 1] = wimg.size();
+            auto add_block = [&](const std::vector<float>& m) {          // m: [co][64]
+                const size_t off = wimg.size();
+                wimg.resize(off + (size_t)co * 128);
+                pack_image(wimg.data() + off, m.data(), 64, 64, nullptr, nullptr, co, 1, true);
+            };
+            auto tap_blocks = [&](auto&& weight_at /* (o, i) -> folded weight */) {          // one block per tap: row = [w_hi (ci) | w_lo (ci)]
+                std::vector<float> m1((size_t)co * 64, 0.f);
+                for (int o = 0; o < co; ++o)
+                    for (int i = 0; i < ci; ++i) {
+                        const float wv = weight_at(o, i), whi = hi_of(wv);
+                        m1[o * 64 + i] = whi, m1[o * 64 + ci + i] = wv - whi;
+                    }
+                add_block(m1);
+            };
+            for (int t = 0; t < 9; ++t) tap_blocks([&](int o, int i) { return wf[((size_t)o * ci + i) * 9 + t]; });
+            if (res) tap_blocks([&](int o, int i) { return w1f[(size_t)o * ci + i]; });
+            for (int o = 0; o < co; ++o) biases[(li - 1) * 64 + o] = bf_[o];
+            if (res)
+                for (int o = 0; o < co; ++o) biases[(li - 1) * 64 + co + o] = b1f[o];
+        }
+        if (upload(h, &h->me_wimg, wimg.data(), wimg.size()) || upload(h, &h->me_bias, biases.data(), biases.size() * 4)) return DC_ERR_CUDA;
         GET(w4, "music_encoder.conv4.0.weight", kMusic, 512, 1);
         GET(b4, "music_encoder.conv4.0.bias", kMusic);
         std::vector<float> sc4, sh4;
@@ -1256,34 +1308,38 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         DC_CUDA(h, cudaMalloc((void**)&h->me_buf1, (size_t)chunk * per_clip * 4));
         h->me_cap = (size_t)chunk * per_clip;
     }
-    float *p0 = h->me_buf0, *p1 = h->me_buf1;
-    auto conv_grid = [](int H, int W, int nb) { return dim3((unsigned)((W + kCvTW - 1) / kCvTW), (unsigned)((H + kCvTH - 1) / kCvTH), (unsigned)nb); };
-    auto pool_grid = [](int Ho, int Wo, int planes) { return dim3((unsigned)((Wo + kMpTW - 1) / kMpTW), (unsigned)((Ho + kMpTH - 1) / kMpTH), (unsigned)planes); };
+    uint16_t *p0 = reinterpret_cast<uint16_t*>(h->me_buf0), *p1 = reinterpret_cast<uint16_t*>(h->me_buf1);   // split pixels [C hi | C lo]
+    auto conv = [&](auto kern, int smem, int occ, int R, const uint16_t* src, uint16_t* dst, int H, int nb, int li) {
+        const int bands = (H + R - 1) / R, jobs = bands * nb;
+        kern<<<(unsigned)std::min(jobs, h->num_sms * occ), kMeThreads, smem, st>>>(src, dst, H, bands, jobs, h->me_wimg + h->me_woff[li - 1],
+                                                                                   h->me_bias + (li - 1) * 64);
+    };
+    auto blocks256 = [](long n) { return (unsigned)((n + 255) / 256); };
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
         int H = Tm, W = kBins, Ho, Wo;
-        conv3x3_bn_relu_kernel<1, 16, 0><<<conv_grid(H, W, nb), 256, 0, st>>>(m0, p0, H, W, 0, h->me_c10);
-        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, 0, h->me_c11);
-        conv3x3_bn_relu_kernel<16, 16, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, 0, h->me_c12);
+        conv10_split_kernel<<<dim3(blocks256((long)H * W), (unsigned)nb), 256, 0, st>>>(m0, p0, H, W, h->me_c10);
+        conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p0, p1, H, nb, 1);
+        conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
-        maxpool2d_kernel<5, 5, 1, 2, 2, 2><<<pool_grid(Ho, Wo, nb * 16), 256, 0, st>>>(p0, p1, H, W, Ho, Wo);
+        maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 2), 256, 0, st>>>(p0, p1, H, W, Ho, Wo, (long)nb * Ho * Wo * 2);
         H = Ho, W = Wo;
-        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<16, 32, 2><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c20[g2]);
-        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c21[g2]);
+        conv(conv_tc_kernel<16, 32, 2, 64, kMeR64>, me_smem_bytes<16, 32, 2, 64, kMeR64>(), h->me_occ[1], kMeR64, p1, p0, H, nb, 3);
+        conv(conv_tc_kernel<32, 32, 1, 64, kMeR64>, me_smem_bytes<32, 32, 1, 64, kMeR64>(), h->me_occ[2], kMeR64, p0, p1, H, nb, 4);
         Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
-        maxpool2d_kernel<5, 5, 3, 2, 2, 2><<<pool_grid(Ho, Wo, nb * 32), 256, 0, st>>>(p1, p0, H, W, Ho, Wo);
+        maxpool_split_kernel<32, 5, 5, 3, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p1, p0, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
         H = Ho, W = Wo;
-        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p0, p1, H, W, g2, h->me_c30[g2]);
-        for (int g2 = 0; g2 < 2; ++g2) conv3x3_bn_relu_kernel<32, 32, 1><<<conv_grid(H, W, nb), 256, 0, st>>>(p1, p0, H, W, g2, h->me_c31[g2]);
+        conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p0, p1, H, nb, 5);
+        conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p1, p0, H, nb, 6);
         Ho = (H + 2 - 3) / 1 + 1, Wo = (W + 2 - 3) / 2 + 1;           // MaxPool2d((3,3), stride (1,2), padding 1)
-        maxpool2d_kernel<3, 3, 1, 2, 1, 1><<<pool_grid(Ho, Wo, nb * 32), 256, 0, st>>>(p0, p1, H, W, Ho, Wo);
-        H = Ho, W = Wo;                                               // (nb, 32, T, 16)
+        maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p0, p1, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
+        H = Ho, W = Wo;                                               // (nb, T, 16, 32 split)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;
-        conv4_proj_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
-                                                                                   xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, nb, T);
-        h->launches += 15;
+        conv4_proj_split_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
+                                                                                         xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, M);
+        h->launches += 11;
     }
     DC_CUDA(h, cudaGetLastError());
     return 0;

@@ -1,0 +1,332 @@
+// M2SNet music encoder on the tensor cores: the six 16/32-channel 3x3 convolutions of
+// MusicEncoder.forward (reference Diffusion_Stage/models/transformer.py:289-340) as implicit GEMMs on tcgen05, fp32-equivalent.
+//
+// Activations live in HBM as NHWC "split" pixels: [C x hi | C x lo] bf16 with value = hi + lo (16 mantissa bits).  For every tap of
+// the 3x3 window the 128 pixels of an M tile are gathered (reflect padding by index arithmetic, reads served by L1) straight into a
+// K-major SWIZZLE_128B A block; the BatchNorm-folded weights sit in shared memory as B blocks [w_hi | w_hi] and [w_lo], so
+//      a . w  ~=  a_hi w_hi + a_lo w_hi + a_hi w_lo        (the dropped a_lo w_lo term is 2^-18 relative)
+// accumulates in fp32 in TMEM over 9 taps x (4 + 2) MMAs of M = 128, N = C_out, K = 16.  The epilogue (bias, ReLU, identity or
+// 1x1-convolution residual, re-split) runs on the 128 row threads while the MMA warp already works on the next tile (two
+// accumulators).  Byte-bound on the gather (1.1 KB of L1 reads + 1.1 KB of shared-memory writes per pixel), not on the tensor pipe.
+#pragma once
+#include "tc_common.cuh"
+
+namespace dc {
+
+__device__ __forceinline__ int me_reflect(int i, int n) {      // padding_mode='reflect', pad 1
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+// 8 fp32 -> hi chunk, lo chunk (8 bf16 each)
+__device__ __forceinline__ void me_split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack2<true>(v[2 * i], v[2 * i + 1]);
+        const float2 b = unpack2<true>(h[i]);
+        l[i] = pack2<true>(v[2 * i] - b.x, v[2 * i + 1] - b.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]), lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void me_join8(const uint4& hi, const uint4& lo, float* v) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack2<true>(h[i]), b = unpack2<true>(l[i]);
+        v[2 * i] = a.x + b.x, v[2 * i + 1] = a.y + b.y;
+    }
+}
+
+// ---------------------------------------------------------------- conv1.0: 1 -> 16 channels from the fp32 mel (CUDA cores)
+struct alignas(16) Conv10Weights {
+    float w[9 * 16];      // [tap][co], BatchNorm folded
+    float b[16];
+};
+// mel [B][H][W] fp32 -> y [B][H][W][16 hi | 16 lo]; no residual (reference MusicEncoder.conv1[0], residual=False)
+__global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restrict__ mel, uint16_t* __restrict__ y, int H, int W,
+                                                          const __grid_constant__ Conv10Weights cw) {
+    const long q = (long)blockIdx.x * 256 + threadIdx.x;
+    if (q >= (long)H * W) return;
+    const int yy = (int)(q / W), xx = (int)(q % W);
+    const float* mb = mel + (size_t)blockIdx.y * H * W;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = cw.b[c];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float v = __ldg(mb + (size_t)me_reflect(yy + dy - 1, H) * W + me_reflect(xx + dx - 1, W));
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, cw.w[(dy * 3 + dx) * 16 + c], acc[c]);
+        }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    uint4 hi0, lo0, hi1, lo1;
+    me_split8(acc, hi0, lo0);
+    me_split8(acc + 8, hi1, lo1);
+    uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)blockIdx.y * H * W + q) * 32);
+    dst[0] = hi0, dst[1] = hi1, dst[2] = lo0, dst[3] = lo1;
+}
+
+// ---------------------------------------------------------------- 3x3 convolutions, 16 / 32 channels, tcgen05
+// A CTA takes a BAND of R image rows: the (R + 2) x (W + 2) input pixels (reflect halo resolved while loading) are staged ONCE in
+// shared memory, one 128-byte row per pixel ([hi | lo], 16-byte chunk c of staged row s stored at c ^ (s & 7)).  The tcgen05
+// SWIZZLE_128B pattern is a function of the shared-memory ADDRESS bits (checked on the GPU with tools/experiments/desc_shift.cu:
+// a K-major descriptor whose start is 128- but not 1024-byte aligned reads exactly the rows it points at, with base_offset 0), so
+// the A operand of tap (dy, dx) is simply the SAME strip read through a descriptor shifted by dy (W + 2) + dx rows: no im2col
+// copy exists anywhere.  Output pixel (yl, x) is accumulator row o = yl (W + 2) + x of the band; the two columns x >= W of every
+// image row are junk rows that the epilogue skips (1.5 - 6 % of the MMA work).
+// image rows per band for the 128-, 64- and 32-bin feature maps: sized so that two CTAs fit an SM (one stages while the other's MMAs run)
+constexpr int kMeR128 = 2, kMeR64 = 3, kMeR32 = 15;
+constexpr int kMeThreads = 288;           // 8 row warps (staging; two threads per accumulator row in the epilogue) + 1 MMA warp
+struct MeBarriers {
+    uint64_t staged;                      // rows -> MMA: the strip of this band is in shared memory (8 warp arrivals)
+    uint64_t acc_full[2], acc_free[2];    // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (8 warp arrivals)
+    uint32_t tmem_base;
+};
+template <int W, int R>
+__host__ __device__ constexpr int me_mtiles() { return (R * (W + 2) + kTileRows - 1) / kTileRows; }
+template <int W, int R>
+__host__ __device__ constexpr int me_strip_rows() { return ((me_mtiles<W, R>() * kTileRows + 2 * (W + 2) + 3 + 7) / 8) * 8; }
+template <int CIN, int COUT, int RES, int W, int R>
+constexpr int me_smem_bytes() {
+    return me_strip_rows<W, R>() * 128 + (9 + (RES == 2 ? 1 : 0)) * COUT * 128 + 2 * COUT * 4 + (int)sizeof(MeBarriers) + 1024;
+}
+
+// x [B][H][W][CIN hi | CIN lo], y [B][H][W][COUT hi | COUT lo].  wimg: one block per tap (+ one for the 1x1 residual convolution),
+// COUT rows x 128 B, K-major SW128, row = [w_hi (CIN) | w_lo (CIN)];  a . w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo is three (CIN = 16)
+// or six (CIN = 32) K = 16 MMAs per tap, each picking its own 32-byte K chunk of the A and of the B rows.
+// bias [COUT] (+ [COUT] of the 1x1 residual when RES == 2).  RES: 1 = identity residual, 2 = 1x1 convolution + BatchNorm.
+template <int CIN, int COUT, int RES, int W, int R>
+__global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int bands_per_clip,
+                                                            int n_jobs, const uint8_t* __restrict__ wimg, const float* __restrict__ bias) {
+    static_assert((CIN == 16 || CIN == 32) && (COUT == 16 || COUT == 32) && (RES == 1 || RES == 2), "unsupported shape");
+    static_assert(RES == 2 || CIN == COUT, "identity residual needs CIN == COUT");
+    constexpr int P = W + 2, NM = me_mtiles<W, R>(), SROWS = me_strip_rows<W, R>();
+    constexpr int NBLK = 9 + (RES == 2 ? 1 : 0), BLK = COUT * 128;
+    constexpr int NCH = CIN / 4;                               // 16-byte chunks of a split pixel: NCH / 2 hi, NCH / 2 lo
+    constexpr int KH = CIN / 16;                               // K = 16 chunks of the hi (and of the lo) half
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* strip = smem;                                     // SROWS x 128 B
+    uint8_t* wsm = strip + SROWS * 128;                        // NBLK x [COUT x 128 B]   (SROWS % 8 == 0: 1024-aligned)
+    float* bsm = reinterpret_cast<float*>(wsm + NBLK * BLK);   // [2 * COUT]
+    MeBarriers* bars = reinterpret_cast<MeBarriers*>(bsm + 2 * COUT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < NBLK * BLK / 16; i += kMeThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    for (int i = tid; i < SROWS * 8; i += kMeThreads) reinterpret_cast<uint4*>(strip)[i] = make_uint4(0, 0, 0, 0);   // junk rows must stay finite
+    if (tid < (RES == 2 ? 2 : 1) * COUT) bsm[tid] = __ldg(bias + tid);
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars->staged), 8);
+        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1), mbar_init(smem_u32(&bars->acc_free[i]), 8);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(smem_u32(&bars->tmem_base), 128);
+        tmem_relinquish();
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int my_jobs = n_jobs > (int)blockIdx.x ? (n_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc<true>(kTileRows, COUT);
+            const uint32_t sbase = smem_u32(strip);
+            uint32_t mc = 0;                                    // accumulator tiles issued so far
+            for (int j = 0; j < my_jobs; ++j) {
+                mbar_wait(smem_u32(&bars->staged), (uint32_t)j & 1u);
+                tc_fence_after();
+                for (int m = 0; m < NM; ++m, ++mc) {
+                    const uint32_t acc = mc & 1u, dcol = tmem_base + acc * 64u;
+                    mbar_wait(smem_u32(&bars->acc_free[acc]), ((mc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int tap = 0; tap < NBLK; ++tap) {
+                        const int dy = tap < 9 ? tap / 3 - 1 : 0, dx = tap < 9 ? tap % 3 - 1 : 0;
+                        // staged row of the tap's pixel for accumulator row 0 of this tile: o + 2 + (1 + dy) P + dx
+                        const uint64_t ad = make_desc_kmajor_sw128(sbase + (uint32_t)(m * kTileRows + 2 + (1 + dy) * P + dx) * 128u);
+                        const uint64_t bd = make_desc_kmajor_sw128(smem_u32(wsm + tap * BLK));
+                        const uint32_t d = (RES == 2 && tap == 9) ? dcol + 32u : dcol;
+                        const bool first = tap == 0 || tap == 9;
+#pragma unroll
+                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);          // a_hi . w_hi
+#pragma unroll
+                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * (KH + k), bd + 2 * k, idesc, 1u);                               // a_lo . w_hi
+#pragma unroll
+                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * k, bd + 2 * (KH + k), idesc, 1u);                               // a_hi . w_lo
+                    }
+                    umma_commit(smem_u32(&bars->acc_full[acc]));
+                }
+            }
+        }
+    } else {
+        // epilogue: warp w and w + 4 share the TMEM lanes 32 (w % 4) ..; `half` selects which half of the output channels
+        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        constexpr int HC = COUT / 2;
+        uint32_t mc = 0;
+        for (int j = 0; j < my_jobs; ++j) {
+            const int job = (int)blockIdx.x + j * (int)gridDim.x;
+            const int clip = job / bands_per_clip, y0 = (job - clip * bands_per_clip) * R;
+            const uint16_t* xc = x + (size_t)clip * H * W * (2 * CIN);
+            // ---- stage the (R + 2) x P pixels of the band: coalesced 16-byte chunks, reflect halo by index arithmetic
+            for (int i = tid; i < (R + 2) * P * NCH; i += 256) {
+                const int sp = i / NCH, ch = i - sp * NCH, ys = sp / P, xs = sp - ys * P;
+                const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);
+                const int c = ch < NCH / 2 ? ch : ch - NCH / 2 + 2 * KH;       // hi chunks at 0 .., lo chunks right behind the hi K chunks
+                *reinterpret_cast<uint4*>(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)c)) = v;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->staged));
+            for (int m = 0; m < NM; ++m, ++mc) {
+                const uint32_t acc = mc & 1u;
+                const int o = m * kTileRows + r, yl = o / P, xx = o - yl * P;
+                const bool valid = xx < W && yl < R && y0 + yl < H;
+                mbar_wait(smem_u32(&bars->acc_full[acc]), (mc >> 1) & 1u);
+                tc_fence_after();
+                float v[HC], v2[RES == 2 ? HC : 1];
+                if (HC == 16) tmem_ld16(trow + acc * 64u + half * HC, v);
+                else tmem_ld8(trow + acc * 64u + half * HC, v);
+                if (RES == 2) {
+                    if (HC == 16) tmem_ld16(trow + acc * 64u + 32u + half * HC, v2);
+                    else tmem_ld8(trow + acc * 64u + 32u + half * HC, v2);
+                }
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free[acc]));
+                if (valid) {
+#pragma unroll
+                    for (int cidx = 0; cidx < HC; ++cidx) v[cidx] = fmaxf(v[cidx] + bsm[half * HC + cidx], 0.f);
+                    if (RES == 1) {                              // + x (identity): the centre pixel is staged row o + 2 + P
+                        const uint32_t srow = (uint32_t)(o + 2 + P);
+#pragma unroll
+                        for (int g8 = 0; g8 < HC / 8; ++g8) {
+                            const uint4 xh = *reinterpret_cast<const uint4*>(strip + sw128_offset(srow, (uint32_t)(half * (HC / 8) + g8)));
+                            const uint4 xl = *reinterpret_cast<const uint4*>(strip + sw128_offset(srow, (uint32_t)(2 * KH + half * (HC / 8) + g8)));
+                            float xr[8];
+                            me_join8(xh, xl, xr);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * g8 + e] += xr[e];
+                        }
+                    } else {
+#pragma unroll
+                        for (int cidx = 0; cidx < HC; ++cidx) v[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + y0 + yl) * W + xx) * (2 * COUT));
+#pragma unroll
+                    for (int g8 = 0; g8 < HC / 8; ++g8) {
+                        uint4 hi, lo;
+                        me_split8(v + 8 * g8, hi, lo);
+                        dst[half * (HC / 8) + g8] = hi, dst[COUT / 8 + half * (HC / 8) + g8] = lo;
+                    }
+                }
+            }
+            // every MMA of the band has completed (the last acc_full was observed) and every residual read of the strip is done
+            named_bar_sync(1, 256);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// ---------------------------------------------------------------- max-pool on split pixels (torch MaxPool2d, -inf padding)
+// x [B][H][W][C hi | C lo] -> y [B][Ho][Wo][C hi | C lo]; a thread takes 8 channels of one output pixel
+template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
+                                                           long n_items) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_items) return;
+    constexpr int G = C / 8;
+    const int g = (int)(i % G);
+    const long op = i / G;
+    const int wo = (int)(op % Wo), ho = (int)((op / Wo) % Ho);
+    const long clip = op / ((long)Wo * Ho);
+    const uint16_t* xc = x + (size_t)clip * H * W * (2 * C);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+        const int h = ho * SH - PH + kh;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+            const int w_ = wo * SW - PW + kw;
+            if (w_ < 0 || w_ >= W) continue;
+            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            float v[8];
+            me_join8(__ldg(p + g), __ldg(p + G + g), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+        }
+    }
+    uint4 hi, lo;
+    me_split8(m, hi, lo);
+    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)op * (2 * C));
+    dst[g] = hi, dst[G + g] = lo;
+}
+
+// h3 [B][T][16 bins][32 hi | 32 lo] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded
+// BatchNorm1d) -> xf_out [B][T][64];  xf_proj = proj(xf_out) (transformer.py:458).  w4t [512][64], wpt [64][64] (input-major).
+constexpr int kC4Rows = 16;
+__global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* __restrict__ h3, const float* __restrict__ w4t, const float* __restrict__ b4,
+                                                              const float* __restrict__ wpt, const float* __restrict__ bp, float* __restrict__ xf_out,
+                                                              float* __restrict__ xf_proj, long M) {
+    __shared__ float s_f[kC4Rows][512 + 4];
+    __shared__ float s_o[kC4Rows][64];
+    const long row0 = (long)blockIdx.x * kC4Rows;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kC4Rows * 16 * 4; i += 256) {         // (row, bin, 8-channel group)
+        const int r = i >> 6, w = (i >> 2) & 15, g = i & 3;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (row0 + r < M) {
+            const uint4* p = reinterpret_cast<const uint4*>(h3 + ((size_t)(row0 + r) * 16 + w) * 64);
+            me_join8(__ldg(p + g), __ldg(p + 4 + g), v);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s_f[r][(8 * g + e) * 16 + w] = v[e];
+    }
+    __syncthreads();
+    const int o = tid & 63, rq = tid >> 6;                     // output feature, row quarter (4 rows each)
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = __ldg(b4 + o);
+    for (int k = 0; k < 512; ++k) {
+        const float wv = __ldg(w4t + k * 64 + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(s_f[4 * rq + j][k], wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_o[4 * rq + j][o] = acc[j];
+        if (row0 + 4 * rq + j < M) xf_out[(row0 + 4 * rq + j) * 64 + o] = acc[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = __ldg(bp + o);
+    for (int k = 0; k < 64; ++k) {
+        const float wv = __ldg(wpt + k * 64 + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(s_o[4 * rq + j][k], wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (row0 + 4 * rq + j < M) xf_proj[(row0 + 4 * rq + j) * 64 + o] = acc[j];
+}
+
+}  // namespace dc
