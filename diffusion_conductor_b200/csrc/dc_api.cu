@@ -327,8 +327,8 @@ int init_kernel_attrs(dc_handle* h) {
             DC_CUDA(h, cudaFuncGetAttributes(&fa, fn[i]));
             const int by_smem = (227 * 1024) / (sm[i] + (int)fa.sharedSizeBytes + 1024);
             const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * ((kMeThreads + 31) & ~31));
-            h->me_occ[i] = std::max(1, std::min(std::min(by_smem, by_regs), 4));
-            if (getenv("DC_VERBOSE")) fprintf(stderr, "[dc_b200] conv_tc variant %d: %d regs, %d B smem -> %d CTAs/SM\n", i, fa.numRegs, sm[i], h->me_occ[i]);
+            if (h) h->me_occ[i] = std::max(1, std::min(std::min(by_smem, by_regs), 4));           // (h is null in dc_selftest_gemm)
+            if (h && getenv("DC_VERBOSE")) fprintf(stderr, "[dc_b200] conv_tc variant %d: %d regs, %d B smem -> %d CTAs/SM\n", i, fa.numRegs, sm[i], h->me_occ[i]);
         }
     }
     void (*clip_variants[8])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>,
@@ -1315,6 +1315,13 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
                                                                                    h->me_bias + (li - 1) * 64);
     };
     auto blocks256 = [](long n) { return (unsigned)((n + 255) / 256); };
+    // output rows per thread of the sliding-window pools: long segments where there are many rows, short ones where the
+    // parallelism is needed (a segment costs KH - SH start-up rows)
+    auto pool = [&](auto kern, const uint16_t* src, uint16_t* dst, int H, int W, int Ho, int Wo, int nb, int groups, int seg) {
+        const int nseg = (Ho + seg - 1) / seg;
+        const long items = (long)nb * nseg * Wo * groups;
+        kern<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(src, dst, H, W, Ho, Wo, seg, nseg, items);
+    };
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
@@ -1323,17 +1330,17 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p0, p1, H, nb, 1);
         conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
-        maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 2), 256, 0, st>>>(p0, p1, H, W, Ho, Wo, (long)nb * Ho * Wo * 2);
+        pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 30);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<16, 32, 2, 64, kMeR64>, me_smem_bytes<16, 32, 2, 64, kMeR64>(), h->me_occ[1], kMeR64, p1, p0, H, nb, 3);
         conv(conv_tc_kernel<32, 32, 1, 64, kMeR64>, me_smem_bytes<32, 32, 1, 64, kMeR64>(), h->me_occ[2], kMeR64, p0, p1, H, nb, 4);
         Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
-        maxpool_split_kernel<32, 5, 5, 3, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p1, p0, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
+        pool(maxpool_split_kernel<32, 5, 5, 3, 2, 2, 2>, p1, p0, H, W, Ho, Wo, nb, 4, 1);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p0, p1, H, nb, 5);
         conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p1, p0, H, nb, 6);
         Ho = (H + 2 - 3) / 1 + 1, Wo = (W + 2 - 3) / 2 + 1;           // MaxPool2d((3,3), stride (1,2), padding 1)
-        maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p0, p1, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
+        pool(maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1>, p0, p1, H, W, Ho, Wo, nb, 4, 6);
         H = Ho, W = Wo;                                               // (nb, T, 16, 32 split)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;

@@ -176,12 +176,31 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
             const int clip = job / bands_per_clip, y0 = (job - clip * bands_per_clip) * R;
             const uint16_t* xc = x + (size_t)clip * H * W * (2 * CIN);
             // ---- stage the (R + 2) x P pixels of the band: coalesced 16-byte chunks, reflect halo by index arithmetic
-            for (int i = tid; i < (R + 2) * P * NCH; i += 256) {
-                const int sp = i / NCH, ch = i - sp * NCH, ys = sp / P, xs = sp - ys * P;
-                const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);
-                const int c = ch < NCH / 2 ? ch : ch - NCH / 2 + 2 * KH;       // hi chunks at 0 .., lo chunks right behind the hi K chunks
-                *reinterpret_cast<uint4*>(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)c)) = v;
+            {
+                // thread -> fixed 16-byte chunk ch of the pixels sp = tid / NCH, + 256 / NCH, ...: (row, column) of the staged pixel
+                // advance incrementally (no divisions); U loads are in flight per thread (one L2 round trip per batch)
+                constexpr int NPIX = (R + 2) * P, D = 256 / NCH, U = 6;
+                const int ch = tid % NCH;
+                int sp = tid / NCH, ys = sp / P, xs = sp - ys * P;
+                while (sp < NPIX) {
+                    uint4 v[U];
+                    uint32_t dst[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (sp < NPIX) {
+                            const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
+                            v[u] = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);
+                            dst[u] = sw128_offset((uint32_t)(1 + sp), (uint32_t)ch);      // hi chunks first, lo chunks right behind
+                        } else {
+                            dst[u] = 0xFFFFFFFFu;
+                        }
+                        sp += D, xs += D;
+                        while (xs >= P) xs -= P, ++ys;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (dst[u] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(strip + dst[u]) = v[u];
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -243,25 +262,29 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
 }
 
 // ---------------------------------------------------------------- max-pool on split pixels (torch MaxPool2d, -inf padding)
-// x [B][H][W][C hi | C lo] -> y [B][Ho][Wo][C hi | C lo]; a thread takes 8 channels of one output pixel
+// x [B][H][W][C hi | C lo] -> y [B][Ho][Wo][C hi | C lo].  A thread owns 8 channels of one output COLUMN segment and slides down
+// the rows: the maximum over the KW input columns of an input row is computed once and kept in a register ring of KH rows, so an
+// output costs SH x KW pixel loads instead of KH x KW.
 template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
-__global__ void __launch_bounds__(256) maxpool_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
-                                                           long n_items) {
-    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+__global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
+                                                           int seg_rows, int nseg, long n_items) {
+    const long i = (long)blockIdx.x * 128 + threadIdx.x;
     if (i >= n_items) return;
     constexpr int G = C / 8;
     const int g = (int)(i % G);
-    const long op = i / G;
-    const int wo = (int)(op % Wo), ho = (int)((op / Wo) % Ho);
-    const long clip = op / ((long)Wo * Ho);
+    long t = i / G;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int seg = (int)(t % nseg);
+    const long clip = t / nseg;
     const uint16_t* xc = x + (size_t)clip * H * W * (2 * C);
-    float m[8];
+    uint16_t* yc = y + (size_t)clip * Ho * Wo * (2 * C);
+    const int ho0 = seg * seg_rows, ho1 = min(ho0 + seg_rows, Ho);
+    float ring[KH][8];                                           // row maxima of input rows h, indexed h mod KH (fully unrolled below)
+    auto row_max = [&](int h, float* m) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
-#pragma unroll
-    for (int kh = 0; kh < KH; ++kh) {
-        const int h = ho * SH - PH + kh;
-        if (h < 0 || h >= H) continue;
+        for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+        if (h < 0 || h >= H) return;
 #pragma unroll
         for (int kw = 0; kw < KW; ++kw) {
             const int w_ = wo * SW - PW + kw;
@@ -272,11 +295,38 @@ __global__ void __launch_bounds__(256) maxpool_split_kernel(const uint16_t* __re
 #pragma unroll
             for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
         }
+    };
+    // rows of the first window except its last SH rows
+    int hnext = ho0 * SH - PH;                                   // next input row to fetch
+#pragma unroll
+    for (int k = 0; k < KH - SH; ++k, ++hnext) row_max(hnext, ring[k]);
+    int slot = KH - SH;                                          // ring slot of the next fetched row (compile-time pattern: KH, SH small)
+    for (int ho = ho0; ho < ho1; ++ho) {
+#pragma unroll
+        for (int k = 0; k < SH; ++k, ++hnext) {
+            float m[8];
+            row_max(hnext, m);
+#pragma unroll
+            for (int s2 = 0; s2 < KH; ++s2)
+                if (s2 == slot) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ring[s2][e] = m[e];
+                }
+            slot = slot + 1 == KH ? 0 : slot + 1;
+        }
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float m = ring[0][e];
+#pragma unroll
+            for (int k = 1; k < KH; ++k) m = fmaxf(m, ring[k][e]);
+            o8[e] = m;
+        }
+        uint4 hi, lo;
+        me_split8(o8, hi, lo);
+        uint4* dst = reinterpret_cast<uint4*>(yc + ((size_t)ho * Wo + wo) * (2 * C));
+        dst[g] = hi, dst[G + g] = lo;
     }
-    uint4 hi, lo;
-    me_split8(m, hi, lo);
-    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)op * (2 * C));
-    dst[g] = hi, dst[G + g] = lo;
 }
 
 // h3 [B][T][16 bins][32 hi | 32 lo] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded
