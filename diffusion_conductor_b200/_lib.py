@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdc_b200.so")
+# DC_B200_LIB: an alternative build of the same library (A/B experiments on one GPU box); the product is the in-tree file
+LIB_PATH = os.environ.get("DC_B200_LIB") or os.path.join(_HERE, "libdc_b200.so")
 
 DC_OPERAND_BF16, DC_OPERAND_FP16 = 0, 1
 DC_SAMPLER_NONE, DC_SAMPLER_DDIM, DC_SAMPLER_DDPM = 0, 1, 2

@@ -103,6 +103,7 @@ struct ClipBarriers : LayerBarriers {
     uint64_t slice_ready[2];            // large clusters: "my merged slice of reduction seq is ready" (count nt - 1)
     uint64_t w1c_full;                  // the (W1 Wo_ca) image of the current layer has landed
     uint64_t w_free;                    // row threads -> MMA issuer: y_ca has been read out of W, h16 . W1 may start (16 warp arrivals)
+    uint64_t recv_free[2];              // kPush: peer -> this CTA: "my W1 Wo_ca buffer may receive your partial of reduction seq" (count 1)
 };
 
 // Merge of the per-clip partials through L2 (StepArgs::gx; only the kGx instantiation of the kernel contains it, so that the
@@ -193,7 +194,10 @@ __device__ __forceinline__ void gx_merge(const uint2* pbase, uint2* slices, floa
 
 // kTl: instrumented build for dc_debug_timeline (the marks cost ~5 % of the instruction stream, so the production
 // instantiation compiles them out)
-template <bool kBf16, bool kTl = false, bool kGx = false>
+// kPush (two-tile clips, cluster of 2): each CTA writes its partial straight into the peer's shared memory (the W1 Wo_ca buffer,
+// idle between its MMA and the next refill; the peer grants it with a credit) and the merge reads local shared memory only:
+// one DSMEM latency on the critical path instead of the arrive + pull round trips.
+template <bool kBf16, bool kTl = false, bool kGx = false, bool kPush = false>
 __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_constant__ StepArgs a) {
     constexpr int kNA = kPRingAStages, kSA = kStageBytes, kNB = kRingBStages, kSB = kRingBStageBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -233,6 +237,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             mbar_init(smem_u32(&bars->part_ready[i]), (uint32_t)max(nt - 1, 1));
             mbar_init(smem_u32(&bars->pull_done[i]), (uint32_t)max(nt - 1, 1));
             mbar_init(smem_u32(&bars->slice_ready[i]), (uint32_t)max(nt - 1, 1));
+            mbar_init(smem_u32(&bars->recv_free[i]), 1);
         }
         mbar_fence_init();
     }
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     // ring B held the V image and then this tile's partial of the reduction that opened layer `it`:
                     // refill only when the local q . blockdiag(A_sa) has been issued AND every peer has pulled the partial
                     mbar_wait(smem_u32(&bars->q_full), qf++ & 1u);
-                    if (!kGx && nt > 1) {
+                    if (!kGx && !kPush && nt > 1) {
                         const uint32_t seq = (uint32_t)(si * L + it);
                         mbar_wait(smem_u32(&bars->pull_done[seq & 1u]), (seq >> 1) & 1u);
                     }
@@ -585,6 +590,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 //                   with the Wo_ca residual GEMM (see the MMA issuer); the deferred bias of Wo_ca is part
                 //                   of the folded FFN-up bias and of the layer's final residual bias
                 rows_wait(bars, 2, ph[2]); tl.mark(108);
+                if constexpr (kPush) {
+                    // the a . (W1 Wo_ca) MMAs have completed: the buffer is idle until the refill that follows the next reduction, so the
+                    // peer may deposit its partial of that reduction there
+                    const uint32_t nseq = (uint32_t)(si * L + it + 1);
+                    if (threadIdx.x == 0 && nseq < (uint32_t)(a.n_steps * L))
+                        mbar_arrive_cluster(mapa_u32(smem_u32(&bars->recv_free[nseq & 1u]), (uint32_t)(rank ^ 1)));
+                }
                 {
                     float u[16];                                             // hidden 64 = 4 quarters of 16
                     tmem_ld16(trow + kColW + 16 * cq, u);
@@ -872,6 +884,24 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         st_global_v2(gp + 128 + tx, make_uint2(__float_as_uint(ssm[tx]), gtag));
                         if (!static_shift) st_global_v2(gp + tx, make_uint2(__float_as_uint(msm[tx]), gtag));
                     }
+                } else if (kPush && cq == 0) {
+                    float pr[32];
+                    tmem_ld32(trow + kColW + 32 * lq, pr);
+                    tmem_wait_ld();
+                    const int o = (lane & 16);
+                    const uint32_t off = (uint32_t)(256 + (r >> 4) * 256 + (r & 15) * 16);
+                    float4* dst = reinterpret_cast<float4*>(mypart + off);
+                    if (seq > 0) mbar_wait(smem_u32(&bars->recv_free[seq & 1u]), ((seq - 1u) >> 1) & 1u);
+                    const uint32_t rb = mapa_u32(smem_u32(w1c), (uint32_t)(rank ^ 1));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 pv = o ? make_float4(pr[16 + 4 * i], pr[17 + 4 * i], pr[18 + 4 * i], pr[19 + 4 * i])
+                                            : make_float4(pr[4 * i], pr[4 * i + 1], pr[4 * i + 2], pr[4 * i + 3]);
+                        dst[i] = pv;
+                        st_dsmem_f32x4(rb + (off + 4u * i) * 4u, pv);
+                    }
+                    mypart[tx] = msm[tx], mypart[128 + tx] = ssm[tx];
+                    st_dsmem_f32(rb + (uint32_t)tx * 4u, msm[tx]), st_dsmem_f32(rb + (uint32_t)(128 + tx) * 4u, ssm[tx]);
                 } else if (cq == 0) {      // TMEM lane = key feature r; its head's 16 value columns are the diagonal block
                     float pr[32];
                     tmem_ld32(trow + kColW + 32 * lq, pr);
@@ -906,6 +936,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     gx_merge<kBf16>(a.gx_part + ((size_t)clip * 2 + (seq & 1u)) * nt * kKvPartFloats,
                                     a.gx_slice + ((size_t)clip * 2 + (seq & 1u)) * (kD * 8), reinterpret_cast<float4*>(ringB), xbuf, nt, rank, tx,
                                     gtag, static_shift);
+                } else if (kPush) {
+                    // two tiles, both partials in THIS CTA's shared memory (own: ring B, peer's: W1 Wo_ca buffer): plain loads.
+                    // Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
+                    const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
+                    const float* pa = mypart;
+                    const float* pb = reinterpret_cast<const float*>(w1c);
+                    const int o_m = 16 * hh + d0, o_r = 256 + hh * 256 + d0 * 16 + l0;
+                    const float2 ma = *reinterpret_cast<const float2*>(pa + o_m), mb = *reinterpret_cast<const float2*>(pb + o_m);
+                    const float2 sa = *reinterpret_cast<const float2*>(pa + 128 + o_m), sb = *reinterpret_cast<const float2*>(pb + 128 + o_m);
+                    const float2 ra0 = *reinterpret_cast<const float2*>(pa + o_r), rb0 = *reinterpret_cast<const float2*>(pb + o_r);
+                    const float2 ra1 = *reinterpret_cast<const float2*>(pa + o_r + 16), rb1 = *reinterpret_cast<const float2*>(pb + o_r + 16);
+                    float wa0 = 1.f, wb0 = 1.f, wa1 = 1.f, wb1 = 1.f;
+                    if (!static_shift) {                                  // running column max: rescale to the common maximum
+                        const float M0 = fmaxf(ma.x, mb.x), M1 = fmaxf(ma.y, mb.y);
+                        wa0 = __expf(ma.x - M0), wb0 = __expf(mb.x - M0), wa1 = __expf(ma.y - M1), wb1 = __expf(mb.y - M1);
+                    }
+                    const float s0 = fmaf(sa.x, wa0, sb.x * wb0), s1 = fmaf(sa.y, wa1, sb.y * wb1);
+                    const float i0 = s0 > 0.f ? 1.f / s0 : 0.f, i1 = s1 > 0.f ? 1.f / s1 : 0.f;      // s = 0: every frame masked (static shift)
+                    const float o[2][2] = {{fmaf(ra0.x, wa0, rb0.x * wb0) * i0, fmaf(ra0.y, wa0, rb0.y * wb0) * i0},
+                                           {fmaf(ra1.x, wa1, rb1.x * wb1) * i1, fmaf(ra1.y, wa1, rb1.y * wb1) * i1}};
+#pragma unroll
+                    for (int dd = 0; dd < 2; ++dd) {
+                        const int ki = 16 * hh + d0 + dd;
+                        uint8_t* base = xbuf + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
+#pragma unroll
+                        for (int ll = 0; ll < 2; ++ll) {
+                            const int nj = 16 * hh + l0 + ll;
+                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
+                        }
+                    }
                 } else if (nt <= kDirectMergeTiles) {
                     // small clusters: every CTA pulls every partial.  Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
                     const int hh = tx >> 6, sub = tx & 63, d0 = (sub >> 3) * 2, l0 = (sub & 7) * 2;
@@ -1007,7 +1067,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 }
                 rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
                 tl.mark(126);
-                if (!kGx && nt > 1) {                                      // every pull of this CTA has completed: the peers may reuse ring B
+                if (!kGx && !kPush && nt > 1) {                            // every pull of this CTA has completed: the peers may reuse ring B
                     named_bar_sync(5, kRowThreads);                        // (off the critical path: the q . A GEMM is already on its way)
                     if (tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pull_done[seq & 1u]), (uint32_t)tx));
                 }

@@ -331,9 +331,10 @@ int init_kernel_attrs(dc_handle* h) {
             if (h && getenv("DC_VERBOSE")) fprintf(stderr, "[dc_b200] conv_tc variant %d: %d regs, %d B smem -> %d CTAs/SM\n", i, fa.numRegs, sm[i], h->me_occ[i]);
         }
     }
-    void (*clip_variants[8])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>,
-                                          clip_kernel<true, false, true>, clip_kernel<false, false, true>, clip_kernel<true, true, true>,
-                                          clip_kernel<false, true, true>};
+    void (*clip_variants[12])(StepArgs) = {clip_kernel<true, false>, clip_kernel<false, false>, clip_kernel<true, true>, clip_kernel<false, true>,
+                                           clip_kernel<true, false, true>, clip_kernel<false, false, true>, clip_kernel<true, true, true>,
+                                           clip_kernel<false, true, true>, clip_kernel<true, false, false, true>, clip_kernel<false, false, false, true>,
+                                           clip_kernel<true, true, false, true>, clip_kernel<false, true, false, true>};
     for (auto k : clip_variants) {
         DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kClipSmemBytes));
         DC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));     // clusters of 9..16 tiles
@@ -480,8 +481,13 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
         sa.gx_part = h->gx_part, sa.gx_slice = h->gx_slice, sa.gx_tag0 = h->gx_tag;
         h->gx_tag += need;
     }
+    // two-tile clips: the partials are pushed into the peer's shared memory (DC_PUSH=0: pulled, as for clusters of 3 and 4)
+    const char* pe = getenv("DC_PUSH");
+    const bool push = !h->clip_gx && h->clip_nt == 2 && !(pe && pe[0] == '0');
     void (*kern)(StepArgs) = h->clip_gx ? (h->timeline_on ? (h->bf16 ? clip_kernel<true, true, true> : clip_kernel<false, true, true>)
                                                           : (h->bf16 ? clip_kernel<true, false, true> : clip_kernel<false, false, true>))
+                             : push     ? (h->timeline_on ? (h->bf16 ? clip_kernel<true, true, false, true> : clip_kernel<false, true, false, true>)
+                                                          : (h->bf16 ? clip_kernel<true, false, false, true> : clip_kernel<false, false, false, true>))
                                         : (h->timeline_on ? (h->bf16 ? clip_kernel<true, true> : clip_kernel<false, true>)
                                                           : (h->bf16 ? clip_kernel<true, false> : clip_kernel<false, false>));
     DC_CUDA(h, launch_kc(h->use_pdl, h->clip_gx ? 1 : h->clip_nt, kern, dim3((unsigned)(h->B * h->clip_nt)), dim3(kTileThreads), kClipSmemBytes, st, sa));

@@ -324,6 +324,12 @@ __device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t par
         ::"r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
 }
+__device__ __forceinline__ void st_dsmem_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_f32x4(uint32_t cluster_addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
     float v;
     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
