@@ -366,7 +366,11 @@ def main():
     launches = plan.kernel_launches() - launches0
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    per_rank_ms = [round(total_ms / args.steps, 4)]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [round(float(v.item()) / args.steps, 4) for v in allt]       # every rank's own loop time (the line reports the max)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
@@ -481,7 +485,7 @@ def main():
         n_in = (hp.numel() + ho.numel() + hn.numel()) * 4
         line = {
             "metric": "motion-seconds generated/sec (50-step DDIM)", "value": round(value, 2), "unit": "motion-s/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4),
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "ms_per_step_by_rank": per_rank_ms,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": args.operand, "parity": parity, "data": "synthetic",
             "config": {"workload": workload_text(name, world), "global_batch": Bg, "clips_on_rank0": B,
                        "token_steps_per_step": Bg * T * S, "l2": "256 MiB buffer written between timed iterations",

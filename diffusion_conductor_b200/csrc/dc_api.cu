@@ -112,6 +112,8 @@ struct dc_handle {
     uint8_t* bd_sa = nullptr;     // [B][32 KB] block-diagonal self-attention K^T V images
     uint8_t* bd_ca = nullptr;     // [B][L][32 KB] cross-attention counterparts (step-invariant)
     int mask_invert = 0;
+    size_t kv_stride = 0;         // floats between the per-layer slices of `kv`
+    int kv_layers = 1;            // slices allocated
     float* kv_part = nullptr;     // [tiles][2][kKvPartFloats] partial time-axis reductions (per-layer path)
     int* clip_cnt = nullptr;      // [B]
     bool fuse_kv = false;
@@ -283,7 +285,10 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->aemb, aemb_tiles * 8 * (size_t)kABlockBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->hbuf, Mpad * kD * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->q_img, tiles * (size_t)kAworkBytes));
-    DC_CUDA(h, cudaMalloc((void**)&h->kv, Mpad * 256 * 4));
+    // K | V workspace: one [Mpad][256] slice per layer of a precompute chunk (as many layers as fit 1 GiB, at least one)
+    h->kv_stride = Mpad * 256;
+    h->kv_layers = (int)std::max<size_t>(1, std::min<size_t>((size_t)L, ((size_t)1 << 30) / (h->kv_stride * 4)));
+    DC_CUDA(h, cudaMalloc((void**)&h->kv, h->kv_stride * 4 * h->kv_layers));
     DC_CUDA(h, cudaMalloc((void**)&h->bd_sa, (size_t)B * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->bd_ca, (size_t)B * L * kAworkBytes));
     DC_CUDA(h, cudaMalloc((void**)&h->length, (size_t)B * 8));
@@ -375,8 +380,8 @@ cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, si
 }
 
 template <bool kBf16>
-int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream_t st) {
-    gemm_rows_kernel<kBf16><<<tiles, kTileThreads, kGemmSmemBytes, st>>>(ga);
+int launch_gemm_rows(dc_handle* h, const GemmRowsArgs& ga, int tiles, cudaStream_t st, int layers = 1) {
+    gemm_rows_kernel<kBf16><<<dim3((unsigned)tiles, (unsigned)layers), kTileThreads, kGemmSmemBytes, st>>>(ga);
     return 0;
 }
 
@@ -534,7 +539,7 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         mark(1);
         if (l + 1 < L && !h->fuse_kv) {
             DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? kv_reduce_kernel<true> : kv_reduce_kernel<false>, dim3(h->B * kH), dim3(256), 0, st,
-                                (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes));
+                                (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes, (size_t)0, (size_t)0));
             h->launches++;
             mark(2);
         }
@@ -1086,19 +1091,24 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
     else
         cond_prep_kernel<false><<<blocks4, 128, 0, st>>>(xf_proj, xf_out, h->WlinT, h->blin, h->M, h->xp, h->zimg);
     h->launches++;
-    for (int l = 0; l < L; ++l) {
+    // cross-attention K | V projections and their time-axis softmax + K^T V (step-invariant): all layers of a chunk in ONE launch
+    // each (blockIdx.y = layer) -- 16 launches of ~11 us were 0.18 ms of every host-to-host call
+    for (int l0 = 0; l0 < L; l0 += h->kv_layers) {
+        const int nl = std::min(h->kv_layers, L - l0);
         GemmRowsArgs ga{};
         ga.a_img = h->zimg;
-        ga.w_img = h->wkv + (size_t)l * 8 * 32768;
-        ga.bias = h->bkv + (size_t)l * 256;
+        ga.w_img = h->wkv + (size_t)l0 * 8 * 32768;
+        ga.bias = h->bkv + (size_t)l0 * 256;
         ga.out = h->kv;
         ga.M = h->M, ga.N = 256, ga.kblocks = 8, ga.ldo = 256, ga.blocked = 1;
-        const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st) : launch_gemm_rows<false>(h, ga, h->tiles, st);
+        ga.w_layer_stride = (size_t)8 * 32768, ga.bias_layer_stride = 256, ga.out_layer_stride = h->kv_stride;
+        const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st, nl) : launch_gemm_rows<false>(h, ga, h->tiles, st, nl);
         if (rc) return rc;
+        uint8_t* bd = h->bd_ca + (size_t)l0 * kAworkBytes;
         if (h->bf16)
-            kv_reduce_kernel<true><<<B * kH, 256, 0, st>>>(h->kv, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
+            kv_reduce_kernel<true><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * kAworkBytes, h->kv_stride, (size_t)kAworkBytes);
         else
-            kv_reduce_kernel<false><<<B * kH, 256, 0, st>>>(h->kv, T, h->bd_ca + (size_t)l * kAworkBytes, (size_t)L * kAworkBytes);
+            kv_reduce_kernel<false><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * kAworkBytes, h->kv_stride, (size_t)kAworkBytes);
         h->launches += 2;
     }
     DC_CUDA(h, cudaGetLastError());

@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 template <bool kBf16>
 __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv /*blocked [*,256]*/, int T,
-                                                         uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride) {
+                                                         uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride,
+                                                         size_t kv_layer_stride = 0 /* floats; blockIdx.y = layer */, size_t bd_layer_stride = 0 /* bytes */) {
+    kv += (size_t)blockIdx.y * kv_layer_stride;
+    bd += (size_t)blockIdx.y * bd_layer_stride;
     // loads: thread = (column chunk q of the head's 16 key/value columns, token lane) -> float4, 32 consecutive
     //        tokens per warp = 512 contiguous bytes of the blocked layout.
     // accumulation: 4 token groups x 64 threads, each thread a 2x2 block of the 16x16 result.

@@ -148,6 +148,9 @@ struct GemmRowsArgs {
     float* out;
     int M, N, kblocks, ldo;
     int blocked;            // 1: out is in the blocked activation layout with N columns (ldo ignored)
+    // blockIdx.y = layer (the step-invariant cross-attention K | V projections of several layers in one launch): strides between layers
+    size_t w_layer_stride;  // bytes
+    size_t bias_layer_stride, out_layer_stride;   // floats
 };
 
 template <bool kBf16>
@@ -179,13 +182,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
 
     if (warp == kProducerWarp) {
         if (lane == 0)
-            producer_loop(&op, 1, a.w_img, a.a_img + (size_t)blockIdx.x * a.kblocks * kStageABytes, ring, bars);
+            producer_loop(&op, 1, a.w_img + (size_t)blockIdx.y * a.w_layer_stride, a.a_img + (size_t)blockIdx.x * a.kblocks * kStageABytes, ring, bars);
     } else if (warp == kMmaWarp) {
         if (lane == 0) mma_loop<kBf16>(&op, 1, ring, nullptr, bars, tmem_base);
     } else {
         const int lq = warp & 3, cq = warp >> 2;
         const long g = (long)blockIdx.x * kTileRows + lq * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
+        float* outp = a.out + (size_t)blockIdx.y * a.out_layer_stride;
+        const float* biasp = a.bias ? a.bias + (size_t)blockIdx.y * a.bias_layer_stride : nullptr;
         mbar_wait(smem_u32(&bars->d_ready[0]), 0);
         tc_fence_after();
         // column quarter cq covers columns [64 cq, 64 cq + 64) in 16-column pieces
@@ -196,13 +201,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) gemm_rows_kernel(const __grid
             if (g < a.M) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float4* dst = reinterpret_cast<float4*>(a.blocked ? a.out + blk_index(g, c + 4 * i, a.N) : a.out + (size_t)g * a.ldo + c + 4 * i);
+                    float4* dst = reinterpret_cast<float4*>(a.blocked ? outp + blk_index(g, c + 4 * i, a.N) : outp + (size_t)g * a.ldo + c + 4 * i);
                     float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    if (a.bias) {
-                        o.x += a.bias[c + 4 * i];
-                        o.y += a.bias[c + 4 * i + 1];
-                        o.z += a.bias[c + 4 * i + 2];
-                        o.w += a.bias[c + 4 * i + 3];
+                    if (biasp) {
+                        o.x += biasp[c + 4 * i];
+                        o.y += biasp[c + 4 * i + 1];
+                        o.z += biasp[c + 4 * i + 2];
+                        o.w += biasp[c + 4 * i + 3];
                     }
                     *dst = o;
                 }
