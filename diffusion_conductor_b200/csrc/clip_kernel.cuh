@@ -45,6 +45,7 @@ struct StepArgs {
     const uint8_t* wout_img;    // output head `out` as a [32 x 384] K-major operand image [W_hi | W_hi | W_lo] (rows >= 26 zero), 24 KB
     const float* bo;            // [32]
     uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
+    size_t aemb_stride;         // bytes between the two A_emb images (step parity): the image of step i + 1 is built during step i
     const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
     size_t bd_ca_stride;
     const long long* length;    // [B] or null
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         // ---------------- ring A: per layer 3 FiLM projections (8 stages each), then Wk, Wv of the next layer
         //                  (kRingAItems = 26 items per layer; item order is what the two consumers below assume)
         if (lane == 0) {
-            const uint8_t* a_img = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
+            const uint8_t* a_img0 = a.aemb + (size_t)blockIdx.x * 8 * kStageABytes;
             uint32_t it_ = 0;
             auto stage_in = [&](const uint8_t* a_src, const uint8_t* w_src, uint32_t w_bytes) {
                 const uint32_t st = it_ % kNA, ph = (it_ / kNA) & 1u;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             };
             for (int si = 0; si < a.n_steps; ++si)
             for (int it = -1; it < L; ++it) {
+                const uint8_t* a_img = a_img0 + (kGx ? (size_t)(si & 1) * a.aemb_stride : (size_t)0);   // (one image is enough when it is rebuilt in place)
                 if (it >= 0) {
                     if (it == 0) {
                         mbar_wait(smem_u32(&bars->aemb_ready), (uint32_t)si & 1u);   // the row threads have written this step's A_emb image
@@ -486,8 +488,39 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
         RowStats rs{xchg, 1 + lq, r, cq, 0};
         float mean, rstd;
         float v[32];
+        // One 8-feature chunk (task = chunk * 512 + thread: row = task / 64, features 8 (task % 64) ..) of the A_emb image
+        // SiLU(time embedding of `tstep_img` + linear(xf_proj)) of this tile -> image `img`.  The first step of a launch builds all 16
+        // chunks per thread in its prologue; every later step finds its image ready, built two chunks per layer inside the MMA wait
+        // windows of the step before (the whole build in one place was 13 k cycles of every step's critical path).
+        auto aemb_chunk = [&](int chunk, int tstep_img, uint8_t* img) {
+            const int task = chunk * kRowThreads + (int)threadIdx.x;
+            const int row = task >> 6, ch = task & 63;
+            const long gg = row0g + min(row, max(nrows - 1, 0));
+            const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + ch * 8);
+            const float4* tr4 = reinterpret_cast<const float4*>(a.te + (size_t)tstep_img * a.te_step_stride + (size_t)clip * a.te_stride + ch * 8);
+            const float4 a0 = __ldg(xr4), a1 = __ldg(xr4 + 1), t0v = __ldg(tr4), t1v = __ldg(tr4 + 1);
+            const float e8[8] = {a0.x + t0v.x, a0.y + t0v.y, a0.z + t0v.z, a0.w + t0v.w, a1.x + t1v.x, a1.y + t1v.y, a1.z + t1v.z, a1.w + t1v.w};
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(silu_f<kBf16>(e8[2 * i]), silu_f<kBf16>(e8[2 * i + 1]));
+            const uint4 pk = row < nrows ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
+        };
+        const int chunks_per_window = (16 + 2 * L - 1) / (2 * L);          // two windows per layer carry the next step's 16 chunks
 
         for (int si = 0; si < a.n_steps; ++si) {
+        // (only where it pays: long clips, +2 %; on two-tile clips the same slices cost 2 - 7 % -- their MMA wait windows are not idle enough)
+        uint8_t* img_next = (kGx && si + 1 < a.n_steps) ? a.aemb_out + (size_t)((si + 1) & 1) * a.aemb_stride + (size_t)blockIdx.x * 8 * kStageABytes : nullptr;
+        auto next_chunks = [&](int window) {                               // window = 2 it, 2 it + 1
+            if (img_next == nullptr) return;
+            for (int c = window * chunks_per_window; c < min(16, (window + 1) * chunks_per_window); ++c) aemb_chunk(c, a.step0 - si - 1, img_next);
+            // the linear(xf_proj) values of the NEXT window's chunks -> L1 now: an L2 round trip behind the weight stream is 1.5 - 2 k cycles
+            for (int c = (window + 1) * chunks_per_window; c < min(16, (window + 2) * chunks_per_window); ++c) {
+                const int task = c * kRowThreads + (int)threadIdx.x;
+                const long gg = row0g + min(task >> 6, max(nrows - 1, 0));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.xp + gg * kE + (task & 63) * 8));
+            }
+        };
         const int tstep = a.step0 - si;                                  // timestep index of this step
         const float* x_src = si == 0 ? a.x_in : a.x_out;
         // ---- step prologue (reference transformer.py:482,488-490): h0 = joint_embed(x) + sequence_embedding -> TMEM (stays
@@ -551,6 +584,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 rows_wait(bars, 0, ph[0]); tl.mark(102);                                   // S = A_emb . We_sa
                 film_to_a<kBf16>(trow, v, mean, rstd, prm + kPrmStSa, awork, r, c0, s_free_addr, lane);   // releases S as soon as it has been read
                 rows_publish<false>(a_ready_addr, lane); tl.mark(151);                                          // -> h += A . Wo_sa
+                next_chunks(2 * it);
 
                 // ================= cross-attention
                 rows_wait(bars, 1, ph[1]); tl.mark(103);
@@ -566,6 +600,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 store_a16<kBf16>(awork, r, c0 + 16, v + 16);
                 tmem_wait_st();
                 rows_publish<false>(a_ready_addr, lane); tl.mark(152);                                          // -> W = LN(h) . Wq_ca
+                next_chunks(2 * it + 1);
                 rows_wait(bars, 2, ph[2]); tl.mark(104);
                 tmem_ld32(trow + kColW + c0, v);
                 tmem_wait_ld();
@@ -691,30 +726,33 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
             rows_publish<false>(a_ready_addr, lane); tl.mark(158);
             if (it < 0) {
                 // ---- rest of the step prologue, overlapped with the first q|k|v MMAs: this tile's A_emb image -> global
-                const int tx = threadIdx.x;
-                const float* ste = reinterpret_cast<const float*>(xbuf) + kP * kD + kD + kTileRows * kP;
-                uint8_t* img = a.aemb_out + (size_t)blockIdx.x * 8 * kStageABytes;
-                for (int k0 = 0; k0 < 16; k0 += 4) {                 // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
-                    float4 xa[4][2];
+                if (!kGx || si == 0) {
+                    // the whole image here, four chunks per thread with their loads in flight together
+                    uint8_t* img = a.aemb_out + (kGx ? (size_t)(si & 1) * a.aemb_stride : (size_t)0) + (size_t)blockIdx.x * 8 * kStageABytes;
+                    const int tx = threadIdx.x;
+                    const float* ste = reinterpret_cast<const float*>(xbuf) + kP * kD + kD + kTileRows * kP;
+                    for (int k0 = 0; k0 < 16; k0 += 4) {                 // 128 rows x 64 chunks of 8 features; a warp = 1 KB of one row
+                        float4 xa[4][2];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int task = (k0 + k) * kRowThreads + tx;
-                        const long gg = row0g + min(task >> 6, max(nrows - 1, 0));
-                        const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + (task & 63) * 8);
-                        xa[k][0] = __ldg(xr4), xa[k][1] = __ldg(xr4 + 1);
-                    }
+                        for (int k = 0; k < 4; ++k) {
+                            const int task = (k0 + k) * kRowThreads + tx;
+                            const long gg = row0g + min(task >> 6, max(nrows - 1, 0));
+                            const float4* xr4 = reinterpret_cast<const float4*>(a.xp + gg * kE + (task & 63) * 8);
+                            xa[k][0] = __ldg(xr4), xa[k][1] = __ldg(xr4 + 1);
+                        }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int task = (k0 + k) * kRowThreads + tx;
-                        const int row = task >> 6, ch = task & 63;
-                        const float4* tr = reinterpret_cast<const float4*>(ste + ch * 8);
-                        const float4 a0 = xa[k][0], a1 = xa[k][1], t0v = tr[0], t1v = tr[1];
-                        const float e8[8] = {a0.x + t0v.x, a0.y + t0v.y, a0.z + t0v.z, a0.w + t0v.w, a1.x + t1v.x, a1.y + t1v.y, a1.z + t1v.z, a1.w + t1v.w};
-                        uint32_t p[4];
+                        for (int k = 0; k < 4; ++k) {
+                            const int task = (k0 + k) * kRowThreads + tx;
+                            const int row = task >> 6, ch = task & 63;
+                            const float4* tr = reinterpret_cast<const float4*>(ste + ch * 8);
+                            const float4 a0 = xa[k][0], a1 = xa[k][1], t0v = tr[0], t1v = tr[1];
+                            const float e8[8] = {a0.x + t0v.x, a0.y + t0v.y, a0.z + t0v.z, a0.w + t0v.w, a1.x + t1v.x, a1.y + t1v.y, a1.z + t1v.z, a1.w + t1v.w};
+                            uint32_t p[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(silu_f<kBf16>(e8[2 * i]), silu_f<kBf16>(e8[2 * i + 1]));
-                        const uint4 pk = row < nrows ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
+                            for (int i = 0; i < 4; ++i) p[i] = pack2<kBf16>(silu_f<kBf16>(e8[2 * i]), silu_f<kBf16>(e8[2 * i + 1]));
+                            const uint4 pk = row < nrows ? make_uint4(p[0], p[1], p[2], p[3]) : make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(img + (size_t)(ch >> 3) * kABlockBytes + sw128_offset(row, ch & 7)) = pk;
+                        }
                     }
                 }
                 __threadfence();                                       // the image must have reached L2 ...

@@ -106,6 +106,7 @@ struct dc_handle {
     float* xp = nullptr;
     uint8_t* zimg = nullptr;
     uint8_t* aemb = nullptr;
+    size_t aemb_stride = 0;
     float* hbuf = nullptr;
     uint8_t* q_img = nullptr;     // [tiles][32 KB] packed softmax_hd(Q) image
     float* kv = nullptr;
@@ -282,7 +283,8 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->xp, Mpad * kE * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->zimg, tiles * 8 * (size_t)kABlockBytes));
     const size_t aemb_tiles = std::max(tiles, clip_tiles);
-    DC_CUDA(h, cudaMalloc((void**)&h->aemb, aemb_tiles * 8 * (size_t)kABlockBytes));
+    h->aemb_stride = aemb_tiles * 8 * (size_t)kABlockBytes;           // two images (step parity) for the persistent kernel
+    DC_CUDA(h, cudaMalloc((void**)&h->aemb, 2 * h->aemb_stride));
     DC_CUDA(h, cudaMalloc((void**)&h->hbuf, Mpad * kD * 4));
     DC_CUDA(h, cudaMalloc((void**)&h->q_img, tiles * (size_t)kAworkBytes));
     // K | V workspace: one [Mpad][256] slice per layer of a precompute chunk (as many layers as fit 1 GiB, at least one)
@@ -302,7 +304,7 @@ int ensure_workspace(dc_handle* h, int B, int T) {
     DC_CUDA(h, cudaMalloc((void**)&h->in_out, M * kMusic * 4));
     // padded rows of the operand images must hold finite values
     DC_CUDA(h, cudaMemset(h->zimg, 0, tiles * 8 * (size_t)kABlockBytes));
-    DC_CUDA(h, cudaMemset(h->aemb, 0, aemb_tiles * 8 * (size_t)kABlockBytes));
+    DC_CUDA(h, cudaMemset(h->aemb, 0, 2 * h->aemb_stride));
     DC_CUDA(h, cudaMemset(h->q_img, 0, tiles * (size_t)kAworkBytes));
     // off-diagonal head blocks of the attention images are never written: they must be zero
     DC_CUDA(h, cudaMemset(h->bd_sa, 0, (size_t)B * kAworkBytes));
@@ -456,7 +458,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     StepArgs sa{};
     sa.L = L, sa.M = h->M, sa.T = h->T;
     sa.n_steps = n_steps, sa.step0 = step0;
-    sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.prm = h->prm_clip, sa.wfuse = h->wfuse;
+    sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.aemb_stride = h->aemb_stride, sa.prm = h->prm_clip, sa.wfuse = h->wfuse;
     sa.kshift = h->kshift, sa.static_mask = h->static_mask;
     sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
     sa.length = h->has_length ? h->length : nullptr;
