@@ -331,6 +331,42 @@ def test_cluster_sizes_and_merge_paths(operand):
         close(y, ref, operand, f"forward B={B} T={T} ({-(-T // 128)} tiles per clip)")
 
 
+@pytest.mark.parametrize("operand", ["bf16", "fp16"])
+def test_exchange_paths_agree(monkeypatch, operand):
+    """The per-clip exchange of the time-axis reduction has three implementations (distributed shared memory pulled, pushed for
+    two-tile clips, and flag-in-data words through L2 for long clips).  Force each of them on shapes the default would route
+    elsewhere -- with the running-max softmax shift too, which exercises the rescaling merge -- and compare against the oracle
+    and against each other."""
+    m, sd = make_model(2, 41, operand, num_frames=2048)
+    monkeypatch.setenv("DC_STATIC_SHIFT", "0")               # read when the weights are finalised (first call): a second model
+    m_run, _ = make_model(2, 41, operand, num_frames=2048)
+    xf_proj, xf_out = synth_features(1, 8, seed=1)
+    m_run(torch.zeros(1, 8, 26).cuda(), torch.zeros(1, dtype=torch.long).cuda(), length=[8], xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+    monkeypatch.delenv("DC_STATIC_SHIFT")
+    for (B, T, length) in [(3, 200, [200, 129, 0]), (2, 500, [500, 499]), (2, 700, [700, 130]), (1, 1800, [1800])]:
+        xf_proj, xf_out = synth_features(B, T, seed=B * 100 + T)
+        _, x = synth_inputs(B, T, seed=B * 100 + T)
+        t = (torch.arange(B) * 5 + 2) % 25
+        with torch.no_grad():
+            ref = O.motion_transformer_forward(sd, x, t, length, xf_proj, xf_out)
+        outs = {}
+        for name, model, env in (("cluster", m, {"DC_GX": "0", "DC_PUSH": "0"}), ("cluster-push", m, {"DC_GX": "0", "DC_PUSH": "1"}),
+                                 ("l2", m, {"DC_GX": "1"}), ("l2-running-max", m_run, {"DC_GX": "1"}),
+                                 ("cluster-running-max", m_run, {"DC_GX": "0"})):
+            for k in ("DC_GX", "DC_PUSH"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            y = model(x.cuda(), t.cuda(), length=length, xf_proj=xf_proj.cuda(), xf_out=xf_out.cuda())
+            close(y, ref, operand, f"forward T={T}, exchange {name}")
+            outs[name] = y.cpu()
+        for k in ("DC_GX", "DC_PUSH"):
+            monkeypatch.delenv(k, raising=False)
+        rms = float(ref.pow(2).mean().sqrt())
+        for a, b in (("cluster", "l2"), ("cluster", "cluster-push"), ("l2-running-max", "cluster-running-max")):
+            assert float((outs[a] - outs[b]).pow(2).mean().sqrt()) < (2e-3 if operand == "bf16" else 3e-4) * rms, (T, a, b)
+
+
 def test_static_and_running_softmax_shift(monkeypatch):
     """Time-axis softmax of the self-attention keys: the kernel replaces the running column max by a static
     weight-norm bound of |k| when that bound is small (bf16 operands, ordinary weights) and keeps the exact running max
