@@ -46,7 +46,7 @@ struct StepArgs {
     const float* bo;            // [32]
     uint8_t* aemb_out;          // == aemb: this CTA writes its own tile's A_emb image first
     size_t aemb_stride;         // bytes between the two A_emb images (step parity): the image of step i + 1 is built during step i
-    const uint8_t* bd_ca;       // cross-attention images: clip stride bd_ca_stride, layer stride kAworkBytes
+    const uint8_t* bd_ca;       // cross-attention images, compact 4 KB head-block form (bdc_offset): clip stride bd_ca_stride, layer stride kBdcBytes
     size_t bd_ca_stride;
     const long long* length;    // [B] or null
     uint32_t off[12];           // byte offsets of the packed matrices inside a layer slab (see dc_api.cu)
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     }
                     load(slab + a.off[kOWoSa], 2, 16384);
                     load(slab + a.off[kOWqCa], 2, 16384);
-                    load(a.bd_ca + (size_t)clip * a.bd_ca_stride + (size_t)it * kAworkBytes, 2, 16384);
+                    load(a.bd_ca + (size_t)clip * a.bd_ca_stride + (size_t)it * kBdcBytes, 1, kBdcBytes);      // eight 16 x 16 head blocks
                     load(slab + a.off[kOW1], 1, 16384);                            // both 8 KB k-blocks of W1 in one stage
                     load(slab + a.off[kOWoCa], 2, 16384);
                     load(slab + a.off[kOW2], 1, 16384);
@@ -399,7 +399,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     umma_commit(smem_u32(&bars->q_full));
                     wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(201);   // h += . Wo_sa
                     wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(202);  // q_ca
-                    wait_a(), gemm_b(2, 128, kColW, false, awork), done(2), tl.mark(203);  // y = softmax(q) . blockdiag(A_ca)
+                    {   // y = softmax(q) . blockdiag(A_ca): one N = 16 MMA per head on the compact image (one ring-B stage)
+                        wait_a();
+                        const uint32_t st = itB % kNB, ph = (itB / kNB) & 1u;
+                        ++itB;
+                        mbar_wait(smem_u32(&bars->fullB[st]), ph);
+                        tc_fence_after();
+                        tl.mark(401);
+                        const uint32_t b_base = smem_u32(ringB + st * kSB), idesc16 = make_idesc<kBf16>(kTileRows, 16);
+#pragma unroll
+                        for (int hh = 0; hh < kH; ++hh)
+                            umma_f16(tmem_base + kColW + 16 * hh, make_desc_kmajor_sw128(awork + (hh >> 2) * kABlockBytes) + 2 * (hh & 3),
+                                     make_desc_kmajor_sw128(b_base + (hh >> 2) * 2048) + 2 * (hh & 3), idesc16, 0u);
+                        umma_commit(smem_u32(&bars->emptyB[st]));
+                        done(2), tl.mark(203);
+                    }
                     // The FFN has no pre-norm, so its up-projection is linear in the residual add before it:
                     //   u = (h + a . Wo_ca + bo) . W1 = h16 . W1 + a . (W1 Wo_ca) + const.
                     // h16 . W1 is issued as soon as the row threads have read y_ca out of W (while they do the FiLM math);

@@ -460,7 +460,7 @@ int enqueue_persistent(dc_handle* h, const float* x_in, const float* te, int te_
     sa.n_steps = n_steps, sa.step0 = step0;
     sa.wbuf = h->wbuf, sa.aemb = h->aemb, sa.aemb_out = h->aemb, sa.aemb_stride = h->aemb_stride, sa.prm = h->prm_clip, sa.wfuse = h->wfuse;
     sa.kshift = h->kshift, sa.static_mask = h->static_mask;
-    sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kAworkBytes;
+    sa.bd_ca = h->bd_ca, sa.bd_ca_stride = (size_t)L * kBdcBytes;          // compact head-block images (written so by dc_prepare_cond when persist)
     sa.length = h->has_length ? h->length : nullptr;
     sa.x_in = x_in, sa.x_out = x_upd, sa.x0_out = x0_out, sa.x0_stride = x0_stride, sa.x_trace = x_trace;
     sa.noise = noise, sa.noise_stride = noise_stride, sa.xp = h->xp;
@@ -541,7 +541,7 @@ int enqueue_step(dc_handle* h, const float* x_in, const float* te, int te_stride
         mark(1);
         if (l + 1 < L && !h->fuse_kv) {
             DC_CUDA(h, launch_k(h->use_pdl, h->bf16 ? kv_reduce_kernel<true> : kv_reduce_kernel<false>, dim3(h->B * kH), dim3(256), 0, st,
-                                (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes, (size_t)0, (size_t)0));
+                                (const float*)h->kv, h->T, h->bd_sa, (size_t)kAworkBytes, (size_t)0, (size_t)0, 0));
             h->launches++;
             mark(2);
         }
@@ -1071,6 +1071,9 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
             }
         }
         if (fuse != h->fuse_kv || persist != h->persist) drop_graph(h);
+        // the two paths keep the cross-attention images in different layouts (compact head blocks / block-diagonal with zero
+        // off-diagonal blocks that are never rewritten): start from zeros when the path changes
+        if (persist != h->persist) DC_CUDA(h, cudaMemsetAsync(h->bd_ca, 0, h->cap_B * (size_t)h->cfg.num_layers * kAworkBytes, st));
         h->fuse_kv = fuse;
         h->persist = persist;
         h->clip_nt = nt;
@@ -1106,11 +1109,14 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         ga.w_layer_stride = (size_t)8 * 32768, ga.bias_layer_stride = 256, ga.out_layer_stride = h->kv_stride;
         const int rc = h->bf16 ? launch_gemm_rows<true>(h, ga, h->tiles, st, nl) : launch_gemm_rows<false>(h, ga, h->tiles, st, nl);
         if (rc) return rc;
-        uint8_t* bd = h->bd_ca + (size_t)l0 * kAworkBytes;
+        // persistent kernel: compact 4 KB head-block images (16.8 -> 2.1 MB on C2: the working set is re-streamed out of L2 every
+        // step); per-layer path: the [128 x 128] block-diagonal B operand its GEMM expects
+        const size_t lstride = h->persist ? (size_t)kBdcBytes : (size_t)kAworkBytes;
+        uint8_t* bd = h->bd_ca + (size_t)l0 * lstride;
         if (h->bf16)
-            kv_reduce_kernel<true><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * kAworkBytes, h->kv_stride, (size_t)kAworkBytes);
+            kv_reduce_kernel<true><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * lstride, h->kv_stride, lstride, h->persist ? 1 : 0);
         else
-            kv_reduce_kernel<false><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * kAworkBytes, h->kv_stride, (size_t)kAworkBytes);
+            kv_reduce_kernel<false><<<dim3((unsigned)(B * kH), (unsigned)nl), 256, 0, st>>>(h->kv, T, bd, (size_t)L * lstride, h->kv_stride, lstride, h->persist ? 1 : 0);
         h->launches += 2;
     }
     DC_CUDA(h, cudaGetLastError());

@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(128) step_begin_kernel(const float* __restrict
 template <bool kBf16>
 __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict__ kv /*blocked [*,256]*/, int T,
                                                          uint8_t* __restrict__ bd /*[B] images of 32 KB*/, size_t bd_stride,
-                                                         size_t kv_layer_stride = 0 /* floats; blockIdx.y = layer */, size_t bd_layer_stride = 0 /* bytes */) {
+                                                         size_t kv_layer_stride = 0 /* floats; blockIdx.y = layer */, size_t bd_layer_stride = 0 /* bytes */,
+                                                         int compact = 0 /* 1: 4 KB head-block image (bdc_offset) instead of the [128 x 128] one */) {
     kv += (size_t)blockIdx.y * kv_layer_stride;
     bd += (size_t)blockIdx.y * bd_layer_stride;
     // loads: thread = (column chunk q of the head's 16 key/value columns, token lane) -> float4, 32 consecutive
@@ -346,7 +347,8 @@ __global__ void __launch_bounds__(256) kv_reduce_kernel(const float* __restrict_
     const float acc = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
     const float se = (part[0][256 + d] + part[1][256 + d]) + (part[2][256 + d] + part[3][256 + d]);
     const int ki = hh * kHd + d, nj = hh * kHd + l;
-    const size_t off = (size_t)b * bd_stride + (size_t)(ki >> 6) * kABlockBytes + sw128_offset(nj, (ki & 63) >> 3) + (ki & 7) * 2;
+    const size_t off = (size_t)b * bd_stride + (compact ? (size_t)bdc_offset((uint32_t)hh, (uint32_t)d, (uint32_t)l)
+                                                        : (size_t)(ki >> 6) * kABlockBytes + sw128_offset(nj, (ki & 63) >> 3) + (ki & 7) * 2);
     *reinterpret_cast<uint16_t*>(bd + off) = pack1<kBf16>(acc / se);
 }
 

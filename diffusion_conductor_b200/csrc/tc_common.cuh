@@ -458,6 +458,16 @@ __device__ __forceinline__ uint16_t pack1(float v) {
 // byte offset of (row r, 16-byte chunk c) inside a [rows x 64] K-major SW128 block
 __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
+// Compact block-diagonal attention image (persistent kernel): only the eight 16 x 16 head blocks of A = softmax_T(K)^T V exist.
+// Two [16 rows x 128 B] SW128 blocks; block hh / 4, row l (value column of the head), K elements 16 (hh % 4) + d (key feature of the
+// head): y[:, 16 hh + l] = sum_d q[:, 16 hh + d] A_hh[d][l] is ONE M = 128, N = 16, K = 16 MMA per head (an M = 128 MMA costs the same
+// ~64 cycles for N = 16 as for N = 128), and the image is 4 KB instead of a 32 KB block-diagonal [128 x 128] one that is 7/8 zeros.
+constexpr uint32_t kBdcBytes = 4096;
+__device__ __host__ __forceinline__ uint32_t bdc_offset(uint32_t hh, uint32_t d, uint32_t l) {
+    const uint32_t k = (hh & 3u) * 16u + d;
+    return (hh >> 2) * 2048u + l * 128u + (((k >> 3) ^ (l & 7u)) << 4) + (k & 7u) * 2u;
+}
+
 // write 16 consecutive fp32 (columns col0..col0+15 of the 128-wide row, col0 % 16 == 0) of row r
 // into the A-operand buffer made of [128 x 64] blocks.
 template <bool kBf16>
