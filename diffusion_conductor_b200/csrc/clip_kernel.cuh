@@ -186,10 +186,9 @@ __device__ __forceinline__ void gx_merge(const uint2* pbase, uint2* slices, floa
         do w = ld_volatile_v4(reinterpret_cast<const uint4*>(slices + dd * 8 + 2 * q4));
         while (w.y != gtag || w.w != gtag);
         const uint16_t vals[4] = {(uint16_t)(w.x & 0xFFFFu), (uint16_t)(w.x >> 16), (uint16_t)(w.z & 0xFFFFu), (uint16_t)(w.z >> 16)};
-        uint8_t* base = xbuf + (size_t)(dd >> 6) * kABlockBytes + (dd & 7) * 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint16_t*>(base + sw128_offset(16 * (dd >> 4) + 4 * q4 + i, (dd & 63) >> 3)) = vals[i];
+            *reinterpret_cast<uint16_t*>(xbuf + bdc_offset((uint32_t)(dd >> 4), (uint32_t)(dd & 15), (uint32_t)(4 * q4 + i))) = vals[i];
     }
 }
 
@@ -393,8 +392,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 if (it < 0) wait_a(), gemm_b(2, 128, kColH, false, awork), done(1), tl.mark(211);   // h0 = [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T
                 if (it >= 0) {
                     wait_a();                                                      // merged attention image written by the row threads
-                    for (int k = 0; k < 2; ++k)                                    // y = q . blockdiag(A_sa)
-                        umma_kblock(tmem_base + kColW, awork + k * kABlockBytes, smem_u32(xbuf) + k * kABlockBytes, idesc128, k > 0);
+                    {   // y = q . blockdiag(A_sa): one N = 16 MMA per head on the compact merged image
+                        const uint32_t idesc16 = make_idesc<kBf16>(kTileRows, 16);
+#pragma unroll
+                        for (int hh = 0; hh < kH; ++hh)
+                            umma_f16(tmem_base + kColW + 16 * hh, make_desc_kmajor_sw128(awork + (hh >> 2) * kABlockBytes) + 2 * (hh & 3),
+                                     make_desc_kmajor_sw128(smem_u32(xbuf) + (hh >> 2) * 2048) + 2 * (hh & 3), idesc16, 0u);
+                    }
                     done(2), tl.mark(200);
                     umma_commit(smem_u32(&bars->q_full));
                     wait_a(), gemm_b(2, 128, kColH, true, awork), done(1), tl.mark(201);   // h += . Wo_sa
@@ -972,13 +976,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 // (no separate fence: the arrive is a release at cluster scope, and release is cumulative over the writes of the
                 //  other row threads that were ordered before it by the CTA barrier above)
                 if (!kGx && nt > 1 && tx < nt && tx != rank) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->part_ready[seq & 1u]), (uint32_t)tx));
-                // ---- while the peers' partials are in flight: clear the image buffer (the merge writes only the diagonal
-                //      blocks); the parameter blocks fetched with cp.async above must have landed before the barrier below
-                {
-                    const uint4 z4 = make_uint4(0, 0, 0, 0);
-                    for (int i = tx; i < kAworkBytes / 16; i += kRowThreads) reinterpret_cast<uint4*>(xbuf)[i] = z4;
-                    cp_async_wait_all();
-                }
+                // ---- the parameter blocks fetched with cp.async above must have landed before the barrier below (the merge writes
+                //      the compact head-block image over the dead E image: nothing to clear)
+                cp_async_wait_all();
                 if (!kGx && nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
                 named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared
                 tl.mark(125);
@@ -1010,13 +1010,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                                            {fmaf(ra1.x, wa1, rb1.x * wb1) * i1, fmaf(ra1.y, wa1, rb1.y * wb1) * i1}};
 #pragma unroll
                     for (int dd = 0; dd < 2; ++dd) {
-                        const int ki = 16 * hh + d0 + dd;
-                        uint8_t* base = xbuf + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
 #pragma unroll
-                        for (int ll = 0; ll < 2; ++ll) {
-                            const int nj = 16 * hh + l0 + ll;
-                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
-                        }
+                        for (int ll = 0; ll < 2; ++ll)
+                            *reinterpret_cast<uint16_t*>(xbuf + bdc_offset((uint32_t)hh, (uint32_t)(d0 + dd), (uint32_t)(l0 + ll))) = pack1<kBf16>(o[dd][ll]);
                     }
                 } else if (nt <= kDirectMergeTiles) {
                     // small clusters: every CTA pulls every partial.  Thread -> head hh, key features d0, d0 + 1, value columns l0, l0 + 1.
@@ -1058,13 +1054,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                     const float o[2][2] = {{a00 * i0, a01 * i0}, {a10 * i1, a11 * i1}};
 #pragma unroll
                     for (int dd = 0; dd < 2; ++dd) {
-                        const int ki = 16 * hh + d0 + dd;
-                        uint8_t* base = xbuf + (size_t)(ki >> 6) * kABlockBytes + (ki & 7) * 2;
 #pragma unroll
-                        for (int ll = 0; ll < 2; ++ll) {
-                            const int nj = 16 * hh + l0 + ll;
-                            *reinterpret_cast<uint16_t*>(base + sw128_offset(nj, (ki & 63) >> 3)) = pack1<kBf16>(o[dd][ll]);
-                        }
+                        for (int ll = 0; ll < 2; ++ll)
+                            *reinterpret_cast<uint16_t*>(xbuf + bdc_offset((uint32_t)hh, (uint32_t)(d0 + dd), (uint32_t)(l0 + ll))) = pack1<kBf16>(o[dd][ll]);
                     }
                 } else {
                     // large clusters: reduce-scatter + all-gather (the shared-memory port of an SM serves ~20 B/clk to its
@@ -1111,10 +1103,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                         uint32_t w0, w1;
                         asm volatile("ld.shared::cluster.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src) : "memory");
                         const uint16_t vals[4] = {(uint16_t)(w0 & 0xFFFFu), (uint16_t)(w0 >> 16), (uint16_t)(w1 & 0xFFFFu), (uint16_t)(w1 >> 16)};
-                        uint8_t* base = xbuf + (size_t)(d >> 6) * kABlockBytes + (d & 7) * 2;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<uint16_t*>(base + sw128_offset(16 * (d >> 4) + l4 + i, (d & 63) >> 3)) = vals[i];
+                            *reinterpret_cast<uint16_t*>(xbuf + bdc_offset((uint32_t)(d >> 4), (uint32_t)(d & 15), (uint32_t)(l4 + i))) = vals[i];
                     }
                 }
                 rows_publish<false>(a_ready_addr, lane);                          // -> y = q . blockdiag(A_sa) of layer it+1
