@@ -9,7 +9,8 @@
 // reduction (reference transformer.py:111,117) -- is exchanged through DISTRIBUTED SHARED MEMORY: each CTA leaves its
 // partial (column max, column sum, 8 diagonal 16x16 blocks of E^T V) in its own shared memory, signals the peers'
 // mbarriers (release.cluster), and every CTA pulls the nt partials with ld.shared::cluster and merges them (online
-// softmax rescaling) straight into its block-diagonal B-operand image.  No global memory, no atomics, no polling.
+// softmax rescaling) straight into its compact head-block B-operand image (bdc_offset).  Clips of more than four tiles exchange
+// through L2 instead (kGx), two-tile clips push instead of pull (kPush).
 #pragma once
 #include "tile_kernels.cuh"
 
@@ -796,7 +797,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 //   P = E^T V as 8 MN-major MMAs over the tile's tokens ; column sums by a column scan of the E image
                 //   (same rounded values as the MMA sees).
                 // The partial (max, sum, diagonal 16x16 blocks of P) stays in this CTA's shared memory (over Y); every CTA
-                // of the cluster pulls all nt partials and merges them into its own block-diagonal B-operand image (X).
+                // of the cluster pulls all nt partials and merges them into its own compact head-block B-operand image (X).
                 float* pm = reinterpret_cast<float*>(xchg);            // [8 rg][128] exchange (max, then sums); xchg is idle here
                 float* msm = red;                                      // [128] maxima
                 float* ssm = msm + 128;                                // [128] sums
@@ -980,9 +981,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) clip_kernel(const __grid_cons
                 //      the compact head-block image over the dead E image: nothing to clear)
                 cp_async_wait_all();
                 if (!kGx && nt > 1 && tx == 0) mbar_wait_acq_cluster(smem_u32(&bars->part_ready[seq & 1u]), (seq >> 1) & 1u);
-                named_bar_sync(5, kRowThreads);                            // peers' partials visible, buffer cleared
+                named_bar_sync(5, kRowThreads);                            // peers' partials visible
                 tl.mark(125);
-                // ---- merge the nt partials (online-softmax rescaling, four tiles per round trip) into the block-diagonal
+                // ---- merge the nt partials (online-softmax rescaling, four tiles per round trip) into the compact head-block
                 //      B-operand image.
                 if constexpr (kGx) {
                     gx_merge<kBf16>(a.gx_part + ((size_t)clip * 2 + (seq & 1u)) * nt * kKvPartFloats,
