@@ -98,6 +98,7 @@ constexpr int kClipRedFloats = 128 + 128 + 8;   // column maxima, column sums (t
 constexpr uint32_t kRingAItems = 26;    // ring-A items per layer: 3 x 8 FiLM stages + Wk + Wv
 constexpr int kMaxClipTiles = 16;       // cluster size limit (non-portable); T <= 16 * 128
 constexpr int kDirectMergeTiles = 4;    // up to this cluster size every CTA pulls every partial; beyond: reduce-scatter + all-gather
+constexpr int kGxMinTiles = 7;          // from this many tiles per clip on: independent CTAs, exchange through L2 (StepArgs::gx)
 
 struct ClipBarriers : LayerBarriers {
     uint64_t part_ready[2];             // peers -> this CTA: "my partial of reduction seq is in my shared memory" (count nt - 1)

@@ -1032,10 +1032,12 @@ int dc_prepare_cond(dc_handle* h, const float* xf_proj, const float* xf_out, con
         const char* pe = getenv("DC_PERSIST");
         const int nt = (T + kTileRows - 1) / kTileRows;
         bool persist = nt <= kMaxClipTiles && !h->use_pair && !(pe && pe[0] == '0');
-        // Clusters of more than 4 CTAs leave SMs idle (measured: 15 resident clusters of 8, 7 of 15 or 16 -- 120 / 105 of 148
-        // SMs): those clips run as independent CTAs that exchange their partials through L2.  DC_GX=0 / 1 forces the choice.
+        // Large clusters leave SMs idle (measured: 15 resident clusters of 8, 7 of 15 or 16 -- 120 / 105 of 148 SMs): clips of 7 tiles and
+        // more run as independent CTAs that exchange their partials through L2.  Measured crossover (tools/exchange_crossover.py, motion-s/s
+        // cluster vs L2): 5 tiles 52.7 k vs 51.0 k, 6 tiles 52.1 k vs 50.0 k, 7 tiles 44.5 k vs 57.3 k, 8 tiles 47.3 k vs 54.0 k.
+        // DC_GX=0 / 1 forces the choice.
         const char* gxe = getenv("DC_GX");
-        const bool gx = persist && nt > 1 && (gxe ? gxe[0] == '1' : nt > kDirectMergeTiles);
+        const bool gx = persist && nt > 1 && (gxe ? gxe[0] == '1' : nt >= kGxMinTiles);
         if (gx && ((size_t)B * nt > h->gx_cap || (size_t)B > h->gx_cap_b)) {
             if (h->gx_part) cudaFree(h->gx_part);
             if (h->gx_slice) cudaFree(h->gx_slice);
