@@ -325,8 +325,8 @@ int init_kernel_attrs(dc_handle* h) {
     {   // music-encoder convolutions: opt in to their shared memory; resident CTAs per SM = min over shared memory (227 KB, 1 KB
         // reserved per CTA), registers and 4 x 128 TMEM columns -- the persistent grids are sized to exactly that
         const void* fn[4] = {(const void*)conv_tc_kernel<16, 16, 1, 128, kMeR128>, (const void*)conv_tc_kernel<16, 32, 2, 64, kMeR64>,
-                             (const void*)conv_tc_kernel<32, 32, 1, 64, kMeR64>, (const void*)conv_tc_kernel<32, 32, 1, 32, kMeR32>};
-        const int sm[4] = {me_smem_bytes<16, 16, 1, 128, kMeR128>(), me_smem_bytes<16, 32, 2, 64, kMeR64>(), me_smem_bytes<32, 32, 1, 64, kMeR64>(),
+                             (const void*)conv_tc_kernel<32, 32, 1, 64, kMeR64b>, (const void*)conv_tc_kernel<32, 32, 1, 32, kMeR32>};
+        const int sm[4] = {me_smem_bytes<16, 16, 1, 128, kMeR128>(), me_smem_bytes<16, 32, 2, 64, kMeR64>(), me_smem_bytes<32, 32, 1, 64, kMeR64b>(),
                            me_smem_bytes<32, 32, 1, 32, kMeR32>()};
         for (int i = 0; i < 4; ++i) {
             DC_CUDA(h, cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, sm[i]));
@@ -928,7 +928,7 @@ int dc_finalize_weights(dc_handle* h) {
                 for (int q = 0; q < 16; ++q) h->me_c10.w[t * 16 + q] = wf[(size_t)q * 9 + t];
             for (int q = 0; q < 16; ++q) h->me_c10.b[q] = bf_[q];
         }
-        // tensor-core layers: per tap one [COUT x 64] B block of (hi, lo)-split weights, row = [w_hi | w_lo] (A rows: [a_hi | a_lo])
+        // tensor-core layers: per window row one B block of (hi, lo)-split weights, see music_encoder_tc.cuh
         auto hi_of = [](float v) {
             const uint16_t u = to16(v, true);
             uint32_t w32 = (uint32_t)u << 16;
@@ -944,22 +944,24 @@ int dc_finalize_weights(dc_handle* h) {
             std::vector<float> wf, bf_, w1f, b1f;
             if (folded(li, wf, bf_, res ? &w1f : nullptr, res ? &b1f : nullptr)) return DC_ERR_INVALID;
             h->me_woff[li - 1] = wimg.size();
-            auto add_block = [&](const std::vector<float>& m) {          // m: [co][64]
+            // one block per window row dy: rows dxb * co + c = [w_hi (ci) | w_lo (ci)] of tap (dy, dxb); rows 3 co + c: 1x1 residual (centre row)
+            const int wrows = (res ? 4 : 3) * co;
+            for (int dy = 0; dy < 3; ++dy) {
+                std::vector<float> m1((size_t)wrows * 64, 0.f);
+                auto put = [&](int row, int i, float wv) {
+                    const float whi = hi_of(wv);
+                    m1[(size_t)row * 64 + i] = whi, m1[(size_t)row * 64 + ci + i] = wv - whi;
+                };
+                for (int dxb = 0; dxb < 3; ++dxb)
+                    for (int o = 0; o < co; ++o)
+                        for (int i = 0; i < ci; ++i) put(dxb * co + o, i, wf[((size_t)o * ci + i) * 9 + dy * 3 + dxb]);
+                if (res && dy == 1)
+                    for (int o = 0; o < co; ++o)
+                        for (int i = 0; i < ci; ++i) put(3 * co + o, i, w1f[(size_t)o * ci + i]);
                 const size_t off = wimg.size();
-                wimg.resize(off + (size_t)co * 128);
-                pack_image(wimg.data() + off, m.data(), 64, 64, nullptr, nullptr, co, 1, true);
-            };
-            auto tap_blocks = [&](auto&& weight_at /* (o, i) -> folded weight */) {          // one block per tap: row = [w_hi (ci) | w_lo (ci)]
-                std::vector<float> m1((size_t)co * 64, 0.f);
-                for (int o = 0; o < co; ++o)
-                    for (int i = 0; i < ci; ++i) {
-                        const float wv = weight_at(o, i), whi = hi_of(wv);
-                        m1[o * 64 + i] = whi, m1[o * 64 + ci + i] = wv - whi;
-                    }
-                add_block(m1);
-            };
-            for (int t = 0; t < 9; ++t) tap_blocks([&](int o, int i) { return wf[((size_t)o * ci + i) * 9 + t]; });
-            if (res) tap_blocks([&](int o, int i) { return w1f[(size_t)o * ci + i]; });
+                wimg.resize(off + (size_t)wrows * 128);
+                pack_image(wimg.data() + off, m1.data(), 64, 64, nullptr, nullptr, wrows, 1, true);
+            }
             for (int o = 0; o < co; ++o) biases[(li - 1) * 64 + o] = bf_[o];
             if (res)
                 for (int o = 0; o < co; ++o) biases[(li - 1) * 64 + co + o] = b1f[o];
@@ -1359,9 +1361,9 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 30);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<16, 32, 2, 64, kMeR64>, me_smem_bytes<16, 32, 2, 64, kMeR64>(), h->me_occ[1], kMeR64, p1, p0, H, nb, 3);
-        conv(conv_tc_kernel<32, 32, 1, 64, kMeR64>, me_smem_bytes<32, 32, 1, 64, kMeR64>(), h->me_occ[2], kMeR64, p0, p1, H, nb, 4);
+        conv(conv_tc_kernel<32, 32, 1, 64, kMeR64b>, me_smem_bytes<32, 32, 1, 64, kMeR64b>(), h->me_occ[2], kMeR64b, p0, p1, H, nb, 4);
         Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
-        pool(maxpool_split_kernel<32, 5, 5, 3, 2, 2, 2>, p1, p0, H, W, Ho, Wo, nb, 4, 1);
+        maxpool_split_simple_kernel<32, 5, 5, 3, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p1, p0, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p0, p1, H, nb, 5);
         conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p1, p0, H, nb, 6);

@@ -75,47 +75,58 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
 // shared memory, one 128-byte row per pixel ([hi | lo], 16-byte chunk c of staged row s stored at c ^ (s & 7)).  The tcgen05
 // SWIZZLE_128B pattern is a function of the shared-memory ADDRESS bits (checked on the GPU with tools/experiments/desc_shift.cu:
 // a K-major descriptor whose start is 128- but not 1024-byte aligned reads exactly the rows it points at, with base_offset 0), so
-// the A operand of tap (dy, dx) is simply the SAME strip read through a descriptor shifted by dy (W + 2) + dx rows: no im2col
-// copy exists anywhere.  Output pixel (yl, x) is accumulator row o = yl (W + 2) + x of the band; the two columns x >= W of every
-// image row are junk rows that the epilogue skips (1.5 - 6 % of the MMA work).
+// the A operand of window row dy is simply the SAME strip read through a descriptor shifted by dy (W + 2) rows: no im2col copy
+// exists anywhere.
+// An M = 128 MMA costs the same 64+ cycles for N = 16 as for N = 128, so the three taps of a window row are ONE MMA with
+// N = 3 C_out: accumulator row i (staged pixel s_i) gets E_i[dx] = sum_dy pix(s_i + dy (W + 2)) . W[dy][dx] for dx = -1, 0, +1 side
+// by side, and the output of pixel s is E(s - 1)[-1] + E(s)[0] + E(s + 1)[+1]: the horizontal shift happens on the OUTPUT side, in
+// the epilogue, with two warp shuffles per value (lanes 0 / 127 of a tile are its halo: tiles advance by 126 rows; the lanes at
+// warp boundaries go through 1 KB of shared memory).  9 (C_in = 16) or 18 (C_in = 32) MMAs per 126 pixels instead of 27 / 54.
+// The two columns x >= W of every image row are junk rows that the epilogue skips.
 // image rows per band for the 128-, 64- and 32-bin feature maps: sized so that two CTAs fit an SM (one stages while the other's MMAs run)
-constexpr int kMeR128 = 2, kMeR64 = 3, kMeR32 = 15;
+constexpr int kMeR128 = 2, kMeR64 = 3, kMeR64b = 5, kMeR32 = 14;   // (kMeR64b: conv2.1, whose smaller weight block leaves room for a longer strip)
 constexpr int kMeThreads = 288;           // 8 row warps (staging; two threads per accumulator row in the epilogue) + 1 MMA warp
+constexpr int kMeTile = kTileRows - 2;    // finished pixels per accumulator tile
 struct MeBarriers {
     uint64_t staged;                      // rows -> MMA: the strip of this band is in shared memory (8 warp arrivals)
     uint64_t acc_full[2], acc_free[2];    // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (8 warp arrivals)
     uint32_t tmem_base;
 };
 template <int W, int R>
-__host__ __device__ constexpr int me_mtiles() { return (R * (W + 2) + kTileRows - 1) / kTileRows; }
+__host__ __device__ constexpr int me_mtiles() { return (R * (W + 2) + kMeTile - 1) / kMeTile; }
 template <int W, int R>
-__host__ __device__ constexpr int me_strip_rows() { return ((me_mtiles<W, R>() * kTileRows + 2 * (W + 2) + 3 + 7) / 8) * 8; }
+__host__ __device__ constexpr int me_strip_rows() { return ((me_mtiles<W, R>() * kMeTile + 2 * (W + 2) + 4 + 7) / 8) * 8; }
+template <int COUT, int RES>
+__host__ __device__ constexpr int me_wrows() { return (RES == 2 ? 4 : 3) * COUT; }          // B rows per window row: [dx = -1 | 0 | +1 (| 1x1 residual)]
 template <int CIN, int COUT, int RES, int W, int R>
 constexpr int me_smem_bytes() {
-    return me_strip_rows<W, R>() * 128 + (9 + (RES == 2 ? 1 : 0)) * COUT * 128 + 2 * COUT * 4 + (int)sizeof(MeBarriers) + 1024;
+    return me_strip_rows<W, R>() * 128 + 3 * me_wrows<COUT, RES>() * 128 + 2 * COUT * 4 + 2 * 2 * 4 * 2 * (COUT / 2) * 4 + (int)sizeof(MeBarriers) + 1024;
 }
 
-// x [B][H][W][CIN hi | CIN lo], y [B][H][W][COUT hi | COUT lo].  wimg: one block per tap (+ one for the 1x1 residual convolution),
-// COUT rows x 128 B, K-major SW128, row = [w_hi (CIN) | w_lo (CIN)];  a . w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo is three (CIN = 16)
-// or six (CIN = 32) K = 16 MMAs per tap, each picking its own 32-byte K chunk of the A and of the B rows.
-// bias [COUT] (+ [COUT] of the 1x1 residual when RES == 2).  RES: 1 = identity residual, 2 = 1x1 convolution + BatchNorm.
+// x [B][H][W][CIN hi | CIN lo], y [B][H][W][COUT hi | COUT lo].  wimg: one block per window row dy, me_wrows() rows x 128 B, K-major
+// SW128, row dxb * COUT + c = [w_hi (CIN) | w_lo (CIN)] of tap (dy, dxb) (rows 3 COUT + c: the 1x1 residual convolution, centre row
+// only); a . w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo is three (CIN = 16) or six (CIN = 32) K = 16 MMAs per window row, each picking
+// its own 32-byte K chunk of the A and of the B rows.  bias [COUT] (+ [COUT] of the 1x1 residual when RES == 2).
+// RES: 1 = identity residual, 2 = 1x1 convolution + BatchNorm.
 template <int CIN, int COUT, int RES, int W, int R>
 __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int bands_per_clip,
                                                             int n_jobs, const uint8_t* __restrict__ wimg, const float* __restrict__ bias) {
     static_assert((CIN == 16 || CIN == 32) && (COUT == 16 || COUT == 32) && (RES == 1 || RES == 2), "unsupported shape");
     static_assert(RES == 2 || CIN == COUT, "identity residual needs CIN == COUT");
     constexpr int P = W + 2, NM = me_mtiles<W, R>(), SROWS = me_strip_rows<W, R>();
-    constexpr int NBLK = 9 + (RES == 2 ? 1 : 0), BLK = COUT * 128;
-    constexpr int NCH = CIN / 4;                               // 16-byte chunks of a split pixel: NCH / 2 hi, NCH / 2 lo
+    constexpr int WROWS = me_wrows<COUT, RES>(), BLK = WROWS * 128;
+    constexpr int NCH = CIN / 4;                               // 16-byte chunks of a split pixel: NCH / 2 hi, then NCH / 2 lo
     constexpr int KH = CIN / 16;                               // K = 16 chunks of the hi (and of the lo) half
+    constexpr int HC = COUT / 2;                               // output channels per epilogue thread
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* strip = smem;                                     // SROWS x 128 B
-    uint8_t* wsm = strip + SROWS * 128;                        // NBLK x [COUT x 128 B]   (SROWS % 8 == 0: 1024-aligned)
-    float* bsm = reinterpret_cast<float*>(wsm + NBLK * BLK);   // [2 * COUT]
-    MeBarriers* bars = reinterpret_cast<MeBarriers*>(bsm + 2 * COUT);
+    uint8_t* wsm = strip + SROWS * 128;                        // 3 x [WROWS x 128 B]   (SROWS % 8 == 0: 1024-aligned)
+    float* bsm = reinterpret_cast<float*>(wsm + 3 * BLK);      // [2 * COUT]
+    float* xch = bsm + 2 * COUT;                               // [2 tile parity][2 side][4 quarter][2 half][HC] lanes at the warp boundaries
+    MeBarriers* bars = reinterpret_cast<MeBarriers*>(xch + 2 * 2 * 4 * 2 * HC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < NBLK * BLK / 16; i += kMeThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+    for (int i = tid; i < 3 * BLK / 16; i += kMeThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
     for (int i = tid; i < SROWS * 8; i += kMeThreads) reinterpret_cast<uint4*>(strip)[i] = make_uint4(0, 0, 0, 0);   // junk rows must stay finite
     if (tid < (RES == 2 ? 2 : 1) * COUT) bsm[tid] = __ldg(bias + tid);
     if (tid == 0) {
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
         mbar_fence_init();
     }
     if (warp == 8) {
-        tmem_alloc(smem_u32(&bars->tmem_base), 128);
+        tmem_alloc(smem_u32(&bars->tmem_base), 256);
         tmem_relinquish();
     }
     fence_async_smem();
@@ -136,30 +147,30 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
 
     if (warp == 8) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc<true>(kTileRows, COUT);
+            const uint32_t idesc3 = make_idesc<true>(kTileRows, 3 * COUT), idesc4 = make_idesc<true>(kTileRows, WROWS);
             const uint32_t sbase = smem_u32(strip);
             uint32_t mc = 0;                                    // accumulator tiles issued so far
             for (int j = 0; j < my_jobs; ++j) {
                 mbar_wait(smem_u32(&bars->staged), (uint32_t)j & 1u);
                 tc_fence_after();
                 for (int m = 0; m < NM; ++m, ++mc) {
-                    const uint32_t acc = mc & 1u, dcol = tmem_base + acc * 64u;
+                    const uint32_t acc = mc & 1u, dcol = tmem_base + acc * 128u;
                     mbar_wait(smem_u32(&bars->acc_free[acc]), ((mc >> 1) & 1u) ^ 1u);
                     tc_fence_after();
+                    // lane i of this tile <-> output candidate o = kMeTile m + i - 1, centre pixel = staged row o + P + 2.  The centre
+                    // window row goes first: with RES == 2 it is the one MMA group that also writes the residual columns.
 #pragma unroll
-                    for (int tap = 0; tap < NBLK; ++tap) {
-                        const int dy = tap < 9 ? tap / 3 - 1 : 0, dx = tap < 9 ? tap % 3 - 1 : 0;
-                        // staged row of the tap's pixel for accumulator row 0 of this tile: o + 2 + (1 + dy) P + dx
-                        const uint64_t ad = make_desc_kmajor_sw128(sbase + (uint32_t)(m * kTileRows + 2 + (1 + dy) * P + dx) * 128u);
-                        const uint64_t bd = make_desc_kmajor_sw128(smem_u32(wsm + tap * BLK));
-                        const uint32_t d = (RES == 2 && tap == 9) ? dcol + 32u : dcol;
-                        const bool first = tap == 0 || tap == 9;
+                    for (int q = 0; q < 3; ++q) {
+                        const int dy = q == 0 ? 0 : (q == 1 ? -1 : 1);
+                        const uint64_t ad = make_desc_kmajor_sw128(sbase + (uint32_t)(m * kMeTile + 1 + (1 + dy) * P) * 128u);
+                        const uint64_t bd = make_desc_kmajor_sw128(smem_u32(wsm + (dy + 1) * BLK));
+                        const uint32_t idesc = dy == 0 ? idesc4 : idesc3;
 #pragma unroll
-                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * k, bd + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);          // a_hi . w_hi
+                        for (int k = 0; k < KH; ++k) umma_f16(dcol, ad + 2 * k, bd + 2 * k, idesc, (q > 0 || k > 0) ? 1u : 0u);            // a_hi . w_hi
 #pragma unroll
-                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * (KH + k), bd + 2 * k, idesc, 1u);                               // a_lo . w_hi
+                        for (int k = 0; k < KH; ++k) umma_f16(dcol, ad + 2 * (KH + k), bd + 2 * k, idesc, 1u);                              // a_lo . w_hi
 #pragma unroll
-                        for (int k = 0; k < KH; ++k) umma_f16(d, ad + 2 * k, bd + 2 * (KH + k), idesc, 1u);                               // a_hi . w_lo
+                        for (int k = 0; k < KH; ++k) umma_f16(dcol, ad + 2 * k, bd + 2 * (KH + k), idesc, 1u);                              // a_hi . w_lo
                     }
                     umma_commit(smem_u32(&bars->acc_full[acc]));
                 }
@@ -167,9 +178,8 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
         }
     } else {
         // epilogue: warp w and w + 4 share the TMEM lanes 32 (w % 4) ..; `half` selects which half of the output channels
-        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
-        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        constexpr int HC = COUT / 2;
+        const int qw = warp & 3, half = warp >> 2, r = qw * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
         uint32_t mc = 0;
         for (int j = 0; j < my_jobs; ++j) {
             const int job = (int)blockIdx.x + j * (int)gridDim.x;
@@ -177,54 +187,71 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
             const uint16_t* xc = x + (size_t)clip * H * W * (2 * CIN);
             // ---- stage the (R + 2) x P pixels of the band: coalesced 16-byte chunks, reflect halo by index arithmetic
             {
-                // thread -> fixed 16-byte chunk ch of the pixels sp = tid / NCH, + 256 / NCH, ...: (row, column) of the staged pixel
-                // advance incrementally (no divisions); U loads are in flight per thread (one L2 round trip per batch)
-                constexpr int NPIX = (R + 2) * P, D = 256 / NCH, U = 6;
+                // thread -> fixed 16-byte chunk ch of the pixels sp = tid / NCH, + 256 / NCH, ...; cp.async holds no registers per copy, so
+                // every chunk of the band is in flight at once (one memory latency per band)
+                constexpr int NPIX = (R + 2) * P, D = 256 / NCH;
                 const int ch = tid % NCH;
                 int sp = tid / NCH, ys = sp / P, xs = sp - ys * P;
                 while (sp < NPIX) {
-                    uint4 v[U];
-                    uint32_t dst[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (sp < NPIX) {
-                            const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
-                            v[u] = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);
-                            dst[u] = sw128_offset((uint32_t)(1 + sp), (uint32_t)ch);      // hi chunks first, lo chunks right behind
-                        } else {
-                            dst[u] = 0xFFFFFFFFu;
-                        }
-                        sp += D, xs += D;
-                        while (xs >= P) xs -= P, ++ys;
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (dst[u] != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(strip + dst[u]) = v[u];
+                    const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
+                    cp_async16(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)ch),
+                               reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);   // hi chunks first, lo chunks right behind
+                    sp += D, xs += D;
+                    while (xs >= P) xs -= P, ++ys;
                 }
+                cp_async_wait_all();
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->staged));
             for (int m = 0; m < NM; ++m, ++mc) {
                 const uint32_t acc = mc & 1u;
-                const int o = m * kTileRows + r, yl = o / P, xx = o - yl * P;
-                const bool valid = xx < W && yl < R && y0 + yl < H;
+                const int o = m * kMeTile + r - 1, yl = o >= 0 ? o / P : 0, xx = o - yl * P;
+                const bool valid = r >= 1 && r <= kMeTile && xx < W && yl < R && y0 + yl < H;
                 mbar_wait(smem_u32(&bars->acc_full[acc]), (mc >> 1) & 1u);
                 tc_fence_after();
-                float v[HC], v2[RES == 2 ? HC : 1];
-                if (HC == 16) tmem_ld16(trow + acc * 64u + half * HC, v);
-                else tmem_ld8(trow + acc * 64u + half * HC, v);
-                if (RES == 2) {
-                    if (HC == 16) tmem_ld16(trow + acc * 64u + 32u + half * HC, v2);
-                    else tmem_ld8(trow + acc * 64u + 32u + half * HC, v2);
+                float el[HC], ec[HC], er[HC], v2[RES == 2 ? HC : 1];      // E[dx = -1], E[0], E[+1] of THIS row
+                if (HC == 16) {
+                    tmem_ld16(trow + acc * 128u + half * HC, el), tmem_ld16(trow + acc * 128u + COUT + half * HC, ec);
+                    tmem_ld16(trow + acc * 128u + 2 * COUT + half * HC, er);
+                    if (RES == 2) tmem_ld16(trow + acc * 128u + 3 * COUT + half * HC, v2);
+                } else {
+                    tmem_ld8(trow + acc * 128u + half * HC, el), tmem_ld8(trow + acc * 128u + COUT + half * HC, ec);
+                    tmem_ld8(trow + acc * 128u + 2 * COUT + half * HC, er);
+                    if (RES == 2) tmem_ld8(trow + acc * 128u + 3 * COUT + half * HC, v2);
                 }
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free[acc]));
+                // ---- horizontal shift on the output side: out(i) = E(i - 1)[-1] + E(i)[0] + E(i + 1)[+1]
+                float* xa = xch + (((size_t)(acc * 2 + 0) * 4 + qw) * 2 + half) * HC;     // lane 31's E[-1] of this quarter (for lane 0 of the next)
+                float* xb = xch + (((size_t)(acc * 2 + 1) * 4 + qw) * 2 + half) * HC;     // lane 0's E[+1] of this quarter (for lane 31 of the previous)
+                if (lane == 31) {
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) xa[c] = el[c];
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) xb[c] = er[c];
+                }
+                named_bar_sync(2, 256);
+#pragma unroll
+                for (int c = 0; c < HC; ++c) {                     // interior lanes: two shuffles per value, selects instead of branches
+                    const float sl = __shfl_up_sync(0xFFFFFFFFu, el[c], 1), sr = __shfl_down_sync(0xFFFFFFFFu, er[c], 1);
+                    ec[c] += (lane == 0 ? 0.f : sl) + (lane == 31 ? 0.f : sr);
+                }
+                if (lane == 0 && qw > 0) {                         // the two lanes at a warp boundary: ONE divergent block per tile each
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) ec[c] += xa[c - 2 * HC];                     // quarter qw - 1, same half: HC * 2 floats back
+                }
+                if (lane == 31 && qw < 3) {
+#pragma unroll
+                    for (int c = 0; c < HC; ++c) ec[c] += xb[c + 2 * HC];
+                }
                 if (valid) {
 #pragma unroll
-                    for (int cidx = 0; cidx < HC; ++cidx) v[cidx] = fmaxf(v[cidx] + bsm[half * HC + cidx], 0.f);
+                    for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] = fmaxf(ec[cidx] + bsm[half * HC + cidx], 0.f);
                     if (RES == 1) {                              // + x (identity): the centre pixel is staged row o + 2 + P
                         const uint32_t srow = (uint32_t)(o + 2 + P);
 #pragma unroll
@@ -234,17 +261,17 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
                             float xr[8];
                             me_join8(xh, xl, xr);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[8 * g8 + e] += xr[e];
+                            for (int e = 0; e < 8; ++e) ec[8 * g8 + e] += xr[e];
                         }
                     } else {
 #pragma unroll
-                        for (int cidx = 0; cidx < HC; ++cidx) v[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
+                        for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
                     }
                     uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + y0 + yl) * W + xx) * (2 * COUT));
 #pragma unroll
                     for (int g8 = 0; g8 < HC / 8; ++g8) {
                         uint4 hi, lo;
-                        me_split8(v + 8 * g8, hi, lo);
+                        me_split8(ec + 8 * g8, hi, lo);
                         dst[half * (HC / 8) + g8] = hi, dst[COUT / 8 + half * (HC / 8) + g8] = lo;
                     }
                 }
@@ -257,7 +284,7 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -327,6 +354,42 @@ __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __re
         uint4* dst = reinterpret_cast<uint4*>(yc + ((size_t)ho * Wo + wo) * (2 * C));
         dst[g] = hi, dst[G + g] = lo;
     }
+}
+
+// one thread per (output pixel, 8 channels), no row reuse: better when the window stride is close to the window (the stride-3 pool)
+template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
+__global__ void __launch_bounds__(256) maxpool_split_simple_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
+                                                                  long n_items) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_items) return;
+    constexpr int G = C / 8;
+    const int g = (int)(i % G);
+    const long op = i / G;
+    const int wo = (int)(op % Wo), ho = (int)((op / Wo) % Ho);
+    const long clip = op / ((long)Wo * Ho);
+    const uint16_t* xc = x + (size_t)clip * H * W * (2 * C);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+        const int h = ho * SH - PH + kh;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+            const int w_ = wo * SW - PW + kw;
+            if (w_ < 0 || w_ >= W) continue;
+            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            float v[8];
+            me_join8(__ldg(p + g), __ldg(p + G + g), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+        }
+    }
+    uint4 hi, lo;
+    me_split8(m, hi, lo);
+    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)op * (2 * C));
+    dst[g] = hi, dst[G + g] = lo;
 }
 
 // h3 [B][T][16 bins][32 hi | 32 lo] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded
