@@ -324,10 +324,10 @@ int init_kernel_attrs(dc_handle* h) {
     DC_CUDA(h, cudaFuncSetAttribute(layer_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLayerSmemBytes));
     {   // music-encoder convolutions: opt in to their shared memory; resident CTAs per SM = min over shared memory (227 KB, 1 KB
         // reserved per CTA), registers and 4 x 128 TMEM columns -- the persistent grids are sized to exactly that
-        const void* fn[4] = {(const void*)conv_tc_kernel<16, 16, 1, 128, kMeR128>, (const void*)conv_tc_kernel<16, 32, 2, 64, kMeR64>,
-                             (const void*)conv_tc_kernel<32, 32, 1, 64, kMeR64b>, (const void*)conv_tc_kernel<32, 32, 1, 32, kMeR32>};
-        const int sm[4] = {me_smem_bytes<16, 16, 1, 128, kMeR128>(), me_smem_bytes<16, 32, 2, 64, kMeR64>(), me_smem_bytes<32, 32, 1, 64, kMeR64b>(),
-                           me_smem_bytes<32, 32, 1, 32, kMeR32>()};
+        const void* fn[4] = {(const void*)conv_tc_kernel<16, 16, 1, 128, kMeNM128>, (const void*)conv_tc_kernel<16, 32, 2, 64, kMeNM64>,
+                             (const void*)conv_tc_kernel<32, 32, 1, 64, kMeNM64b>, (const void*)conv_tc_kernel<32, 32, 1, 32, kMeNM32>};
+        const int sm[4] = {me_smem_bytes<16, 16, 1, 128, kMeNM128>(), me_smem_bytes<16, 32, 2, 64, kMeNM64>(), me_smem_bytes<32, 32, 1, 64, kMeNM64b>(),
+                           me_smem_bytes<32, 32, 1, 32, kMeNM32>()};
         for (int i = 0; i < 4; ++i) {
             DC_CUDA(h, cudaFuncSetAttribute(fn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, sm[i]));
             cudaFuncAttributes fa{};
@@ -1337,8 +1337,8 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         h->me_cap = (size_t)chunk * per_clip;
     }
     uint16_t *p0 = reinterpret_cast<uint16_t*>(h->me_buf0), *p1 = reinterpret_cast<uint16_t*>(h->me_buf1);   // split pixels [C hi | C lo]
-    auto conv = [&](auto kern, int smem, int occ, int R, const uint16_t* src, uint16_t* dst, int H, int nb, int li) {
-        const int bands = (H + R - 1) / R, jobs = bands * nb;
+    auto conv = [&](auto kern, int smem, int occ, int NM, int W, const uint16_t* src, uint16_t* dst, int H, int nb, int li) {
+        const int bands = (H * (W + 2) + NM * kMeTile - 1) / (NM * kMeTile), jobs = bands * nb;   // bands of NM accumulator tiles each
         kern<<<(unsigned)std::min(jobs, h->num_sms * occ), kMeThreads, smem, st>>>(src, dst, H, bands, jobs, h->me_wimg + h->me_woff[li - 1],
                                                                                    h->me_bias + (li - 1) * 64);
     };
@@ -1355,18 +1355,18 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
         int H = Tm, W = kBins, Ho, Wo;
         conv10_split_kernel<<<dim3(blocks256((long)H * W), (unsigned)nb), 256, 0, st>>>(m0, p0, H, W, h->me_c10);
-        conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p0, p1, H, nb, 1);
-        conv(conv_tc_kernel<16, 16, 1, 128, kMeR128>, me_smem_bytes<16, 16, 1, 128, kMeR128>(), h->me_occ[0], kMeR128, p1, p0, H, nb, 2);
+        conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p0, p1, H, nb, 1);
+        conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
         pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 30);
         H = Ho, W = Wo;
-        conv(conv_tc_kernel<16, 32, 2, 64, kMeR64>, me_smem_bytes<16, 32, 2, 64, kMeR64>(), h->me_occ[1], kMeR64, p1, p0, H, nb, 3);
-        conv(conv_tc_kernel<32, 32, 1, 64, kMeR64b>, me_smem_bytes<32, 32, 1, 64, kMeR64b>(), h->me_occ[2], kMeR64b, p0, p1, H, nb, 4);
+        conv(conv_tc_kernel<16, 32, 2, 64, kMeNM64>, me_smem_bytes<16, 32, 2, 64, kMeNM64>(), h->me_occ[1], kMeNM64, W, p1, p0, H, nb, 3);
+        conv(conv_tc_kernel<32, 32, 1, 64, kMeNM64b>, me_smem_bytes<32, 32, 1, 64, kMeNM64b>(), h->me_occ[2], kMeNM64b, W, p0, p1, H, nb, 4);
         Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
         maxpool_split_simple_kernel<32, 5, 5, 3, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p1, p0, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
         H = Ho, W = Wo;
-        conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p0, p1, H, nb, 5);
-        conv(conv_tc_kernel<32, 32, 1, 32, kMeR32>, me_smem_bytes<32, 32, 1, 32, kMeR32>(), h->me_occ[3], kMeR32, p1, p0, H, nb, 6);
+        conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p0, p1, H, nb, 5);
+        conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p1, p0, H, nb, 6);
         Ho = (H + 2 - 3) / 1 + 1, Wo = (W + 2 - 3) / 2 + 1;           // MaxPool2d((3,3), stride (1,2), padding 1)
         pool(maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1>, p0, p1, H, W, Ho, Wo, nb, 4, 6);
         H = Ho, W = Wo;                                               // (nb, T, 16, 32 split)
@@ -1375,6 +1375,19 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv4_proj_split_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
                                                                                          xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, M);
         h->launches += 11;
+#ifdef DC_ME_TIMELINE
+        if (getenv("DC_ME_TIMELINE")) {                               // debug build only (tools/experiments/me_tl_report.py)
+            static unsigned long long tl[4 * 1024];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(tl, me_tl, sizeof(tl));
+            for (int k = 0; k < 4; ++k) {
+                fprintf(stderr, "[me_tl] kernel %d\n", k);
+                unsigned long long t0 = tl[k * 1024] & 0xFFFFFFFFFFFFFFull;
+                for (int i = 0; i < 160 && tl[k * 1024 + i]; ++i)
+                    fprintf(stderr, "  %d %llu\n", (int)(tl[k * 1024 + i] >> 56), (tl[k * 1024 + i] & 0xFFFFFFFFFFFFFFull) - t0);
+            }
+        }
+#endif
     }
     DC_CUDA(h, cudaGetLastError());
     return 0;

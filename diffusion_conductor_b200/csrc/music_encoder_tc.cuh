@@ -83,24 +83,34 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
 // the epilogue, with two warp shuffles per value (lanes 0 / 127 of a tile are its halo: tiles advance by 126 rows; the lanes at
 // warp boundaries go through 1 KB of shared memory).  9 (C_in = 16) or 18 (C_in = 32) MMAs per 126 pixels instead of 27 / 54.
 // The two columns x >= W of every image row are junk rows that the epilogue skips.
-// image rows per band for the 128-, 64- and 32-bin feature maps: sized so that two CTAs fit an SM (one stages while the other's MMAs run)
-constexpr int kMeR128 = 2, kMeR64 = 3, kMeR64b = 5, kMeR32 = 14;   // (kMeR64b: conv2.1, whose smaller weight block leaves room for a longer strip)
-constexpr int kMeThreads = 288;           // 8 row warps (staging; two threads per accumulator row in the epilogue) + 1 MMA warp
+// One CTA per SM, three roles: 4 producer warps stage band j + 1 into the second strip while the MMA warp issues band j (four
+// accumulator tiles in TMEM, so it runs ahead) and two sets of 8 row warps finish alternate tiles.  Measured alternatives:
+// two thin CTAs per SM that stage and finish their own bands (1.44 ms), 8 producer warps (1.38 ms), sleeping waits (1.33 ms).
+constexpr int kMeNM128 = 4, kMeNM64 = 4, kMeNM64b = 4, kMeNM32 = 4;   // accumulator tiles per band (two strips of that length + the weight blocks fit 227 KB)
+constexpr int kMeRowWarps = 16;           // two sets of 8 epilogue warps (two threads per accumulator row), each finishing every other tile
+constexpr int kMeProducerWarps = 4;       // cp.async staging of the next band
+constexpr int kMeThreads = 32 * (kMeRowWarps + kMeProducerWarps + 1);   // + 1 MMA warp
+constexpr int kMeAcc = 4;                 // accumulator tiles in TMEM (128 columns each)
 constexpr int kMeTile = kTileRows - 2;    // finished pixels per accumulator tile
+#ifdef DC_ME_TIMELINE
+__device__ unsigned long long me_tl[4 * 1024];       // debug build only: clock64 stamps of CTA 0, thread 0 (tools/experiments)
+#define ME_TL(slot) do { if (tl_on && tl_n < 1024) me_tl[tl_base + tl_n++] = ((unsigned long long)(slot) << 56) | (clock64() & 0xFFFFFFFFFFFFFFull); } while (0)
+#else
+#define ME_TL(slot) do { } while (0)
+#endif
 struct MeBarriers {
-    uint64_t staged;                      // rows -> MMA: the strip of this band is in shared memory (8 warp arrivals)
-    uint64_t acc_full[2], acc_free[2];    // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (8 warp arrivals)
+    uint64_t staged[2];                   // producers -> MMA: the strip holds the band (one arrival per producer warp)
+    uint64_t strip_free[2];               // rows -> producers: every residual read of the strip is done (one arrival per row warp)
+    uint64_t acc_full[kMeAcc], acc_free[kMeAcc];   // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (the 8 warps of the owning set)
     uint32_t tmem_base;
 };
-template <int W, int R>
-__host__ __device__ constexpr int me_mtiles() { return (R * (W + 2) + kMeTile - 1) / kMeTile; }
-template <int W, int R>
-__host__ __device__ constexpr int me_strip_rows() { return ((me_mtiles<W, R>() * kMeTile + 2 * (W + 2) + 4 + 7) / 8) * 8; }
+template <int W, int NM>
+__host__ __device__ constexpr int me_strip_rows() { return ((NM * kMeTile + 2 * (W + 2) + 4 + 7) / 8) * 8; }
 template <int COUT, int RES>
 __host__ __device__ constexpr int me_wrows() { return (RES == 2 ? 4 : 3) * COUT; }          // B rows per window row: [dx = -1 | 0 | +1 (| 1x1 residual)]
-template <int CIN, int COUT, int RES, int W, int R>
+template <int CIN, int COUT, int RES, int W, int NM>
 constexpr int me_smem_bytes() {
-    return me_strip_rows<W, R>() * 128 + 3 * me_wrows<COUT, RES>() * 128 + 2 * COUT * 4 + 2 * 2 * 4 * 2 * (COUT / 2) * 4 + (int)sizeof(MeBarriers) + 1024;
+    return 2 * me_strip_rows<W, NM>() * 128 + 3 * me_wrows<COUT, RES>() * 128 + 2 * COUT * 4 + 2 * 2 * 2 * 4 * 2 * (COUT / 2) * 4 + (int)sizeof(MeBarriers) + 1024;
 }
 
 // x [B][H][W][CIN hi | CIN lo], y [B][H][W][COUT hi | COUT lo].  wimg: one block per window row dy, me_wrows() rows x 128 B, K-major
@@ -108,34 +118,34 @@ constexpr int me_smem_bytes() {
 // only); a . w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo is three (CIN = 16) or six (CIN = 32) K = 16 MMAs per window row, each picking
 // its own 32-byte K chunk of the A and of the B rows.  bias [COUT] (+ [COUT] of the 1x1 residual when RES == 2).
 // RES: 1 = identity residual, 2 = 1x1 convolution + BatchNorm.
-template <int CIN, int COUT, int RES, int W, int R>
-__global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int bands_per_clip,
-                                                            int n_jobs, const uint8_t* __restrict__ wimg, const float* __restrict__ bias) {
+template <int CIN, int COUT, int RES, int W, int NM>
+__global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int bands_per_clip,
+                                                               int n_jobs, const uint8_t* __restrict__ wimg, const float* __restrict__ bias) {
     static_assert((CIN == 16 || CIN == 32) && (COUT == 16 || COUT == 32) && (RES == 1 || RES == 2), "unsupported shape");
     static_assert(RES == 2 || CIN == COUT, "identity residual needs CIN == COUT");
-    constexpr int P = W + 2, NM = me_mtiles<W, R>(), SROWS = me_strip_rows<W, R>();
+    constexpr int P = W + 2, SROWS = me_strip_rows<W, NM>();
     constexpr int WROWS = me_wrows<COUT, RES>(), BLK = WROWS * 128;
     constexpr int NCH = CIN / 4;                               // 16-byte chunks of a split pixel: NCH / 2 hi, then NCH / 2 lo
     constexpr int KH = CIN / 16;                               // K = 16 chunks of the hi (and of the lo) half
     constexpr int HC = COUT / 2;                               // output channels per epilogue thread
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* strip = smem;                                     // SROWS x 128 B
-    uint8_t* wsm = strip + SROWS * 128;                        // 3 x [WROWS x 128 B]   (SROWS % 8 == 0: 1024-aligned)
+    uint8_t* strip0 = smem;                                    // 2 x [SROWS x 128 B]: band j lives in strip j & 1
+    uint8_t* wsm = strip0 + 2 * SROWS * 128;                   // 3 x [WROWS x 128 B]   (SROWS % 8 == 0: 1024-aligned)
     float* bsm = reinterpret_cast<float*>(wsm + 3 * BLK);      // [2 * COUT]
-    float* xch = bsm + 2 * COUT;                               // [2 tile parity][2 side][4 quarter][2 half][HC] lanes at the warp boundaries
-    MeBarriers* bars = reinterpret_cast<MeBarriers*>(xch + 2 * 2 * 4 * 2 * HC);
+    float* xch = bsm + 2 * COUT;                               // [2 set][2 tile parity][2 side][4 quarter][2 half][HC] lanes at the warp boundaries
+    MeBarriers* bars = reinterpret_cast<MeBarriers*>(xch + 2 * 2 * 2 * 4 * 2 * HC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 3 * BLK / 16; i += kMeThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
-    for (int i = tid; i < SROWS * 8; i += kMeThreads) reinterpret_cast<uint4*>(strip)[i] = make_uint4(0, 0, 0, 0);   // junk rows must stay finite
+    for (int i = tid; i < 2 * SROWS * 8; i += kMeThreads) reinterpret_cast<uint4*>(strip0)[i] = make_uint4(0, 0, 0, 0);   // junk rows must stay finite
     if (tid < (RES == 2 ? 2 : 1) * COUT) bsm[tid] = __ldg(bias + tid);
     if (tid == 0) {
-        mbar_init(smem_u32(&bars->staged), 8);
-        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1), mbar_init(smem_u32(&bars->acc_free[i]), 8);
+        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars->staged[i]), kMeProducerWarps), mbar_init(smem_u32(&bars->strip_free[i]), kMeRowWarps);
+        for (int i = 0; i < kMeAcc; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1), mbar_init(smem_u32(&bars->acc_free[i]), kMeRowWarps / 2);
         mbar_fence_init();
     }
-    if (warp == 8) {
-        tmem_alloc(smem_u32(&bars->tmem_base), 256);
+    if (warp == kMeRowWarps + kMeProducerWarps) {
+        tmem_alloc(smem_u32(&bars->tmem_base), kMeAcc * 128);
         tmem_relinquish();
     }
     fence_async_smem();
@@ -144,18 +154,29 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const int my_jobs = n_jobs > (int)blockIdx.x ? (n_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // a band is NM * 126 consecutive output candidates og = y P + x of the clip's padded-row raster (x >= W: junk), NOT a whole number
+    // of image rows: every tile but a clip's last is full.  All three roles walk the same (band, tile) sequence; tile number mc (counted
+    // over the CTA's whole life) uses accumulator mc % kMeAcc and is finished by row-warp set mc & 1.
+    auto band_of = [&](int j, int& clip, int& og0, int& nm) {
+        const int job = (int)blockIdx.x + j * (int)gridDim.x;
+        clip = job / bands_per_clip, og0 = (job - clip * bands_per_clip) * (NM * kMeTile);
+        nm = min(NM, (H * P - og0 + kMeTile - 1) / kMeTile);
+    };
 
-    if (warp == 8) {
+    if (warp == kMeRowWarps + kMeProducerWarps) {
+        // ================================================================ MMA issuer
         if (lane == 0) {
             const uint32_t idesc3 = make_idesc<true>(kTileRows, 3 * COUT), idesc4 = make_idesc<true>(kTileRows, WROWS);
-            const uint32_t sbase = smem_u32(strip);
-            uint32_t mc = 0;                                    // accumulator tiles issued so far
+            uint32_t mc = 0;
             for (int j = 0; j < my_jobs; ++j) {
-                mbar_wait(smem_u32(&bars->staged), (uint32_t)j & 1u);
+                int clip, og0, nm;
+                band_of(j, clip, og0, nm);
+                const uint32_t sbase = smem_u32(strip0 + (j & 1) * SROWS * 128);
+                mbar_wait(smem_u32(&bars->staged[j & 1]), (uint32_t)(j >> 1) & 1u);
                 tc_fence_after();
-                for (int m = 0; m < NM; ++m, ++mc) {
-                    const uint32_t acc = mc & 1u, dcol = tmem_base + acc * 128u;
-                    mbar_wait(smem_u32(&bars->acc_free[acc]), ((mc >> 1) & 1u) ^ 1u);
+                for (int m = 0; m < nm; ++m, ++mc) {
+                    const uint32_t acc = mc % kMeAcc, dcol = tmem_base + acc * 128u;
+                    mbar_wait(smem_u32(&bars->acc_free[acc]), ((mc / kMeAcc) & 1u) ^ 1u);
                     tc_fence_after();
                     // lane i of this tile <-> output candidate o = kMeTile m + i - 1, centre pixel = staged row o + P + 2.  The centre
                     // window row goes first: with RES == 2 it is the one MMA group that also writes the residual columns.
@@ -176,39 +197,69 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
                 }
             }
         }
-    } else {
-        // epilogue: warp w and w + 4 share the TMEM lanes 32 (w % 4) ..; `half` selects which half of the output channels
-        const int qw = warp & 3, half = warp >> 2, r = qw * 32 + lane;
-        const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
-        uint32_t mc = 0;
+    } else if (warp >= kMeRowWarps) {
+        // ================================================================ producers: stage band j into strip j & 1 while band j - 1 computes
+        const int pt = tid - kMeRowWarps * 32;
+        constexpr int PT = kMeProducerWarps * 32;
         for (int j = 0; j < my_jobs; ++j) {
-            const int job = (int)blockIdx.x + j * (int)gridDim.x;
-            const int clip = job / bands_per_clip, y0 = (job - clip * bands_per_clip) * R;
+            int clip, og0, nm;
+            band_of(j, clip, og0, nm);
+            uint8_t* strip = strip0 + (j & 1) * SROWS * 128;
             const uint16_t* xc = x + (size_t)clip * H * W * (2 * CIN);
-            // ---- stage the (R + 2) x P pixels of the band: coalesced 16-byte chunks, reflect halo by index arithmetic
-            {
-                // thread -> fixed 16-byte chunk ch of the pixels sp = tid / NCH, + 256 / NCH, ...; cp.async holds no registers per copy, so
-                // every chunk of the band is in flight at once (one memory latency per band)
-                constexpr int NPIX = (R + 2) * P, D = 256 / NCH;
-                const int ch = tid % NCH;
-                int sp = tid / NCH, ys = sp / P, xs = sp - ys * P;
-                while (sp < NPIX) {
-                    const int gy = me_reflect(y0 - 1 + ys, H), gx = me_reflect(xs - 1, W);
-                    cp_async16(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)ch),
-                               reinterpret_cast<const uint4*>(xc + ((size_t)gy * W + gx) * (2 * CIN)) + ch);   // hi chunks first, lo chunks right behind
-                    sp += D, xs += D;
-                    while (xs >= P) xs -= P, ++ys;
+            mbar_wait(smem_u32(&bars->strip_free[j & 1]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+            // image row by image row: the source of a row is contiguous, so a thread's chunk q = pt, pt + 128, .. needs one shift and one
+            // swizzle; cp.async holds no registers per copy, so every chunk of the band is in flight at once
+            const int npix = nm * kMeTile + 2 * P + 2;                        // staged pixel sp <-> padded raster index og0 + sp
+            const int ys0 = og0 / P, ys1 = (og0 + npix - 1) / P;
+            constexpr int CPR = W * NCH;                                      // 16-byte chunks of an image row
+            static_assert(CPR % PT == 0, "row chunks must divide over the staging threads");
+            for (int ys = ys0; ys <= ys1; ++ys) {
+                const uint4* srow = reinterpret_cast<const uint4*>(xc + (size_t)me_reflect(ys - 1, H) * W * (2 * CIN));
+                const int spr = ys * P - og0;                                 // staged index of this row's left halo pixel (may be < 0)
+                if (spr + 1 >= 0 && spr + W < npix) {                           // the whole image row is inside the band (all but its first and last)
+#pragma unroll
+                    for (int q = pt; q < CPR; q += PT) cp_async16(strip + sw128_offset((uint32_t)(2 + spr + q / NCH), (uint32_t)(q % NCH)), srow + q);
+                } else {
+#pragma unroll
+                    for (int q = pt; q < CPR; q += PT) {
+                        const int sp = spr + 1 + q / NCH;
+                        if (sp >= 0 && sp < npix) cp_async16(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)(q % NCH)), srow + q);
+                    }
                 }
-                cp_async_wait_all();
+                if (pt < 2 * NCH) {                                           // reflect halo: x = -1 -> 1, x = W -> W - 2
+                    const int side = pt / NCH, ch = pt % NCH, sp = spr + (side ? P - 1 : 0);
+                    if (sp >= 0 && sp < npix) cp_async16(strip + sw128_offset((uint32_t)(1 + sp), (uint32_t)ch), srow + (side ? W - 2 : 1) * NCH + ch);
+                }
             }
+            cp_async_wait_all();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->staged));
-            for (int m = 0; m < NM; ++m, ++mc) {
-                const uint32_t acc = mc & 1u;
-                const int o = m * kMeTile + r - 1, yl = o >= 0 ? o / P : 0, xx = o - yl * P;
-                const bool valid = r >= 1 && r <= kMeTile && xx < W && yl < R && y0 + yl < H;
-                mbar_wait(smem_u32(&bars->acc_full[acc]), (mc >> 1) & 1u);
+            if (lane == 0) mbar_arrive(smem_u32(&bars->staged[j & 1]));
+        }
+    } else {
+        // ================================================================ epilogue: two sets of 8 row warps; in a set, warp w and w + 4 share
+        // the TMEM lanes 32 (w % 4) .. and `half` selects which half of the output channels
+        const int set = warp >> 3, qw = warp & 3, half = (warp >> 2) & 1, r = qw * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
+        uint32_t mc = 0;
+#ifdef DC_ME_TIMELINE
+        const bool tl_on = blockIdx.x == 0 && tid == 0;
+        const int tl_base = (W == 128 ? 0 : (W == 32 ? 3 : (CIN == 16 ? 1 : 2))) * 1024;
+        int tl_n = 0;
+#endif
+        for (int j = 0; j < my_jobs; ++j) {
+            int clip, og0, nm;
+            band_of(j, clip, og0, nm);
+            const uint8_t* strip = strip0 + (j & 1) * SROWS * 128;
+            ME_TL(1);
+            for (int m = 0; m < nm; ++m, ++mc) {
+                if ((int)(mc & 1u) != set) continue;
+                const uint32_t acc = mc % kMeAcc, par = (mc >> 1) & 1u;
+                const int o = m * kMeTile + r - 1, og = max(og0 + o, 0), yy = og / P, xx = og - yy * P;
+                const bool valid = r >= 1 && r <= kMeTile && xx < W && yy < H;
+                ME_TL(4);
+                mbar_wait(smem_u32(&bars->acc_full[acc]), (mc / kMeAcc) & 1u);
+                ME_TL(5);
                 tc_fence_after();
                 float el[HC], ec[HC], er[HC], v2[RES == 2 ? HC : 1];      // E[dx = -1], E[0], E[+1] of THIS row
                 if (HC == 16) {
@@ -225,8 +276,8 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free[acc]));
                 // ---- horizontal shift on the output side: out(i) = E(i - 1)[-1] + E(i)[0] + E(i + 1)[+1]
-                float* xa = xch + (((size_t)(acc * 2 + 0) * 4 + qw) * 2 + half) * HC;     // lane 31's E[-1] of this quarter (for lane 0 of the next)
-                float* xb = xch + (((size_t)(acc * 2 + 1) * 4 + qw) * 2 + half) * HC;     // lane 0's E[+1] of this quarter (for lane 31 of the previous)
+                float* xa = xch + ((((size_t)(set * 2 + par) * 2 + 0) * 4 + qw) * 2 + half) * HC;     // lane 31's E[-1] of this quarter (for lane 0 of the next)
+                float* xb = xch + ((((size_t)(set * 2 + par) * 2 + 1) * 4 + qw) * 2 + half) * HC;     // lane 0's E[+1] of this quarter (for lane 31 of the previous)
                 if (lane == 31) {
 #pragma unroll
                     for (int c = 0; c < HC; ++c) xa[c] = el[c];
@@ -235,7 +286,7 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
 #pragma unroll
                     for (int c = 0; c < HC; ++c) xb[c] = er[c];
                 }
-                named_bar_sync(2, 256);
+                named_bar_sync(2 + set, 256);
 #pragma unroll
                 for (int c = 0; c < HC; ++c) {                     // interior lanes: two shuffles per value, selects instead of branches
                     const float sl = __shfl_up_sync(0xFFFFFFFFu, el[c], 1), sr = __shfl_down_sync(0xFFFFFFFFu, er[c], 1);
@@ -267,7 +318,7 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
 #pragma unroll
                         for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + y0 + yl) * W + xx) * (2 * COUT));
+                    uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + yy) * W + xx) * (2 * COUT));
 #pragma unroll
                     for (int g8 = 0; g8 < HC / 8; ++g8) {
                         uint4 hi, lo;
@@ -275,16 +326,20 @@ __global__ void __launch_bounds__(kMeThreads) conv_tc_kernel(const uint16_t* __r
                         dst[half * (HC / 8) + g8] = hi, dst[COUT / 8 + half * (HC / 8) + g8] = lo;
                     }
                 }
+                ME_TL(6);
             }
-            // every MMA of the band has completed (the last acc_full was observed) and every residual read of the strip is done
-            named_bar_sync(1, 256);
+            // this warp's MMAs of the band have completed (their acc_full was observed) and its residual reads of the strip are done;
+            // the OTHER set's tiles are covered by that set's own arrivals
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->strip_free[j & 1]));
+            ME_TL(7);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMeRowWarps + kMeProducerWarps) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, kMeAcc * 128);
     }
 }
 
