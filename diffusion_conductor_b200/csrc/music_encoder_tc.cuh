@@ -18,6 +18,12 @@ __device__ __forceinline__ int me_reflect(int i, int n) {      // padding_mode='
     if (i >= n) i = 2 * n - 2 - i;
     return min(max(i, 0), n - 1);
 }
+// one 256-bit store (sm_100: STG.256): a full 32-byte sector per thread instead of two half-sector writes
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 // 8 fp32 -> hi chunk, lo chunk (8 bf16 each)
 __device__ __forceinline__ void me_split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
@@ -67,7 +73,8 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
     me_split8(acc, hi0, lo0);
     me_split8(acc + 8, hi1, lo1);
     uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)blockIdx.y * H * W + q) * 32);
-    dst[0] = hi0, dst[1] = hi1, dst[2] = lo0, dst[3] = lo1;
+    st_global_v8(dst, hi0, hi1);
+    st_global_v8(dst + 2, lo0, lo1);
 }
 
 // ---------------------------------------------------------------- 3x3 convolutions, 16 / 32 channels, tcgen05
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
 // accumulator tiles in TMEM, so it runs ahead) and two sets of 8 row warps finish alternate tiles.  Measured alternatives:
 // two thin CTAs per SM that stage and finish their own bands (1.44 ms), 8 producer warps (1.38 ms), sleeping waits (1.33 ms).
 constexpr int kMeNM128 = 4, kMeNM64 = 4, kMeNM64b = 4, kMeNM32 = 4;   // accumulator tiles per band (two strips of that length + the weight blocks fit 227 KB)
-constexpr int kMeRowWarps = 16;           // two sets of 8 epilogue warps (two threads per accumulator row), each finishing every other tile
+constexpr int kMeRowWarps = 16;           // epilogue warps: sets of 4 (C_out = 16) or 8 (C_out = 32: two threads per accumulator row); set s finishes tiles s, s + SETS, ..
 constexpr int kMeProducerWarps = 4;       // cp.async staging of the next band
 constexpr int kMeThreads = 32 * (kMeRowWarps + kMeProducerWarps + 1);   // + 1 MMA warp
 constexpr int kMeAcc = 4;                 // accumulator tiles in TMEM (128 columns each)
@@ -110,7 +117,7 @@ template <int COUT, int RES>
 __host__ __device__ constexpr int me_wrows() { return (RES == 2 ? 4 : 3) * COUT; }          // B rows per window row: [dx = -1 | 0 | +1 (| 1x1 residual)]
 template <int CIN, int COUT, int RES, int W, int NM>
 constexpr int me_smem_bytes() {
-    return 2 * me_strip_rows<W, NM>() * 128 + 3 * me_wrows<COUT, RES>() * 128 + 2 * COUT * 4 + 2 * 2 * 2 * 4 * 2 * (COUT / 2) * 4 + (int)sizeof(MeBarriers) + 1024;
+    return 2 * me_strip_rows<W, NM>() * 128 + 3 * me_wrows<COUT, RES>() * 128 + 2 * COUT * 4 + kMeRowWarps * 2 * 2 * 16 * 4 + (int)sizeof(MeBarriers) + 1024;
 }
 
 // x [B][H][W][CIN hi | CIN lo], y [B][H][W][COUT hi | COUT lo].  wimg: one block per window row dy, me_wrows() rows x 128 B, K-major
@@ -127,21 +134,24 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
     constexpr int WROWS = me_wrows<COUT, RES>(), BLK = WROWS * 128;
     constexpr int NCH = CIN / 4;                               // 16-byte chunks of a split pixel: NCH / 2 hi, then NCH / 2 lo
     constexpr int KH = CIN / 16;                               // K = 16 chunks of the hi (and of the lo) half
-    constexpr int HC = COUT / 2;                               // output channels per epilogue thread
+    constexpr int HC = 16;                                     // output channels per epilogue thread (its hi and its lo chunks: 32 bytes each)
+    constexpr int NH = COUT / HC;                              // threads per accumulator row
+    constexpr int SETW = 4 * NH, SETS = kMeRowWarps / SETW;    // warps per epilogue set; sets (each finishes every SETS-th tile)
+    static_assert(kMeAcc % SETS == 0, "an accumulator must always belong to the same set");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* strip0 = smem;                                    // 2 x [SROWS x 128 B]: band j lives in strip j & 1
     uint8_t* wsm = strip0 + 2 * SROWS * 128;                   // 3 x [WROWS x 128 B]   (SROWS % 8 == 0: 1024-aligned)
     float* bsm = reinterpret_cast<float*>(wsm + 3 * BLK);      // [2 * COUT]
-    float* xch = bsm + 2 * COUT;                               // [2 set][2 tile parity][2 side][4 quarter][2 half][HC] lanes at the warp boundaries
-    MeBarriers* bars = reinterpret_cast<MeBarriers*>(xch + 2 * 2 * 2 * 4 * 2 * HC);
+    float* xch = bsm + 2 * COUT;                               // [SETS][2 tile parity][2 side][4 quarter][NH][HC] lanes at the warp boundaries
+    MeBarriers* bars = reinterpret_cast<MeBarriers*>(xch + SETS * 2 * 2 * 4 * NH * HC);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 3 * BLK / 16; i += kMeThreads) reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
     for (int i = tid; i < 2 * SROWS * 8; i += kMeThreads) reinterpret_cast<uint4*>(strip0)[i] = make_uint4(0, 0, 0, 0);   // junk rows must stay finite
     if (tid < (RES == 2 ? 2 : 1) * COUT) bsm[tid] = __ldg(bias + tid);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bars->staged[i]), kMeProducerWarps), mbar_init(smem_u32(&bars->strip_free[i]), kMeRowWarps);
-        for (int i = 0; i < kMeAcc; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1), mbar_init(smem_u32(&bars->acc_free[i]), kMeRowWarps / 2);
+        for (int i = 0; i < kMeAcc; ++i) mbar_init(smem_u32(&bars->acc_full[i]), 1), mbar_init(smem_u32(&bars->acc_free[i]), SETW);
         mbar_fence_init();
     }
     if (warp == kMeRowWarps + kMeProducerWarps) {
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
     const int my_jobs = n_jobs > (int)blockIdx.x ? (n_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     // a band is NM * 126 consecutive output candidates og = y P + x of the clip's padded-row raster (x >= W: junk), NOT a whole number
     // of image rows: every tile but a clip's last is full.  All three roles walk the same (band, tile) sequence; tile number mc (counted
-    // over the CTA's whole life) uses accumulator mc % kMeAcc and is finished by row-warp set mc & 1.
+    // over the CTA's whole life) uses accumulator mc % kMeAcc and is finished by row-warp set mc % SETS.
     auto band_of = [&](int j, int& clip, int& og0, int& nm) {
         const int job = (int)blockIdx.x + j * (int)gridDim.x;
         clip = job / bands_per_clip, og0 = (job - clip * bands_per_clip) * (NM * kMeTile);
@@ -237,9 +247,9 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
             if (lane == 0) mbar_arrive(smem_u32(&bars->staged[j & 1]));
         }
     } else {
-        // ================================================================ epilogue: two sets of 8 row warps; in a set, warp w and w + 4 share
-        // the TMEM lanes 32 (w % 4) .. and `half` selects which half of the output channels
-        const int set = warp >> 3, qw = warp & 3, half = (warp >> 2) & 1, r = qw * 32 + lane;
+        // ================================================================ epilogue: SETS sets of 4 NH row warps; warp w of a set reads the TMEM
+        // lanes 32 (w % 4) .., and with C_out = 32 warps w and w + 4 share them (`half` selects which 16 of the output channels)
+        const int set = warp / SETW, qw = warp & 3, half = (warp >> 2) % NH, r = qw * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
         uint32_t mc = 0;
 #ifdef DC_ME_TIMELINE
@@ -253,8 +263,8 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
             const uint8_t* strip = strip0 + (j & 1) * SROWS * 128;
             ME_TL(1);
             for (int m = 0; m < nm; ++m, ++mc) {
-                if ((int)(mc & 1u) != set) continue;
-                const uint32_t acc = mc % kMeAcc, par = (mc >> 1) & 1u;
+                if ((int)(mc % SETS) != set) continue;
+                const uint32_t acc = mc % kMeAcc, par = (mc / SETS) & 1u;
                 const int o = m * kMeTile + r - 1, og = max(og0 + o, 0), yy = og / P, xx = og - yy * P;
                 const bool valid = r >= 1 && r <= kMeTile && xx < W && yy < H;
                 ME_TL(4);
@@ -262,22 +272,16 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
                 ME_TL(5);
                 tc_fence_after();
                 float el[HC], ec[HC], er[HC], v2[RES == 2 ? HC : 1];      // E[dx = -1], E[0], E[+1] of THIS row
-                if (HC == 16) {
-                    tmem_ld16(trow + acc * 128u + half * HC, el), tmem_ld16(trow + acc * 128u + COUT + half * HC, ec);
-                    tmem_ld16(trow + acc * 128u + 2 * COUT + half * HC, er);
-                    if (RES == 2) tmem_ld16(trow + acc * 128u + 3 * COUT + half * HC, v2);
-                } else {
-                    tmem_ld8(trow + acc * 128u + half * HC, el), tmem_ld8(trow + acc * 128u + COUT + half * HC, ec);
-                    tmem_ld8(trow + acc * 128u + 2 * COUT + half * HC, er);
-                    if (RES == 2) tmem_ld8(trow + acc * 128u + 3 * COUT + half * HC, v2);
-                }
+                tmem_ld16(trow + acc * 128u + half * HC, el), tmem_ld16(trow + acc * 128u + COUT + half * HC, ec);
+                tmem_ld16(trow + acc * 128u + 2 * COUT + half * HC, er);
+                if (RES == 2) tmem_ld16(trow + acc * 128u + 3 * COUT + half * HC, v2);
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free[acc]));
                 // ---- horizontal shift on the output side: out(i) = E(i - 1)[-1] + E(i)[0] + E(i + 1)[+1]
-                float* xa = xch + ((((size_t)(set * 2 + par) * 2 + 0) * 4 + qw) * 2 + half) * HC;     // lane 31's E[-1] of this quarter (for lane 0 of the next)
-                float* xb = xch + ((((size_t)(set * 2 + par) * 2 + 1) * 4 + qw) * 2 + half) * HC;     // lane 0's E[+1] of this quarter (for lane 31 of the previous)
+                float* xa = xch + ((((size_t)(set * 2 + par) * 2 + 0) * 4 + qw) * NH + half) * HC;     // lane 31's E[-1] of this quarter (for lane 0 of the next)
+                float* xb = xch + ((((size_t)(set * 2 + par) * 2 + 1) * 4 + qw) * NH + half) * HC;     // lane 0's E[+1] of this quarter (for lane 31 of the previous)
                 if (lane == 31) {
 #pragma unroll
                     for (int c = 0; c < HC; ++c) xa[c] = el[c];
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
 #pragma unroll
                     for (int c = 0; c < HC; ++c) xb[c] = er[c];
                 }
-                named_bar_sync(2 + set, 256);
+                named_bar_sync(2 + set, 32 * SETW);
 #pragma unroll
                 for (int c = 0; c < HC; ++c) {                     // interior lanes: two shuffles per value, selects instead of branches
                     const float sl = __shfl_up_sync(0xFFFFFFFFu, el[c], 1), sr = __shfl_down_sync(0xFFFFFFFFu, er[c], 1);
@@ -294,11 +298,11 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
                 }
                 if (lane == 0 && qw > 0) {                         // the two lanes at a warp boundary: ONE divergent block per tile each
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) ec[c] += xa[c - 2 * HC];                     // quarter qw - 1, same half: HC * 2 floats back
+                    for (int c = 0; c < HC; ++c) ec[c] += xa[c - NH * HC];                    // quarter qw - 1, same half: NH * HC floats back
                 }
                 if (lane == 31 && qw < 3) {
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) ec[c] += xb[c + 2 * HC];
+                    for (int c = 0; c < HC; ++c) ec[c] += xb[c + NH * HC];
                 }
                 if (valid) {
 #pragma unroll
@@ -319,12 +323,11 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
                         for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
                     }
                     uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + yy) * W + xx) * (2 * COUT));
-#pragma unroll
-                    for (int g8 = 0; g8 < HC / 8; ++g8) {
-                        uint4 hi, lo;
-                        me_split8(ec + 8 * g8, hi, lo);
-                        dst[half * (HC / 8) + g8] = hi, dst[COUT / 8 + half * (HC / 8) + g8] = lo;
-                    }
+                    uint4 hi0, lo0, hi1, lo1;                     // this thread's hi chunks and its lo chunks are 32 contiguous bytes each
+                    me_split8(ec, hi0, lo0);
+                    me_split8(ec + 8, hi1, lo1);
+                    st_global_v8(dst + half * 2, hi0, hi1);
+                    st_global_v8(dst + COUT / 8 + half * 2, lo0, lo1);
                 }
                 ME_TL(6);
             }
