@@ -370,15 +370,23 @@ __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __re
 #pragma unroll
         for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
         if (h < 0 || h >= H) return;
+        // unconditional loads from a clamped column + a select on use: no branch sits between the 2 KW loads, so all of them are in flight
+        // together (with `continue` on the padding columns every load waited for the previous one's branch)
+        uint4 vh[KW], vl[KW];
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+            const int w_ = min(max(wo * SW - PW + kw, 0), W - 1);
+            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            vh[kw] = __ldg(p + g), vl[kw] = __ldg(p + G + g);
+        }
 #pragma unroll
         for (int kw = 0; kw < KW; ++kw) {
             const int w_ = wo * SW - PW + kw;
-            if (w_ < 0 || w_ >= W) continue;
-            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            const bool ok = w_ >= 0 && w_ < W;
             float v[8];
-            me_join8(__ldg(p + g), __ldg(p + G + g), v);
+            me_join8(vh[kw], vl[kw], v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+            for (int e = 0; e < 8; ++e) m[e] = ok ? fmaxf(m[e], v[e]) : m[e];
         }
     };
     // rows of the first window except its last SH rows
@@ -431,17 +439,23 @@ __global__ void __launch_bounds__(256) maxpool_split_simple_kernel(const uint16_
     for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
 #pragma unroll
     for (int kh = 0; kh < KH; ++kh) {
-        const int h = ho * SH - PH + kh;
-        if (h < 0 || h >= H) continue;
+        const int h0 = ho * SH - PH + kh, h = min(max(h0, 0), H - 1);
+        const bool row_ok = h0 >= 0 && h0 < H;
+        uint4 vh[KW], vl[KW];                                    // (as above: clamped loads, all in flight, select on use)
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+            const int w_ = min(max(wo * SW - PW + kw, 0), W - 1);
+            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            vh[kw] = __ldg(p + g), vl[kw] = __ldg(p + G + g);
+        }
 #pragma unroll
         for (int kw = 0; kw < KW; ++kw) {
             const int w_ = wo * SW - PW + kw;
-            if (w_ < 0 || w_ >= W) continue;
-            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
+            const bool ok = row_ok && w_ >= 0 && w_ < W;
             float v[8];
-            me_join8(__ldg(p + g), __ldg(p + G + g), v);
+            me_join8(vh[kw], vl[kw], v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+            for (int e = 0; e < 8; ++e) m[e] = ok ? fmaxf(m[e], v[e]) : m[e];
         }
     }
     uint4 hi, lo;
