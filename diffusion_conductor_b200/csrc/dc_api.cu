@@ -1343,9 +1343,22 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
                                                                                    h->me_bias + (li - 1) * 64);
     };
     auto blocks256 = [](long n) { return (unsigned)((n + 255) / 256); };
-    // output rows per thread of the sliding-window pools: long segments where there are many rows, short ones where the
-    // parallelism is needed (a segment costs KH - SH start-up rows)
-    auto pool = [&](auto kern, const uint16_t* src, uint16_t* dst, int H, int W, int Ho, int Wo, int nb, int groups, int seg) {
+    // output rows per thread of the sliding-window pools.  A segment costs `startup` = KH - SH extra input rows, and the grid runs in
+    // waves of num_sms x (resident blocks per SM): pick the segment length that minimises waves x (rows fetched per thread) -- with a
+    // fixed length the C2 batch ran 1.11 waves, i.e. a second wave at 11 % occupancy.
+    auto pool = [&](auto kern, const uint16_t* src, uint16_t* dst, int H, int W, int Ho, int Wo, int nb, int groups, int startup) {
+        int regs = 64;
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, (const void*)kern) == cudaSuccess) regs = fa.numRegs;
+        const long per_wave = (long)h->num_sms * std::max(1, std::min(16, 65536 / (((regs + 7) & ~7) * 128)));
+        int seg = Ho;
+        double best = 1e30;
+        for (int c = 4; c <= std::min(Ho, 96); ++c) {
+            const long blocks = ((long)nb * ((Ho + c - 1) / c) * Wo * groups + 127) / 128;
+            const double cost = (double)((blocks + per_wave - 1) / per_wave) * (c + startup);
+            if (cost < best) best = cost, seg = c;
+        }
+        if (getenv("DC_POOL_SEG")) seg = std::max(1, atoi(getenv("DC_POOL_SEG")));
         const int nseg = (Ho + seg - 1) / seg;
         const long items = (long)nb * nseg * Wo * groups;
         kern<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(src, dst, H, W, Ho, Wo, seg, nseg, items);
@@ -1358,7 +1371,7 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p0, p1, H, nb, 1);
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
-        pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 30);
+        pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 4);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<16, 32, 2, 64, kMeNM64>, me_smem_bytes<16, 32, 2, 64, kMeNM64>(), h->me_occ[1], kMeNM64, W, p1, p0, H, nb, 3);
         conv(conv_tc_kernel<32, 32, 1, 64, kMeNM64b>, me_smem_bytes<32, 32, 1, 64, kMeNM64b>(), h->me_occ[2], kMeNM64b, W, p0, p1, H, nb, 4);
@@ -1368,7 +1381,7 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p0, p1, H, nb, 5);
         conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p1, p0, H, nb, 6);
         Ho = (H + 2 - 3) / 1 + 1, Wo = (W + 2 - 3) / 2 + 1;           // MaxPool2d((3,3), stride (1,2), padding 1)
-        pool(maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1>, p0, p1, H, W, Ho, Wo, nb, 4, 6);
+        pool(maxpool_split_kernel<32, 3, 3, 1, 2, 1, 1>, p0, p1, H, W, Ho, Wo, nb, 4, 2);
         H = Ho, W = Wo;                                               // (nb, T, 16, 32 split)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;
