@@ -227,8 +227,13 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
                 const uint4* srow = reinterpret_cast<const uint4*>(xc + (size_t)me_reflect(ys - 1, H) * W * (2 * CIN));
                 const int spr = ys * P - og0;                                 // staged index of this row's left halo pixel (may be < 0)
                 if (spr + 1 >= 0 && spr + W < npix) {                           // the whole image row is inside the band (all but its first and last)
+                    // chunk q = pt + k PT lands PT / NCH strip rows (a multiple of 8) below chunk pt: same swizzle phase, so one
+                    // offset per image row and thread, then a constant stride
+                    static_assert((PT / NCH) % 8 == 0, "swizzle phase must repeat");
+                    uint8_t* d0 = strip + sw128_offset((uint32_t)(2 + spr + pt / NCH), (uint32_t)(pt % NCH));
+                    const uint4* s0 = srow + pt;
 #pragma unroll
-                    for (int q = pt; q < CPR; q += PT) cp_async16(strip + sw128_offset((uint32_t)(2 + spr + q / NCH), (uint32_t)(q % NCH)), srow + q);
+                    for (int k = 0; k < CPR / PT; ++k) cp_async16(d0 + k * (PT / NCH) * 128, s0 + k * PT);
                 } else {
 #pragma unroll
                     for (int q = pt; q < CPR; q += PT) {
