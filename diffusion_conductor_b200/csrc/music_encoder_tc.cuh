@@ -60,19 +60,26 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
     if (q >= (long)H * W) return;
     const int yy = (int)(q / W), xx = (int)(q % W);
     const float* mb = mel + (size_t)blockIdx.y * H * W;
-    float acc[16];
+    // two output channels per FFMA2 (fma.rn.f32x2: the same IEEE fma per lane, half the issue slots of this math-bound kernel)
+    uint64_t acc2[8];
+    const uint64_t* w2 = reinterpret_cast<const uint64_t*>(cw.w);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = cw.b[c];
+    for (int c = 0; c < 8; ++c) acc2[c] = reinterpret_cast<const uint64_t*>(cw.b)[c];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
             const float v = __ldg(mb + (size_t)me_reflect(yy + dy - 1, H) * W + me_reflect(xx + dx - 1, W));
+            const uint64_t vv = pk2(v, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, cw.w[(dy * 3 + dx) * 16 + c], acc[c]);
+            for (int c = 0; c < 8; ++c) acc2[c] = ffma2(vv, w2[(dy * 3 + dx) * 8 + c], acc2[c]);
         }
+    float acc[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    for (int c = 0; c < 8; ++c) {
+        upk2(acc2[c], acc[2 * c], acc[2 * c + 1]);
+        acc[2 * c] = fmaxf(acc[2 * c], 0.f), acc[2 * c + 1] = fmaxf(acc[2 * c + 1], 0.f);
+    }
     uint4 hi0, lo0, hi1, lo1;
     me_split8(acc, hi0, lo0);
     me_split8(acc + 8, hi1, lo1);
@@ -479,8 +486,8 @@ constexpr int kC4Rows = 16;
 __global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* __restrict__ h3, const float* __restrict__ w4t, const float* __restrict__ b4,
                                                               const float* __restrict__ wpt, const float* __restrict__ bp, float* __restrict__ xf_out,
                                                               float* __restrict__ xf_proj, long M) {
-    __shared__ float s_f[kC4Rows][512 + 4];
-    __shared__ float s_o[kC4Rows][64];
+    __shared__ __align__(16) float s_f[kC4Rows][512 + 4];
+    __shared__ __align__(16) float s_o[kC4Rows][64];
     const long row0 = (long)blockIdx.x * kC4Rows;
     const int tid = threadIdx.x;
     for (int i = tid; i < kC4Rows * 16 * 4; i += 256) {         // (row, bin, 8-channel group)
@@ -500,10 +507,15 @@ __global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* _
     float acc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = __ldg(b4 + o);
-    for (int k = 0; k < 512; ++k) {
-        const float wv = __ldg(w4t + k * 64 + o);
+    for (int k = 0; k < 512; k += 4) {                         // four features per 16-byte shared-memory load; k ascending per accumulator
+        float wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(s_f[4 * rq + j][k], wv, acc[j]);
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(w4t + (k + u) * 64 + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 f = *reinterpret_cast<const float4*>(&s_f[4 * rq + j][k]);
+            acc[j] = fmaf(f.x, wv[0], acc[j]), acc[j] = fmaf(f.y, wv[1], acc[j]), acc[j] = fmaf(f.z, wv[2], acc[j]), acc[j] = fmaf(f.w, wv[3], acc[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -513,10 +525,15 @@ __global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* _
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = __ldg(bp + o);
-    for (int k = 0; k < 64; ++k) {
-        const float wv = __ldg(wpt + k * 64 + o);
+    for (int k = 0; k < 64; k += 4) {
+        float wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(s_o[4 * rq + j][k], wv, acc[j]);
+        for (int u = 0; u < 4; ++u) wv[u] = __ldg(wpt + (k + u) * 64 + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 f = *reinterpret_cast<const float4*>(&s_o[4 * rq + j][k]);
+            acc[j] = fmaf(f.x, wv[0], acc[j]), acc[j] = fmaf(f.y, wv[1], acc[j]), acc[j] = fmaf(f.z, wv[2], acc[j]), acc[j] = fmaf(f.w, wv[3], acc[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
