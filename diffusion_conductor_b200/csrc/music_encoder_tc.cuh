@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* _
     float acc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = __ldg(b4 + o);
+#pragma unroll 4
     for (int k = 0; k < 512; k += 4) {                         // four features per 16-byte shared-memory load; k ascending per accumulator
         float wv[4];
 #pragma unroll
