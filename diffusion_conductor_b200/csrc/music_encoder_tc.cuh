@@ -307,43 +307,67 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
                     for (int c = 0; c < HC; ++c) xb[c] = er[c];
                 }
                 named_bar_sync(2 + set, 32 * SETW);
+                // (from here on two channels per instruction: add.rn.f32x2 / fma.rn.f32x2 round each lane exactly like FADD / FFMA)
+                uint64_t e2[HC / 2];
 #pragma unroll
-                for (int c = 0; c < HC; ++c) {                     // interior lanes: two shuffles per value, selects instead of branches
-                    const float sl = __shfl_up_sync(0xFFFFFFFFu, el[c], 1), sr = __shfl_down_sync(0xFFFFFFFFu, er[c], 1);
-                    ec[c] += (lane == 0 ? 0.f : sl) + (lane == 31 ? 0.f : sr);
+                for (int p2 = 0; p2 < HC / 2; ++p2) {              // interior lanes: two shuffles per value, selects instead of branches
+                    const float sl0 = __shfl_up_sync(0xFFFFFFFFu, el[2 * p2], 1), sl1 = __shfl_up_sync(0xFFFFFFFFu, el[2 * p2 + 1], 1);
+                    const float sr0 = __shfl_down_sync(0xFFFFFFFFu, er[2 * p2], 1), sr1 = __shfl_down_sync(0xFFFFFFFFu, er[2 * p2 + 1], 1);
+                    const uint64_t a2 = pk2(lane == 0 ? 0.f : sl0, lane == 0 ? 0.f : sl1), b2 = pk2(lane == 31 ? 0.f : sr0, lane == 31 ? 0.f : sr1);
+                    e2[p2] = fadd2(pk2(ec[2 * p2], ec[2 * p2 + 1]), fadd2(a2, b2));
                 }
                 if (lane == 0 && qw > 0) {                         // the two lanes at a warp boundary: ONE divergent block per tile each
+                    const uint64_t* xp = reinterpret_cast<const uint64_t*>(xa - NH * HC);     // quarter qw - 1, same half: NH * HC floats back
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) ec[c] += xa[c - NH * HC];                    // quarter qw - 1, same half: NH * HC floats back
+                    for (int p2 = 0; p2 < HC / 2; ++p2) e2[p2] = fadd2(e2[p2], xp[p2]);
                 }
                 if (lane == 31 && qw < 3) {
+                    const uint64_t* xp = reinterpret_cast<const uint64_t*>(xb + NH * HC);
 #pragma unroll
-                    for (int c = 0; c < HC; ++c) ec[c] += xb[c + NH * HC];
+                    for (int p2 = 0; p2 < HC / 2; ++p2) e2[p2] = fadd2(e2[p2], xp[p2]);
                 }
                 if (valid) {
+                    const uint64_t* b2 = reinterpret_cast<const uint64_t*>(bsm + half * HC);
 #pragma unroll
-                    for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] = fmaxf(ec[cidx] + bsm[half * HC + cidx], 0.f);
+                    for (int p2 = 0; p2 < HC / 2; ++p2) {          // + bias, ReLU
+                        float a, b;
+                        upk2(fadd2(e2[p2], b2[p2]), a, b);
+                        e2[p2] = pk2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                    }
                     if (RES == 1) {                              // + x (identity): the centre pixel is staged row o + 2 + P
                         const uint32_t srow = (uint32_t)(o + 2 + P);
 #pragma unroll
                         for (int g8 = 0; g8 < HC / 8; ++g8) {
                             const uint4 xh = *reinterpret_cast<const uint4*>(strip + sw128_offset(srow, (uint32_t)(half * (HC / 8) + g8)));
                             const uint4 xl = *reinterpret_cast<const uint4*>(strip + sw128_offset(srow, (uint32_t)(2 * KH + half * (HC / 8) + g8)));
-                            float xr[8];
-                            me_join8(xh, xl, xr);
+                            const uint32_t hw[4] = {xh.x, xh.y, xh.z, xh.w}, lw[4] = {xl.x, xl.y, xl.z, xl.w};
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) ec[8 * g8 + e] += xr[e];
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 a = unpack2<true>(hw[i]), b = unpack2<true>(lw[i]);
+                                e2[4 * g8 + i] = fadd2(e2[4 * g8 + i], fadd2(pk2(a.x, a.y), pk2(b.x, b.y)));
+                            }
                         }
                     } else {
+                        const uint64_t* r2 = reinterpret_cast<const uint64_t*>(bsm + COUT + half * HC);
 #pragma unroll
-                        for (int cidx = 0; cidx < HC; ++cidx) ec[cidx] += v2[cidx] + bsm[COUT + half * HC + cidx];
+                        for (int p2 = 0; p2 < HC / 2; ++p2) e2[p2] = fadd2(e2[p2], fadd2(pk2(v2[2 * p2], v2[2 * p2 + 1]), r2[p2]));
+                    }
+                    // re-split: hi = bf16(v), lo = bf16(v - hi) (v - hi as fma(hi, -1, v): exact product, one rounding, = the subtraction)
+                    uint32_t hw[HC / 2], lw[HC / 2];
+                    const uint64_t m1 = pk2(-1.f, -1.f);
+#pragma unroll
+                    for (int p2 = 0; p2 < HC / 2; ++p2) {
+                        float a, b;
+                        upk2(e2[p2], a, b);
+                        hw[p2] = pack2<true>(a, b);
+                        const float2 f = unpack2<true>(hw[p2]);
+                        upk2(ffma2(pk2(f.x, f.y), m1, e2[p2]), a, b);
+                        lw[p2] = pack2<true>(a, b);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(y + (((size_t)clip * H + yy) * W + xx) * (2 * COUT));
-                    uint4 hi0, lo0, hi1, lo1;                     // this thread's hi chunks and its lo chunks are 32 contiguous bytes each
-                    me_split8(ec, hi0, lo0);
-                    me_split8(ec + 8, hi1, lo1);
-                    st_global_v8(dst + half * 2, hi0, hi1);
-                    st_global_v8(dst + COUT / 8 + half * 2, lo0, lo1);
+                    // this thread's hi chunks and its lo chunks are 32 contiguous bytes each
+                    st_global_v8(dst + half * 2, make_uint4(hw[0], hw[1], hw[2], hw[3]), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+                    st_global_v8(dst + COUT / 8 + half * 2, make_uint4(lw[0], lw[1], lw[2], lw[3]), make_uint4(lw[4], lw[5], lw[6], lw[7]));
                 }
                 ME_TL(6);
             }
