@@ -1363,6 +1363,23 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         const long items = (long)nb * nseg * Wo * groups;
         kern<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(src, dst, H, W, Ho, Wo, seg, nseg, items);
     };
+    // the row-staged pools: one block of 128 threads per (clip, segment of output rows); segment length by the same wave rule
+    auto pool_staged = [&](auto kern, const uint16_t* src, uint16_t* dst, int H, int Ho, int nb, int startup, int sh) {
+        int regs = 64;
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, (const void*)kern) == cudaSuccess) regs = fa.numRegs;
+        const long per_wave = (long)h->num_sms * std::max(1, std::min(6, 65536 / (((regs + 7) & ~7) * 128)));   // (32 KB of shared memory per block: <= 6)
+        int seg = Ho;
+        double best = 1e30;
+        for (int c = 2; c <= std::min(Ho, 96); ++c) {
+            const long blocks = (long)nb * ((Ho + c - 1) / c);
+            const double cost = (double)((blocks + per_wave - 1) / per_wave) * (c * sh + startup);
+            if (cost < best) best = cost, seg = c;
+        }
+        if (getenv("DC_POOL_SEG")) seg = std::max(1, atoi(getenv("DC_POOL_SEG")));
+        const int nseg = (Ho + seg - 1) / seg;
+        kern<<<(unsigned)(nb * nseg), 128, 0, st>>>(src, dst, H, Ho, seg, nseg);
+    };
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
@@ -1371,12 +1388,12 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p0, p1, H, nb, 1);
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
-        pool(maxpool_split_kernel<16, 5, 5, 1, 2, 2, 2>, p0, p1, H, W, Ho, Wo, nb, 2, 4);
+        pool_staged(maxpool_staged_kernel<16, 5, 5, 1, 2, 2, 2, 128>, p0, p1, H, Ho, nb, 4, 1);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<16, 32, 2, 64, kMeNM64>, me_smem_bytes<16, 32, 2, 64, kMeNM64>(), h->me_occ[1], kMeNM64, W, p1, p0, H, nb, 3);
         conv(conv_tc_kernel<32, 32, 1, 64, kMeNM64b>, me_smem_bytes<32, 32, 1, 64, kMeNM64b>(), h->me_occ[2], kMeNM64b, W, p0, p1, H, nb, 4);
         Ho = (H + 4 - 5) / 3 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (3,2), padding 2)
-        maxpool_split_simple_kernel<32, 5, 5, 3, 2, 2, 2><<<blocks256((long)nb * Ho * Wo * 4), 256, 0, st>>>(p1, p0, H, W, Ho, Wo, (long)nb * Ho * Wo * 4);
+        pool_staged(maxpool_staged_kernel<32, 5, 5, 3, 2, 2, 2, 64>, p1, p0, H, Ho, nb, 2, 3);
         H = Ho, W = Wo;
         conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p0, p1, H, nb, 5);
         conv(conv_tc_kernel<32, 32, 1, 32, kMeNM32>, me_smem_bytes<32, 32, 1, 32, kMeNM32>(), h->me_occ[3], kMeNM32, W, p1, p0, H, nb, 6);

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
 // ---------------------------------------------------------------- max-pool on split pixels (torch MaxPool2d, -inf padding)
 // x [B][H][W][C hi | C lo] -> y [B][Ho][Wo][C hi | C lo].  A thread owns 8 channels of one output COLUMN segment and slides down
 // the rows: the maximum over the KW input columns of an input row is computed once and kept in a register ring of KH rows, so an
-// output costs SH x KW pixel loads instead of KH x KW.
+// output costs SH x KW pixel loads instead of KH x KW.  (Used for the small last pool; the two big ones are row-staged, below.)
 template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
 __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
                                                            int seg_rows, int nseg, long n_items) {
@@ -462,46 +462,89 @@ __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __re
     }
 }
 
-// one thread per (output pixel, 8 channels), no row reuse: better when the window stride is close to the window (the stride-3 pool)
-template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
-__global__ void __launch_bounds__(256) maxpool_split_simple_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
-                                                                  long n_items) {
-    const long i = (long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_items) return;
-    constexpr int G = C / 8;
-    const int g = (int)(i % G);
-    const long op = i / G;
-    const int wo = (int)(op % Wo), ho = (int)((op / Wo) % Ho);
-    const long clip = op / ((long)Wo * Ho);
+// Row-staged variant for the two big pools (input rows of 8 KB: 128 px x 16 ch or 64 px x 32 ch).  A block of Wo x C / 8 threads owns
+// a segment of output rows of ONE clip and walks down the input rows: every input row is copied ONCE, contiguously, into a 4-row
+// shared-memory ring with cp.async (one L1 tag per 128-byte line; the per-thread loads above touch every line ~10 times, and the L1
+// tag stage was the bound: l1tex 83 %), three rows ahead of the row being reduced.  16-byte chunk c of a row lives in line c / 8 at
+// position (c % 8) ^ f(line), f chosen so that the 8 lanes of a quarter-warp (C / 8 channel groups x neighbouring output columns,
+// i.e. stride-2 pixels) read 8 different bank groups.  Row maxima go through the same register ring as above.
+template <int C, int KH, int KW, int SH, int SW, int PH, int PW, int W>
+__global__ void __launch_bounds__(((W + 2 * PW - KW) / SW + 1) * (C / 8)) maxpool_staged_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y,
+                                                                                             int H, int Ho, int seg_rows, int nseg) {
+    constexpr int G = C / 8, Wo = (W + 2 * PW - KW) / SW + 1, NT = Wo * G;
+    constexpr int CH = W * 2 * G, CPT = CH / NT, RING = 4;          // 16-byte chunks of an input row; per thread; rows in flight + 1
+    static_assert(CH % NT == 0 && CH * 16 == 8192, "one input row = 8 KB");
+    __shared__ __align__(128) uint4 ring_s[RING][CH];
+    const int tid = threadIdx.x, g = tid % G, wo = tid / G;
+    const int seg = blockIdx.x % nseg;
+    const long clip = blockIdx.x / nseg;
     const uint16_t* xc = x + (size_t)clip * H * W * (2 * C);
-    float m[8];
+    uint16_t* yc = y + (size_t)clip * Ho * Wo * (2 * C);
+    const int ho0 = seg * seg_rows, ho1 = min(ho0 + seg_rows, Ho);
+    auto swz = [](int c) {                                          // chunk index of the row -> swizzled chunk index
+        const int line = c >> 3;
+        return (c & ~7) | ((c & 7) ^ (C == 16 ? 2 * (line & 3) : 4 * ((line >> 1) & 1)));
+    };
+    auto stage = [&](int h) {                                       // (rows outside the image are not staged: their maxima are -inf)
+        if (h >= 0 && h < H) {
+            const uint4* src = reinterpret_cast<const uint4*>(xc + (size_t)h * W * (2 * C));
 #pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+            for (int k = 0; k < CPT; ++k) cp_async16(&ring_s[h & (RING - 1)][swz(tid + k * NT)], src + tid + k * NT);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int hfirst = ho0 * SH - PH, hlast = (ho1 - 1) * SH - PH + KH - 1;
 #pragma unroll
-    for (int kh = 0; kh < KH; ++kh) {
-        const int h0 = ho * SH - PH + kh, h = min(max(h0, 0), H - 1);
-        const bool row_ok = h0 >= 0 && h0 < H;
-        uint4 vh[KW], vl[KW];                                    // (as above: clamped loads, all in flight, select on use)
+    for (int k = 0; k < RING - 1; ++k) stage(hfirst + k);
+    float rmax[KH][8];                                               // row maxima of the last KH input rows (slot pattern unrolled below)
 #pragma unroll
-        for (int kw = 0; kw < KW; ++kw) {
-            const int w_ = min(max(wo * SW - PW + kw, 0), W - 1);
-            const uint4* p = reinterpret_cast<const uint4*>(xc + ((size_t)h * W + w_) * (2 * C));
-            vh[kw] = __ldg(p + g), vl[kw] = __ldg(p + G + g);
+    for (int k = 0; k < KH; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rmax[k][e] = -INFINITY;
+    int slot = 0, ho = ho0, hneed = ho0 * SH - PH + KH - 1;          // next output row and the input row that completes its window
+    for (int h = hfirst; h <= hlast; ++h) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");
+        __syncthreads();                                            // row h has landed for every thread; row h - 1 is no longer read
+        stage(h + RING - 1);                                        // into the slot of row h - 1
+        float m[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+        if (h >= 0 && h < H) {
+            const uint4* row = ring_s[h & (RING - 1)];
+#pragma unroll
+            for (int kw = 0; kw < KW; ++kw) {
+                const int w0 = wo * SW - PW + kw, w_ = min(max(w0, 0), W - 1);
+                const bool ok = w0 >= 0 && w0 < W;
+                float v[8];
+                me_join8(row[swz(w_ * 2 * G + g)], row[swz(w_ * 2 * G + G + g)], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m[e] = ok ? fmaxf(m[e], v[e]) : m[e];
+            }
         }
 #pragma unroll
-        for (int kw = 0; kw < KW; ++kw) {
-            const int w_ = wo * SW - PW + kw;
-            const bool ok = row_ok && w_ >= 0 && w_ < W;
-            float v[8];
-            me_join8(vh[kw], vl[kw], v);
+        for (int s2 = 0; s2 < KH; ++s2)
+            if (s2 == slot) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) m[e] = ok ? fmaxf(m[e], v[e]) : m[e];
+                for (int e = 0; e < 8; ++e) rmax[s2][e] = m[e];
+            }
+        slot = slot + 1 == KH ? 0 : slot + 1;
+        if (h == hneed) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = rmax[0][e];
+#pragma unroll
+                for (int k = 1; k < KH; ++k) t = fmaxf(t, rmax[k][e]);
+                o8[e] = t;
+            }
+            uint4 hi, lo;
+            me_split8(o8, hi, lo);
+            uint4* dst = reinterpret_cast<uint4*>(yc + ((size_t)ho * Wo + wo) * (2 * C));
+            st_global_na_v4(dst + g, hi), st_global_na_v4(dst + G + g, lo);
+            ++ho, hneed += SH;
         }
     }
-    uint4 hi, lo;
-    me_split8(m, hi, lo);
-    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)op * (2 * C));
-    st_global_na_v4(dst + g, hi), st_global_na_v4(dst + G + g, lo);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // h3 [B][T][16 bins][32 hi | 32 lo] -> flatten (feature = channel * 16 + bin, transformer.py:337) -> conv4 (512 -> 64, folded
