@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------- 3x3 convolutions, 16 / 32 channels, tcgen05
-// A CTA takes a BAND of R image rows: the (R + 2) x (W + 2) input pixels (reflect halo resolved while loading) are staged ONCE in
-// shared memory, one 128-byte row per pixel ([hi | lo], 16-byte chunk c of staged row s stored at c ^ (s & 7)).  The tcgen05
+// The output candidates of a clip form the raster og = y (W + 2) + x (x >= W: two junk candidates per padded row, skipped by the
+// epilogue).  A BAND is NM accumulator tiles = NM x 126 consecutive candidates (not a whole number of image rows: every tile but a
+// clip's last is full); the NM x 126 + 2 (W + 2) + 2 input pixels it reads (reflect halo resolved while loading) are staged ONCE in a
+// shared-memory strip, one 128-byte row per pixel ([hi | lo], 16-byte chunk c of staged row s stored at c ^ (s & 7)).  The tcgen05
 // SWIZZLE_128B pattern is a function of the shared-memory ADDRESS bits (checked on the GPU with tools/experiments/desc_shift.cu:
 // a K-major descriptor whose start is 128- but not 1024-byte aligned reads exactly the rows it points at, with base_offset 0), so
 // the A operand of window row dy is simply the SAME strip read through a descriptor shifted by dy (W + 2) rows: no im2col copy
@@ -99,11 +101,10 @@ __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restri
 // N = 3 C_out: accumulator row i (staged pixel s_i) gets E_i[dx] = sum_dy pix(s_i + dy (W + 2)) . W[dy][dx] for dx = -1, 0, +1 side
 // by side, and the output of pixel s is E(s - 1)[-1] + E(s)[0] + E(s + 1)[+1]: the horizontal shift happens on the OUTPUT side, in
 // the epilogue, with two warp shuffles per value (lanes 0 / 127 of a tile are its halo: tiles advance by 126 rows; the lanes at
-// warp boundaries go through 1 KB of shared memory).  9 (C_in = 16) or 18 (C_in = 32) MMAs per 126 pixels instead of 27 / 54.
-// The two columns x >= W of every image row are junk rows that the epilogue skips.
+// warp boundaries go through shared memory).  9 (C_in = 16) or 18 (C_in = 32) MMAs per 126 pixels instead of 27 / 54.
 // One CTA per SM, three roles: 4 producer warps stage band j + 1 into the second strip while the MMA warp issues band j (four
-// accumulator tiles in TMEM, so it runs ahead) and two sets of 8 row warps finish alternate tiles.  Measured alternatives:
-// two thin CTAs per SM that stage and finish their own bands (1.44 ms), 8 producer warps (1.38 ms), sleeping waits (1.33 ms).
+// accumulator tiles in TMEM, so it runs ahead) and 16 row warps in 2 or 4 sets finish the tiles (a row thread owns 16 output channels:
+// its hi chunks and its lo chunks leave as one 256-bit store each).  Measured alternatives: DESIGN.md section 4.5.
 constexpr int kMeNM128 = 4, kMeNM64 = 4, kMeNM64b = 4, kMeNM32 = 4;   // accumulator tiles per band (two strips of that length + the weight blocks fit 227 KB)
 constexpr int kMeRowWarps = 16;           // epilogue warps: sets of 4 (C_out = 16) or 8 (C_out = 32: two threads per accumulator row); set s finishes tiles s, s + SETS, ..
 constexpr int kMeProducerWarps = 4;       // cp.async staging of the next band
@@ -119,7 +120,7 @@ __device__ unsigned long long me_tl[4 * 1024];       // debug build only: clock6
 struct MeBarriers {
     uint64_t staged[2];                   // producers -> MMA: the strip holds the band (one arrival per producer warp)
     uint64_t strip_free[2];               // rows -> producers: every residual read of the strip is done (one arrival per row warp)
-    uint64_t acc_full[kMeAcc], acc_free[kMeAcc];   // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (the 8 warps of the owning set)
+    uint64_t acc_full[kMeAcc], acc_free[kMeAcc];   // accumulators: MMA -> rows (tcgen05.commit), rows -> MMA (the warps of the owning set)
     uint32_t tmem_base;
 };
 template <int W, int NM>
