@@ -1337,10 +1337,14 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         h->me_cap = (size_t)chunk * per_clip;
     }
     uint16_t *p0 = reinterpret_cast<uint16_t*>(h->me_buf0), *p1 = reinterpret_cast<uint16_t*>(h->me_buf1);   // split pixels [C hi | C lo]
+    const bool me_pdl = !(getenv("DC_ME_PDL") && atoi(getenv("DC_ME_PDL")) == 0);
     auto conv = [&](auto kern, int smem, int occ, int NM, int W, const uint16_t* src, uint16_t* dst, int H, int nb, int li) {
         const int bands = (H * (W + 2) + NM * kMeTile - 1) / (NM * kMeTile), jobs = bands * nb;   // bands of NM accumulator tiles each
-        kern<<<(unsigned)std::min(jobs, h->num_sms * occ), kMeThreads, smem, st>>>(src, dst, H, bands, jobs, h->me_wimg + h->me_woff[li - 1],
-                                                                                   h->me_bias + (li - 1) * 64);
+        // programmatic dependent launch: the CTAs of this convolution start on the SMs that the previous kernel's last blocks free, and
+        // run their prologue (weight blocks, strip zero-fill, TMEM allocation, barriers) while its tail drains; the kernel calls
+        // griddepcontrol.wait before it touches an activation
+        launch_k(me_pdl, kern, dim3((unsigned)std::min(jobs, h->num_sms * occ)), dim3(kMeThreads), (size_t)smem, st, src, dst, H, bands, jobs,
+                 (const uint8_t*)(h->me_wimg + h->me_woff[li - 1]), (const float*)(h->me_bias + (li - 1) * 64));
     };
     auto blocks256 = [](long n) { return (unsigned)((n + 255) / 256); };
     // output rows per thread of the sliding-window pools.  A segment costs `startup` = KH - SH extra input rows, and the grid runs in
@@ -1361,7 +1365,7 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         if (getenv("DC_POOL_SEG")) seg = std::max(1, atoi(getenv("DC_POOL_SEG")));
         const int nseg = (Ho + seg - 1) / seg;
         const long items = (long)nb * nseg * Wo * groups;
-        kern<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(src, dst, H, W, Ho, Wo, seg, nseg, items);
+        launch_k(me_pdl, kern, dim3((unsigned)((items + 127) / 128)), dim3(128), (size_t)0, st, src, dst, H, W, Ho, Wo, seg, nseg, items);
     };
     // the row-staged pools: one block of 128 threads per (clip, segment of output rows); segment length by the same wave rule
     auto pool_staged = [&](auto kern, const uint16_t* src, uint16_t* dst, int H, int Ho, int nb, int startup, int sh) {
@@ -1378,13 +1382,13 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         }
         if (getenv("DC_POOL_SEG")) seg = std::max(1, atoi(getenv("DC_POOL_SEG")));
         const int nseg = (Ho + seg - 1) / seg;
-        kern<<<(unsigned)(nb * nseg), 128, 0, st>>>(src, dst, H, Ho, seg, nseg);
+        launch_k(me_pdl, kern, dim3((unsigned)(nb * nseg)), dim3(128), (size_t)0, st, src, dst, H, Ho, seg, nseg);
     };
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const float* m0 = mel + (size_t)b0 * Tm * kBins;              // (nb, 1, Tm, 128)
         int H = Tm, W = kBins, Ho, Wo;
-        conv10_split_kernel<<<dim3(blocks256((long)H * W), (unsigned)nb), 256, 0, st>>>(m0, p0, H, W, h->me_c10);
+        launch_k(me_pdl, conv10_split_kernel, dim3(blocks256((long)H * W), (unsigned)nb), dim3(256), (size_t)0, st, m0, p0, H, W, h->me_c10);
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p0, p1, H, nb, 1);
         conv(conv_tc_kernel<16, 16, 1, 128, kMeNM128>, me_smem_bytes<16, 16, 1, 128, kMeNM128>(), h->me_occ[0], kMeNM128, W, p1, p0, H, nb, 2);
         Ho = (H + 4 - 5) / 1 + 1, Wo = (W + 4 - 5) / 2 + 1;           // MaxPool2d((5,5), stride (1,2), padding 2)
@@ -1402,8 +1406,9 @@ int dc_encode_music(dc_handle* h, const float* mel, float* xf_proj, float* xf_ou
         H = Ho, W = Wo;                                               // (nb, T, 16, 32 split)
         if (H != T || W != 16) return fail(h, DC_ERR_INVALID, "dc_encode_music: unexpected feature map %d x %d", H, W);
         const long M = (long)nb * T;
-        conv4_proj_split_kernel<<<(unsigned)((M + kC4Rows - 1) / kC4Rows), 256, 0, st>>>(p1, h->me_w4t, h->me_b4, h->me_wpt, h->me_bp,
-                                                                                         xf_out + (size_t)b0 * T * kMusic, xf_proj + (size_t)b0 * T * kMusic, M);
+        launch_k(me_pdl, conv4_proj_split_kernel, dim3((unsigned)((M + kC4Rows - 1) / kC4Rows)), dim3(256), (size_t)0, st, (const uint16_t*)p1,
+                 (const float*)h->me_w4t, (const float*)h->me_b4, (const float*)h->me_wpt, (const float*)h->me_bp, xf_out + (size_t)b0 * T * kMusic,
+                 xf_proj + (size_t)b0 * T * kMusic, M);
         h->launches += 11;
 #ifdef DC_ME_TIMELINE
         if (getenv("DC_ME_TIMELINE")) {                               // debug build only (tools/experiments/me_tl_report.py)

@@ -56,6 +56,7 @@ struct alignas(16) Conv10Weights {
 // mel [B][H][W] fp32 -> y [B][H][W][16 hi | 16 lo]; no residual (reference MusicEncoder.conv1[0], residual=False)
 __global__ void __launch_bounds__(256) conv10_split_kernel(const float* __restrict__ mel, uint16_t* __restrict__ y, int H, int W,
                                                           const __grid_constant__ Conv10Weights cw) {
+    pdl_wait();                                                  // (every encoder kernel is launched as a programmatic dependent of the one before it)
     const long q = (long)blockIdx.x * 256 + threadIdx.x;
     if (q >= (long)H * W) return;
     const int yy = (int)(q / W), xx = (int)(q % W);
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                                // (launched as a programmatic dependent: everything above overlapped the previous kernel's tail)
     const uint32_t tmem_base = bars->tmem_base;
     const int my_jobs = n_jobs > (int)blockIdx.x ? (n_jobs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     // a band is NM * 126 consecutive output candidates og = y P + x of the clip's padded-row raster (x >= W: junk), NOT a whole number
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(kMeThreads, 1) conv_tc_kernel(const uint16_t* 
 template <int C, int KH, int KW, int SH, int SW, int PH, int PW>
 __global__ void __launch_bounds__(128) maxpool_split_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int H, int W, int Ho, int Wo,
                                                            int seg_rows, int nseg, long n_items) {
+    pdl_wait();
     const long i = (long)blockIdx.x * 128 + threadIdx.x;
     if (i >= n_items) return;
     constexpr int G = C / 8;
@@ -476,6 +479,7 @@ __global__ void __launch_bounds__(((W + 2 * PW - KW) / SW + 1) * (C / 8)) maxpoo
     constexpr int CH = W * 2 * G, CPT = CH / NT, RING = 4;          // 16-byte chunks of an input row; per thread; rows in flight + 1
     static_assert(CH % NT == 0 && CH * 16 == 8192, "one input row = 8 KB");
     __shared__ __align__(128) uint4 ring_s[RING][CH];
+    pdl_wait();
     const int tid = threadIdx.x, g = tid % G, wo = tid / G;
     const int seg = blockIdx.x % nseg;
     const long clip = blockIdx.x / nseg;
@@ -556,6 +560,7 @@ __global__ void __launch_bounds__(256) conv4_proj_split_kernel(const uint16_t* _
                                                               float* __restrict__ xf_proj, long M) {
     __shared__ __align__(16) float s_f[kC4Rows][512 + 4];
     __shared__ __align__(16) float s_o[kC4Rows][64];
+    pdl_wait();
     const long row0 = (long)blockIdx.x * kC4Rows;
     const int tid = threadIdx.x;
     for (int i = tid; i < kC4Rows * 16 * 4; i += 256) {         // (row, bin, 8-channel group)
