@@ -188,17 +188,20 @@ def conditioning_block(torch, model, diff, eng, synth_inputs, B, T, rank, dev, n
         ev[2].record()
         torch.cuda.synchronize(dev)
         cond = {"encode_music_ms": round(ev[0].elapsed_time(ev[1]), 3), "prepare_cond_ms": round(ev[1].elapsed_time(ev[2]), 3)}
-    t0 = 0.0
-    for it in range(6):
-        if it == 1:                                                                   # iteration 0 is the warm-up
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
+    calls = []
+    for it in range(10):                                                              # iteration 0 is the warm-up; median of the other 9 calls
+        torch.cuda.synchronize(dev)                                                   # (each call ends with a synchronize: per-call times, robust to one-off stalls of the host link)
+        t0 = time.perf_counter()
         fp, fo = model.encode_music(hmel.to(dev, non_blocking=True), dev)            # what generate_music_motion does per rank
         out = diff.ddim_sample_loop(model, (B, T, 26), noise=noise_d, clip_denoised=False,
                                     model_kwargs=dict(xf_proj=fp, xf_out=fo, length=[T] * B))
         hout.copy_(out, non_blocking=True)
         torch.cuda.synchronize(dev)
-    cond["e2e_from_mel_motion_s_per_s"] = round((B * T / 30.0) / ((time.perf_counter() - t0) / 5), 2)
+        if it:
+            calls.append(time.perf_counter() - t0)
+    calls.sort()
+    cond["e2e_from_mel_motion_s_per_s"] = round((B * T / 30.0) / calls[len(calls) // 2], 2)
+    cond["e2e_from_mel_calls"] = len(calls)
     cond["mel_h2d_bytes"] = hmel.numel() * 4
     return cond
 
